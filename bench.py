@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- Delaunay points inserted per second (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload u3_10m|u3_1m|u2_1m|c3_5m|l3_5m|batch_100k]
+    python bench.py --impl reference ...      # the reference's CPU algorithm (oracle/refcpu.cpp port) on the host cores
+
+A step = one full pass of the hot path over one synthetic point set: DelaunayTree::new (bounding sphere + super
+simplex) followed by the insertion of every point (BRIO ordering, then rounds of locate / conflict / reserve /
+retriangulate) on the device.
+  value   points/s with the points already resident in HBM when the timed region starts (CUDA events on the
+          library's stream, max over ranks); N>1 shards independent sets, one per rank (weak scaling, no collective).
+  e2e     the same through the public Python API with HOST buffers: voronoids_b200.delaunay(points) + tree.edges()
+          (H2D of the points and D2H of the canonical edge list inside the timed region).
+  roofline  the attempt kernel (locate + conflict + reservation): algorithmic bytes / its CUDA-event time.
+  cpu_baseline  oracle/refcpu.cpp, the float restatement of kazewong/Voronoids, timed on this box's cores on a bounded
+          sample of the same workload (rank 0, N=1 only).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (dim, kind, n, seed, description)
+    "u3_10m": (3, "uniform", 10_000_000, 0, "3D uniform random 10M points (BASELINE.json configs[2])"),
+    "u3_1m": (3, "uniform", 1_000_000, 0, "3D uniform random 1M points"),
+    "u3_100k": (3, "uniform", 100_000, 0, "3D uniform random 100k points"),
+    "u2_1m": (2, "uniform", 1_000_000, 0, "2D uniform random 1M points (configs[1])"),
+    "c3_5m": (3, "clustered", 5_000_000, 1, "3D Gaussian mixture 5M points (configs[3])"),
+    "l3_5m": (3, "lattice", 5_000_000, 2, "3D jittered lattice 5M points (configs[3])"),
+}
+CPU_SAMPLE = {3: 150_000, 2: 400_000}  # points of the same workload given to the CPU baseline (about 10-30 s)
+
+
+def algorithmic_bytes(dim, K, Cn, W=1.0):
+    """bytes per inserted point, SoA store, u32 ids; E = K + C distinct in-sphere tests."""
+    N, M = dim, dim + 1
+    E = K + Cn
+    attempt = 8 * N + W * (8 * M + 8 * N * M) + E * (4 * M + 8 * N * M) + K * 4 * M
+    retri = Cn * (8 * M) + Cn * 4 + K * 4
+    return attempt, attempt + retri
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled while the timed region runs (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_points(name, rank):
+    from voronoids_b200 import pointgen
+    dim, kind, n, seed, desc = WORKLOADS[name]
+    return pointgen.make(kind, n, dim, seed + 7919 * rank), dim, n, desc
+
+
+def cpu_reference_run(name, steps, warmup, as_arm):
+    """The reference's CPU implementation (port) on a bounded sample of the workload, all host threads."""
+    from oracle import oracle as O
+    dim, kind, n, seed, desc = WORKLOADS[name]
+    ns = min(n, CPU_SAMPLE[dim])
+    from voronoids_b200 import pointgen
+    pts = pointgen.make(kind, n, dim, seed)[:ns] if kind != "uniform" else pointgen.uniform(ns, dim, seed)
+    cores = O.lib().vo_ref_max_threads()
+    times = []
+    reps = (warmup + steps) if as_arm else 1
+    for i in range(reps):
+        t0 = time.perf_counter()
+        r = O.RefDelaunay(pts, mode="delaunay")
+        dt = time.perf_counter() - t0
+        if r.err:
+            raise RuntimeError(f"reference restatement failed with code {r.err} (the Rust original would panic here)")
+        if not as_arm or i >= warmup:
+            times.append(dt)
+        del r
+    t = sum(times) / len(times)
+    sample = (f"first {ns} points of {name} through vo_ref_delaunay (lib.rs:104-125: "
+              f"{min(ns, 100000)} sequential inserts + {max(ns - 100000, 0)} via add_points_to_tree), {cores} OpenMP threads")
+    return {"value": ns / t, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample}, t, ns
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default=os.environ.get("VOR_BENCH_WORKLOAD", "u3_10m"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    name = args.workload
+    dim, kind, n, seed, desc = WORKLOADS[name]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cb, t, ns = cpu_reference_run(name, args.steps, args.warmup, as_arm=True)
+        line = {"impl": "reference", "metric": "delaunay_points_inserted_per_sec", "value": cb["value"], "unit": "points/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc, "points_per_set": n, "dim": dim, "sample_points": ns},
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: voronoids_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import voronoids_b200 as vb
+    from voronoids_b200 import _capi, _lib
+    lib = _lib.lib()
+
+    pts_host, dim, n, desc = make_points(name, rank)
+    pts_dev = torch.from_numpy(pts_host).cuda()
+    stream = torch.cuda.current_stream()
+    sptr = C.c_void_p(stream.cuda_stream)
+
+    def step_device(stats=False):
+        """create + insert with device-resident input on torch's current stream; returns (ms, stats dict)."""
+        lib.vor_set_option(b"stats", 1.0 if stats else 0.0)
+        lib.vor_set_option(b"profile", 1.0 if stats else 0.0)
+        h = _capi.tree_p()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        st = lib.vor_tree_create_device(dim, C.c_void_p(pts_dev.data_ptr()), n, local_rank, sptr, C.byref(h))
+        if st != 0:
+            raise RuntimeError(lib.vor_last_error().decode())
+        st = lib.vor_tree_insert_device(h, C.c_void_p(pts_dev.data_ptr()), n, 1)
+        if st not in (0, 3):
+            raise RuntimeError(lib.vor_last_error().decode())
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        s = (C.c_uint64 * _capi.N_STATS)()
+        lib.vor_tree_stats(h, s)
+        sd = dict(zip(_capi.STAT_NAMES, [int(x) for x in s]))
+        prof = (C.c_double * 8)()
+        lib.vor_tree_profile(h, prof)
+        sd["profile_ms"] = {"attempt": prof[0], "check": prof[1], "retri": prof[2], "setup": prof[3]}
+        sd["profile_launches"] = {"attempt": prof[4], "check": prof[5], "retri": prof[6]}
+        lib.vor_tree_destroy(h)
+        return ms, sd
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then K timed steps (barrier + synchronize on both sides; time = max over ranks)
+    for _ in range(args.warmup):
+        step_device()
+    launches0 = lib.vor_kernel_launches()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_ms = []
+    for _ in range(args.steps):
+        ms, _ = step_device()
+        t_ms.append(ms)
+    barrier()
+    clocks = sampler.stop()
+    launches = (lib.vor_kernel_launches() - launches0) // max(args.steps, 1)
+    tot = torch.tensor([sum(t_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tot.item()) / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # ---- one instrumented step (not timed): W/E/K/C counters and per-kernel CUDA-event times for the roofline
+    ms_prof, sd = step_device(stats=True)
+    K = sd["killed"] / max(sd["winners"], 1)
+    Cn = sd["created"] / max(sd["winners"], 1)
+    b_attempt, b_total = algorithmic_bytes(dim, K, Cn)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    t_attempt = sd["profile_ms"]["attempt"] * 1e-3
+    achieved = (n * b_attempt / t_attempt / 1e9) if t_attempt > 0 else None
+    roofline = {"bound": "hbm", "kernel": "attempt_body (locate + conflict + reservation)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_point_kernel": b_attempt, "algorithmic_bytes_per_point_path": b_total,
+                "kernel_launches": sd["profile_launches"]["attempt"], "kernel_ms_total": sd["profile_ms"]["attempt"],
+                "path_frac": (value / world) * b_total / (peak * 1e9),
+                "counters_per_point": {"W_walk_steps_all_attempts": sd["walk_steps"] / n, "E_tests_all_attempts": sd["tests"] / n,
+                                       "K_killed": K, "C_created": Cn, "attempts_per_point": sd["attempts"] / n,
+                                       "rounds": sd["rounds"], "exact_calls": sd["exact_calls"], "exact_zero": sd["exact_zero"]},
+                "step_ms_by_kernel": sd["profile_ms"]}
+
+    # ---- end to end through the public API with host buffers (H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        def step_e2e():
+            t0 = time.perf_counter()
+            tree = vb.delaunay(pts_host, device=local_rank)
+            e = tree.edges()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            ne = len(e)
+            tree.close()
+            return dt, ne
+        step_e2e()
+        barrier()
+        dts = []
+        for _ in range(max(1, min(args.steps, 3))):
+            dt, ne = step_e2e()
+            dts.append(dt)
+        barrier()
+        te = torch.tensor([sum(dts) / len(dts)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n / float(te.item()), "unit": "points/s", "h2d_bytes_per_step": int(n * dim * 8), "d2h_bytes_per_step": int(ne * 8),
+               "api": "voronoids_b200.delaunay(points) + tree.edges()", "edges": ne}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _, _ = cpu_reference_run(name, 1, 0, as_arm=False)
+
+    if rank == 0:
+        line = {"metric": "delaunay_points_inserted_per_sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc, "points_per_set": n, "dim": dim, "sets": world, "parallelism": f"{world} independent set(s), one per GPU",
+                           "timed_region": "vor_tree_create_device + vor_tree_insert_device, input resident in HBM",
+                           "l2": "inputs larger than L2 (%.0f MB of coordinates, multi-GB store)" % (n * dim * 8 / 1e6)},
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,134 @@
+/*
+ * voronoids_b200.h -- C ABI of the B200-native Delaunay engine (libvoronoids_b200.so).
+ *
+ * Drop-in boundary for the parallel randomized-incremental insertion path of kazewong/Voronoids.  The reference
+ * exposes that path as a Rust rlib (`pub mod delaunay_tree/geometry/scheduler`, /root/reference/src/lib.rs:3-5)
+ * and as a PyO3 module (/root/reference/src/lib.rs:104-134); it has no C FFI of its own, so each entry point
+ * below names the Rust item it replaces.  A Rust `build.rs` + `extern "C"` crate, a cgo stub or Python ctypes bind
+ * these symbols directly.
+ *
+ * Conventions
+ *   - opaque handle, caller-owned flat buffers, two-phase size queries (pass NULL to get the count)
+ *   - every function returns a vor_status; nothing unwinds across the ABI; vor_last_error() gives the text
+ *   - points are row-major n x dim float64 (the reference's Vec<[f64; N]>)
+ *   - *_device variants take CUDA device pointers (inputs already resident in HBM)
+ *   - one handle <-> one CUDA stream; calls on one handle must be serialised by the caller (&mut self)
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with VOR_ERR_CUDA
+ *
+ * Vertex ids in exported simplices follow the reference's sequential numbering: 0..dim = super-simplex vertices
+ * (delaunay_tree.rs:395-406), dim+1..2*dim+1 = the ghost copies (never part of an exported simplex), input point i
+ * = 2*(dim+1) + i  (delaunay_tree.rs:173-174 with lib.rs:107,118).  Simplex ids are engine specific (the
+ * reference's depend on its insertion order and are not reproducible by any parallel construction).
+ */
+#ifndef VORONOIDS_B200_H
+#define VORONOIDS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum vor_status {
+    VOR_OK = 0,
+    VOR_ERR_NO_CONFLICT = 1,     /* reference: panic!("No simplex found ...")  delaunay_tree.rs:47-54 */
+    VOR_ERR_DEGENERATE = 2,      /* reference: LU .unwrap() panic             geometry.rs:49 */
+    VOR_ERR_DUPLICATE_POINT = 3, /* duplicate input points were dropped (undefined behaviour in the reference) */
+    VOR_ERR_CUDA = 4,
+    VOR_ERR_OOM = 5,
+    VOR_ERR_CAPACITY = 6,        /* a conflict region exceeded the overflow scratch */
+    VOR_ERR_RANGE = 7,           /* coordinate dynamic range beyond the exact-arithmetic limb budget */
+    VOR_ERR_OUTSIDE = 8,         /* a point lies outside the super simplex built by vor_tree_create */
+    VOR_ERR_INTERNAL = 9,
+    VOR_ERR_ARG = 10
+} vor_status;
+
+typedef struct vor_tree vor_tree; /* opaque; replaces DelaunayTree<N,M>  delaunay_tree.rs:24-30 */
+
+typedef enum vor_insert_mode {
+    VOR_INSERT_SINGLE = 0,   /* loop of TreeUpdate::new + insert_point     delaunay_tree.rs:710-739, :125-211 */
+    VOR_INSERT_PARALLEL = 1  /* add_points_to_tree                          delaunay_tree.rs:336-386 */
+} vor_insert_mode;
+/* Both modes run the same device rounds (the triangulation is unique); the mode is kept for API parity. */
+
+/* ---- construction ------------------------------------------------------------------------------------------- */
+
+/* DelaunayTree::<3,4>::new / ::<2,3>::new (delaunay_tree.rs:390, :545): bounding sphere of ALL n points
+ * (geometry.rs:99-142), 10x super simplex, nothing inserted yet.  device = CUDA ordinal. */
+vor_status vor_tree_create(int dim, const double *points, size_t n, int device, vor_tree **out);
+vor_status vor_tree_create_device(int dim, const double *d_points, size_t n, int device, void *cuda_stream, vor_tree **out);
+/* batch of independent point sets in one store (BASELINE.json config 5): set s = points[set_offsets[s] .. set_offsets[s+1]) */
+vor_status vor_tree_create_batch(int dim, const double *points, const int64_t *set_offsets, size_t n_sets, int device, vor_tree **out);
+vor_status vor_tree_create_batch_device(int dim, const double *d_points, const int64_t *set_offsets, size_t n_sets, int device,
+                                        void *cuda_stream, vor_tree **out);
+void vor_tree_destroy(vor_tree *t);
+
+/* insert n more points; input index of points[i] = (points inserted so far) + i.
+ * For a batch tree, set_offsets (n_sets+1 entries into `points`) is required; pass NULL for a single set. */
+vor_status vor_tree_insert(vor_tree *t, const double *points, size_t n, vor_insert_mode mode);
+vor_status vor_tree_insert_device(vor_tree *t, const double *d_points, size_t n, vor_insert_mode mode);
+vor_status vor_tree_insert_batch(vor_tree *t, const double *points, const int64_t *set_offsets);
+vor_status vor_tree_insert_batch_device(vor_tree *t, const double *d_points, const int64_t *set_offsets);
+
+/* voronoids.delaunay(points) (lib.rs:104-125): create + insert everything (3D in the reference; 2D accepted here) */
+vor_status vor_delaunay(int dim, const double *points, size_t n, int device, vor_tree **out);
+
+/* ---- queries -------------------------------------------------------------------------------------------------- */
+
+/* vertices.len(), live simplices, max_simplex_id (delaunay_tree.rs:26-29).  n_vertices counts the 2*(dim+1)
+ * super+ghost vertices like the reference; max_simplex_id = (dim+1) + simplices created so far. */
+vor_status vor_tree_counts(vor_tree *t, uint64_t *n_vertices, uint64_t *n_simplices, uint64_t *max_simplex_id);
+
+/* Delaunay graph: sorted unique {lo,hi} input-index pairs, u32 little endian.
+ * edges == NULL: only *n_edges is written. */
+vor_status vor_tree_edges(vor_tree *t, uint32_t *edges, size_t cap, size_t *n_edges);
+/* same list left on the device (pointer valid until the next insert/destroy) + an order-independent checksum */
+vor_status vor_tree_edges_device(vor_tree *t, const uint32_t **d_edges, size_t *n_edges, uint64_t *checksum);
+
+/* live simplices: vertices [n x (dim+1)] (reference ids), neighbours [n x (dim+1)] (index into this export, slot k is
+ * opposite vertex k, -1 = hull facet / ghost), centers [n x dim] and radii [n] as geometry.rs computes them.
+ * Any array may be NULL.  Replaces the PyDelauanyTree.simplices getter (lib.rs:87-101). */
+vor_status vor_tree_export_simplices(vor_tree *t, int32_t *vertices, int32_t *neighbors, double *centers, double *radii, size_t cap,
+                                     size_t *n_simplices);
+
+/* check_delaunay (delaunay_tree.rs:512-541): *ok = 1 iff every live simplex is positively oriented, adjacency is
+ * symmetric and every interior facet is locally Delaunay (equivalent to the brute-force empty-sphere test).
+ * fail_counts (optional, 5 entries): orientation, dead neighbour, asymmetric, facet mismatch, not Delaunay. */
+vor_status vor_tree_check_delaunay(vor_tree *t, int *ok, int32_t *fail_counts);
+
+/* bootstrap data: super-simplex vertices [(dim+1) x dim] per set, bounding-sphere centre [dim] and 10x radius */
+vor_status vor_tree_super_simplex(vor_tree *t, size_t set, double *super_vertices, double *center, double *radius);
+
+/* engine statistics: [rounds, attempts, winners, owner_resets, compactions, stages,
+ *                     walk_steps W, in-sphere tests E, killed K, created C, exact_calls, exact_zero, duplicates, simplex_slots] */
+#define VOR_N_STATS 14
+vor_status vor_tree_stats(vor_tree *t, uint64_t *stats);
+
+/* with option "profile": CUDA-event milliseconds per kernel class [attempt, check, retri, setup] followed by the
+ * launch counts of the same four classes (8 doubles) */
+vor_status vor_tree_profile(vor_tree *t, double *out8);
+
+/* ---- geometry (reference: pub mod geometry) ---------------------------------------------------------------- */
+
+/* circumsphere (geometry.rs:58-87): n simplices, verts [n x (dim+1) x dim] -> centers [n x dim], radii [n] */
+vor_status vor_circumsphere(int dim, const double *verts, size_t n, double *centers, double *radii, int device);
+/* in_sphere (geometry.rs:91-97): out[i] = |c_i - p_i|^2 < r_i^2 (float test, strict) */
+vor_status vor_in_sphere(int dim, const double *p, const double *c, const double *r, size_t n, int32_t *out, int device);
+/* bounding_sphere (geometry.rs:99-142) */
+vor_status vor_bounding_sphere(int dim, const double *points, size_t n, double *center, double *radius, int device);
+/* exact predicates (no reference counterpart): kind 0 orient2d [3 pts], 1 orient3d [4 pts],
+ * 2 incircle [4 pts], 3 insphere [5 pts]; rows are packed points; out = sign.  n_exact (optional) = calls that
+ * needed the exact path. */
+vor_status vor_predicates(int kind, const double *rows, size_t n, int32_t *out, uint64_t *n_exact, int device);
+
+/* ---- misc ------------------------------------------------------------------------------------------------------ */
+const char *vor_last_error(void);          /* thread-local text of the last failure */
+uint64_t vor_kernel_launches(void);        /* kernels of this library launched so far in this process */
+int vor_set_option(const char *name, double value); /* engine options for trees created afterwards */
+void vor_tree_set_stream(vor_tree *t, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -199,6 +199,9 @@ class RefDelaunay:
         if mode == "delaunay":
             self._h = L.vo_ref_delaunay(self.dim, pp, self.n, nthreads, C.byref(err))
             e = err.value
+        elif mode == "new":  # DelaunayTree::new only
+            self._h = L.vo_ref_create(self.dim, pp, self.n)
+            e = 0
         else:
             self._h = L.vo_ref_create(self.dim, pp, self.n)
             n_seq = self.n if n_seq is None else n_seq

@@ -1,0 +1,110 @@
+"""Engine parity cases shared by the emulation tests (CPU, kernel logic) and the GPU tests (product library).
+Every case goes through the C ABI (ctypes) and compares with the exact oracle."""
+import numpy as np
+
+from voronoids_b200 import _capi, pointgen
+
+
+def canon_simplices(s):
+    s = np.sort(np.asarray(s, dtype=np.int64), axis=1)
+    return s[np.lexsort(s.T[::-1])]
+
+
+def check_against_oracle(lib, O, pts, device=0, simplices=True):
+    t = _capi.Tree(lib, pts, device=device)
+    try:
+        ok, fails = t.check_delaunay()
+        assert ok, f"device mesh fails validation {fails}"
+        ex = O.ExactDelaunay(pts)
+        e = t.edges()
+        eo = ex.edges()
+        assert e.dtype == np.uint32 and e.shape == eo.shape, (e.shape, eo.shape)
+        assert np.array_equal(e, eo), "edge list differs from the exact oracle"
+        n, ck = t.edge_checksum()
+        assert n == len(eo) and ck == _capi.edge_checksum_host(eo)
+        sv, c, r = t.super_simplex()
+        so, co, ro = O.ref_super_simplex(pts)
+        assert np.array_equal(sv, so) and np.array_equal(c, co) and r == ro, "super simplex is not bit-identical"
+        if simplices:
+            m = pts.shape[1] + 1
+            v, nb = t.simplices()
+            # export ids: super k -> k, input i -> 2M + i ; oracle ids: super k -> k, input i -> M + i
+            v2 = np.where(v >= 2 * m, v - m, v)
+            assert np.array_equal(canon_simplices(v2), canon_simplices(ex.simplices())), "simplex set differs"
+            cnt = t.counts()
+            assert cnt["simplices"] == len(v) and cnt["vertices"] == 2 * m + len(pts)
+        return t.stats()
+    finally:
+        t.close()
+
+
+def case_incremental(lib, O, dim, n0, n1, seed=0):
+    """DelaunayTree::new(all) then two insert calls (examples/parallel_insert.rs: 100k sequential + 1M parallel)."""
+    pts = pointgen.uniform(n0 + n1, dim, seed)
+    t = _capi.Tree(lib, pts, insert=False)
+    try:
+        t.insert(pts[:n0], mode=0)
+        assert t.check_delaunay()[0]
+        e0 = t.edges()
+        # oracle for the first n0 points must use the super simplex of ALL points (tree was created from all)
+        sup = O.ref_super_simplex(pts)[0]
+        assert np.array_equal(e0, O.ExactDelaunay(pts[:n0], super_vertices=sup).edges())
+        t.insert(pts[n0:], mode=1)
+        assert t.check_delaunay()[0]
+        assert np.array_equal(t.edges(), O.ExactDelaunay(pts).edges())
+    finally:
+        t.close()
+
+
+def case_batch(lib, O, dim, sizes, seed0=1000):
+    sets = [pointgen.uniform(n, dim, seed0 + s) for s, n in enumerate(sizes)]
+    off = np.zeros(len(sets) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(sizes)
+    allp = np.concatenate(sets, axis=0)
+    t = _capi.Tree(lib, allp, set_offsets=off)
+    try:
+        assert t.check_delaunay()[0]
+        e = t.edges()
+        for s, p in enumerate(sets):
+            a = np.searchsorted(e[:, 0], off[s], side="left")
+            b = np.searchsorted(e[:, 0], off[s + 1], side="left")
+            es = (e[a:b].astype(np.int64) - off[s]).astype(np.uint32)
+            assert np.array_equal(es, O.ExactDelaunay(p).edges()), f"set {s} differs from its own triangulation"
+            sv = t.super_simplex(s)[0]
+            assert np.array_equal(sv, O.ref_super_simplex(p)[0])
+    finally:
+        t.close()
+
+
+def case_duplicates(lib, O, dim):
+    pts = pointgen.uniform(3000, dim, 5)
+    dup = np.concatenate([pts, pts[:7]], axis=0)  # 7 exact duplicates appended
+    t = _capi.Tree(lib, dup)
+    try:
+        assert t.duplicates, "duplicates must be reported (VOR_ERR_DUPLICATE_POINT)"
+        assert t.check_delaunay()[0]
+        e = t.edges()
+        # the surviving copy of a duplicated pair may be either index; compare through coordinates
+        eo = O.ExactDelaunay(pts).edges()
+        rep = np.arange(len(dup))
+        rep[len(pts):] = np.arange(7)
+        ee = np.sort(rep[e.astype(np.int64)], axis=1)
+        ee = np.unique(ee, axis=0)
+        assert np.array_equal(ee.astype(np.uint32), eo)
+        assert t.stats()["duplicates"] == 7
+    finally:
+        t.close()
+
+
+def case_tiny(lib, O, dim):
+    for n in (2, 3, 4, 5, 9):
+        pts = pointgen.uniform(n, dim, 11 + n)
+        check_against_oracle(lib, O, pts)
+    # one point: zero-radius bounding sphere -> the reference panics ("No simplex found"); here a status code
+    import pytest
+    with pytest.raises(_capi.VorError) as ei:
+        _capi.Tree(lib, pointgen.uniform(1, dim, 3))
+    assert ei.value.status == 2
+    # the reference's own 2D test points (tests/test_delaunay_tree.rs:42)
+    if dim == 2:
+        check_against_oracle(lib, O, np.array([[0.3, 0.1], [1.0, 0.2], [0.1, 1.0], [0.5, 0.5]]))

@@ -1,0 +1,79 @@
+"""Kernel logic + host round loop of voronoids_b200/csrc, compiled for the CPU by tests/emu (sequential launches),
+against the exact oracle.  This checks the algorithm in the GPU-less container; the product build of the very
+same sources is checked on the B200 by tests/test_gpu_engine.py."""
+import numpy as np
+import pytest
+
+import enginecases as ec
+from voronoids_b200 import _capi, pointgen
+
+
+@pytest.mark.parametrize("dim,kind,n", [(3, "uniform", 4000), (2, "uniform", 8000), (3, "clustered", 4000), (3, "lattice", 4000),
+                                        (2, "clustered", 4000), (2, "lattice", 4000)])
+def test_emu_matches_oracle(emu_lib, oracle, dim, kind, n):
+    st = ec.check_against_oracle(emu_lib, oracle, pointgen.make(kind, n, dim, 3))
+    assert st["winners"] == n
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_emu_tiny_inputs(emu_lib, oracle, dim):
+    ec.case_tiny(emu_lib, oracle, dim)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_emu_incremental_insert(emu_lib, oracle, dim):
+    ec.case_incremental(emu_lib, oracle, dim, 700, 5000)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_emu_batch_of_sets(emu_lib, oracle, dim):
+    ec.case_batch(emu_lib, oracle, dim, [1500, 300, 2000, 2, 777])
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_emu_duplicates_are_dropped_and_reported(emu_lib, oracle, dim):
+    ec.case_duplicates(emu_lib, oracle, dim)
+
+
+def test_emu_overflow_scratch_and_compaction(emu_lib, oracle):
+    # tiny regular slots force the overflow path; a small attempt budget forces many rounds + list compaction
+    emu_lib.vor_set_option(b"capk", 8.0)
+    emu_lib.vor_set_option(b"min_attempt", 512.0)
+    try:
+        st = ec.check_against_oracle(emu_lib, oracle, pointgen.uniform(20000, 3, 9))
+        assert st["compactions"] > 0
+    finally:
+        emu_lib.vor_set_option(b"capk", 64.0)
+        emu_lib.vor_set_option(b"min_attempt", float(1 << 17))
+
+
+def test_emu_capacity_error_is_loud(emu_lib):
+    emu_lib.vor_set_option(b"capk", 4.0)
+    emu_lib.vor_set_option(b"big_capk", 8.0)
+    try:
+        with pytest.raises(_capi.VorError) as ei:
+            _capi.Tree(emu_lib, pointgen.uniform(3000, 3, 1))
+        assert ei.value.status == 6
+    finally:
+        emu_lib.vor_set_option(b"capk", 64.0)
+        emu_lib.vor_set_option(b"big_capk", 8192.0)
+
+
+def test_emu_point_outside_super_simplex_is_loud(emu_lib):
+    pts = pointgen.uniform(200, 3, 1)
+    t = _capi.Tree(emu_lib, pts, insert=False)
+    with pytest.raises(_capi.VorError) as ei:
+        t.insert(np.array([[1e6, 1e6, 1e6]]))
+    assert ei.value.status == 8
+    t.close()
+
+
+def test_emu_owner_epoch_reset(emu_lib, oracle):
+    # 2^17+ points in a stage leave 12 epoch bits; a tiny slot cap makes many rounds so the epoch wraps
+    emu_lib.vor_set_option(b"slot_cap", 64.0)
+    try:
+        pts = pointgen.uniform(2500, 2, 4)
+        st = ec.check_against_oracle(emu_lib, oracle, pts)
+        assert st["rounds"] > 50
+    finally:
+        emu_lib.vor_set_option(b"slot_cap", float(1 << 19))

@@ -1,0 +1,163 @@
+"""Parity tests proper: the product library (hand-written sm_100a CUDA behind the C ABI) on a B200 against the
+exact oracle, the committed golden vectors, and size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+
+import enginecases as ec
+import predcases as pc
+from voronoids_b200 import _capi, pointgen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dim,kind,n", [(3, "uniform", 10_000), (3, "uniform", 200_000), (2, "uniform", 200_000), (3, "clustered", 100_000),
+                                        (3, "lattice", 100_000), (2, "clustered", 100_000), (2, "lattice", 100_000)])
+def test_gpu_matches_oracle(gpu_lib, oracle, dim, kind, n):
+    st = ec.check_against_oracle(gpu_lib, oracle, pointgen.make(kind, n, dim, 3))
+    assert st["winners"] == n
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_gpu_tiny_inputs(gpu_lib, oracle, dim):
+    ec.case_tiny(gpu_lib, oracle, dim)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_gpu_incremental_insert(gpu_lib, oracle, dim):
+    # examples/parallel_insert.rs shape at 1/10 scale: 10k "sequential" + 100k "parallel"
+    ec.case_incremental(gpu_lib, oracle, dim, 10_000, 100_000)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_gpu_batch_of_sets(gpu_lib, oracle, dim):
+    ec.case_batch(gpu_lib, oracle, dim, [20_000, 300, 50_000, 2, 7777, 10_000])
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_gpu_duplicates(gpu_lib, oracle, dim):
+    ec.case_duplicates(gpu_lib, oracle, dim)
+
+
+def test_gpu_overflow_scratch(gpu_lib, oracle):
+    gpu_lib.vor_set_option(b"capk", 8.0)
+    gpu_lib.vor_set_option(b"min_attempt", 2048.0)
+    try:
+        st = ec.check_against_oracle(gpu_lib, oracle, pointgen.uniform(60_000, 3, 9))
+        assert st["compactions"] > 0
+    finally:
+        gpu_lib.vor_set_option(b"capk", 64.0)
+        gpu_lib.vor_set_option(b"min_attempt", float(1 << 17))
+
+
+def test_gpu_errors_are_loud(gpu_lib):
+    pts = pointgen.uniform(200, 3, 1)
+    t = _capi.Tree(gpu_lib, pts, insert=False)
+    with pytest.raises(_capi.VorError) as ei:
+        t.insert(np.array([[1e6, 1e6, 1e6]]))
+    assert ei.value.status == 8
+    t.close()
+    with pytest.raises(_capi.VorError) as ei:
+        _capi.Tree(gpu_lib, pointgen.uniform(1, 3, 1))
+    assert ei.value.status == 2
+
+
+@pytest.mark.parametrize("name", ["u3_10k", "u3_100k", "u3_1m", "u2_10k", "u2_1m", "c3_100k", "l3_100k", "c3_500k", "l3_500k", "u3_set1000_100k"])
+def test_gpu_golden_vectors(gpu_lib, oracle, golden, name):
+    g = golden[name]
+    t = _capi.Tree(gpu_lib, pointgen.make(g["kind"], g["n"], g["dim"], g["seed"]))
+    try:
+        e = t.edges()
+        assert len(e) == g["n_edges"]
+        assert oracle.edge_sha256(e) == g["sha256"]
+        assert t.edge_checksum() == (g["n_edges"], g["checksum64"])
+        assert t.counts()["simplices"] == g["live_simplices"]
+    finally:
+        t.close()
+
+
+@pytest.mark.slow
+def test_gpu_full_size_10m(gpu_lib, oracle, golden):
+    """BASELINE.json configs[2]: 3D uniform 10M points, edge set bit-exact (hash of the canonical list) and the
+    size-independent properties: valid orientation, symmetric adjacency, locally Delaunay everywhere."""
+    g = golden.get("u3_10m")
+    pts = pointgen.uniform(10_000_000, 3, 0)
+    t = _capi.Tree(gpu_lib, pts)
+    try:
+        ok, fails = t.check_delaunay()
+        assert ok, fails
+        n, ck = t.edge_checksum()
+        e = t.edges()
+        assert len(e) == n and np.all(e[:, 0] < e[:, 1])
+        k = (e[:, 0].astype(np.uint64) << np.uint64(32)) | e[:, 1]
+        assert np.all(k[1:] > k[:-1]), "edge list must be sorted and unique"
+        assert ck == _capi.edge_checksum_host(e)
+        cnt = t.counts()
+        # Euler-type count for a triangulated ball: live simplices relate to the vertex/edge counts of P u S
+        assert cnt["vertices"] == 8 + 10_000_000
+        if g is not None:
+            assert n == g["n_edges"] and oracle.edge_sha256(e) == g["sha256"]
+            assert cnt["simplices"] == g["live_simplices"]
+    finally:
+        t.close()
+
+
+@pytest.mark.parametrize("kind", ["orient2d", "orient3d", "incircle", "insphere"])
+def test_gpu_predicates_vs_fractions(gpu_lib, oracle, kind):
+    from voronoids_b200 import geometry
+    rows = pc.adversarial(kind, 800, seed=5)
+    want = np.array([pc.EXACT[kind](r) for r in rows])
+    got, n_exact = geometry.predicate(kind, rows, return_exact_count=True)
+    assert np.array_equal(got, want)
+    assert n_exact > 100
+    big = pc.adversarial(kind, 200_000, seed=6)
+    assert np.array_equal(geometry.predicate(kind, big), getattr(oracle, kind)(big))
+    wide = pc.wide_range(kind, 300, seed=7)
+    assert np.array_equal(geometry.predicate(kind, wide), np.array([pc.EXACT[kind](r) for r in wide]))
+
+
+def test_gpu_geometry_module(gpu_lib, oracle):
+    from voronoids_b200 import geometry
+    c, r = geometry.circumsphere([[1.0, 0.0, 0.0], [0.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]])
+    assert c.tolist() == [0.5, 0.5, 0.5] and r == 0.8660254037844386      # tests/test_geometry.rs:5-15
+    rng = np.random.default_rng(0)
+    tets = rng.random((5000, 4, 3))
+    cg, rg = geometry.circumsphere(tets)
+    for i in range(0, 5000, 97):
+        co, ro = oracle.ref_circumsphere(tets[i])
+        assert np.array_equal(cg[i], co) and rg[i] == ro                  # same operation order, no FMA
+    tris = rng.random((1000, 3, 2))
+    cg, rg = geometry.circumsphere(tris)
+    co, ro = oracle.ref_circumsphere(tris[5])
+    assert np.array_equal(cg[5], co) and rg[5] == ro
+    assert geometry.in_sphere([0.0, 0.0, 0.0], [0.5, 0.0, 0.0], 1.0) and not geometry.in_sphere([1.0, 0.0, 0.0], [0.0, 0.0, 0.0], 1.0)
+    pts = pointgen.uniform(100_000, 3, 0) * 2 - 1
+    cb, rb = geometry.bounding_sphere(pts)
+    co, ro = oracle.ref_bounding_sphere(pts)
+    assert np.array_equal(cb, co) and rb == ro
+
+
+def test_gpu_python_api_matches_reference_shape(gpu_lib, oracle):
+    """voronoids.delaunay(points) drop-in: attribute names and id conventions of lib.rs:12-134."""
+    import voronoids_b200 as vb
+    pts = pointgen.uniform(2000, 3, 0)
+    tree = vb.delaunay(pts.tolist())           # the reference takes a list of [x,y,z]
+    assert isinstance(tree, vb.PyDelauanyTree)
+    verts, simps = tree.vertices, tree.simplices
+    assert len(verts) == 8 + 2000 and verts[8].point == pts[0].tolist()
+    assert tree.max_simplex_id >= max(simps)
+    ex = oracle.ExactDelaunay(pts)
+    real = {k: s for k, s in simps.items() if k > 4}
+    assert len(real) == ex.stats()["live"]
+    for k in (1, 2, 3, 4):
+        assert simps[k].radius == 0.0 and simps[k].center == [0.0, 0.0, 0.0]  # ghosts, delaunay_tree.rs:467-502
+    some = next(iter(real.values()))
+    assert len(some.vertices) == 4 and len(some.center) == 3 and len(some.neighbors) == 4
+    # adjacency is symmetric and Vertex.simplex lists are consistent with Simplex.vertices
+    for k, s in list(real.items())[:500]:
+        for nb in s.neighbors:
+            assert k in simps[nb].neighbors
+        for v in s.vertices:
+            assert k in verts[v].simplex
+    # circumspheres follow the reference's float formulas
+    co, ro = oracle.ref_circumsphere(np.array([verts[v].point for v in some.vertices]))
+    assert some.center == co.tolist() and some.radius == ro

@@ -1,0 +1,168 @@
+"""ctypes declarations for include/voronoids_b200.h (shared by the product loader and the emulation tests)."""
+import ctypes as C
+
+import numpy as np
+
+dp = C.POINTER(C.c_double)
+i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+szp = C.POINTER(C.c_size_t)
+tree_p = C.c_void_p
+
+STATUS = {0: "VOR_OK", 1: "VOR_ERR_NO_CONFLICT", 2: "VOR_ERR_DEGENERATE", 3: "VOR_ERR_DUPLICATE_POINT", 4: "VOR_ERR_CUDA",
+          5: "VOR_ERR_OOM", 6: "VOR_ERR_CAPACITY", 7: "VOR_ERR_RANGE", 8: "VOR_ERR_OUTSIDE", 9: "VOR_ERR_INTERNAL", 10: "VOR_ERR_ARG"}
+
+# every symbol include/voronoids_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "vor_tree_create": (C.c_int, [C.c_int, dp, C.c_size_t, C.c_int, C.POINTER(tree_p)]),
+    "vor_tree_create_device": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(tree_p)]),
+    "vor_tree_create_batch": (C.c_int, [C.c_int, dp, i64p, C.c_size_t, C.c_int, C.POINTER(tree_p)]),
+    "vor_tree_create_batch_device": (C.c_int, [C.c_int, C.c_void_p, i64p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(tree_p)]),
+    "vor_tree_destroy": (None, [tree_p]),
+    "vor_tree_insert": (C.c_int, [tree_p, dp, C.c_size_t, C.c_int]),
+    "vor_tree_insert_device": (C.c_int, [tree_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "vor_tree_insert_batch": (C.c_int, [tree_p, dp, i64p]),
+    "vor_tree_insert_batch_device": (C.c_int, [tree_p, C.c_void_p, i64p]),
+    "vor_delaunay": (C.c_int, [C.c_int, dp, C.c_size_t, C.c_int, C.POINTER(tree_p)]),
+    "vor_tree_counts": (C.c_int, [tree_p, u64p, u64p, u64p]),
+    "vor_tree_edges": (C.c_int, [tree_p, u32p, C.c_size_t, szp]),
+    "vor_tree_edges_device": (C.c_int, [tree_p, C.POINTER(C.c_void_p), szp, u64p]),
+    "vor_tree_export_simplices": (C.c_int, [tree_p, i32p, i32p, dp, dp, C.c_size_t, szp]),
+    "vor_tree_check_delaunay": (C.c_int, [tree_p, C.POINTER(C.c_int), i32p]),
+    "vor_tree_super_simplex": (C.c_int, [tree_p, C.c_size_t, dp, dp, dp]),
+    "vor_tree_stats": (C.c_int, [tree_p, u64p]),
+    "vor_tree_profile": (C.c_int, [tree_p, dp]),
+    "vor_circumsphere": (C.c_int, [C.c_int, dp, C.c_size_t, dp, dp, C.c_int]),
+    "vor_in_sphere": (C.c_int, [C.c_int, dp, dp, dp, C.c_size_t, i32p, C.c_int]),
+    "vor_bounding_sphere": (C.c_int, [C.c_int, dp, C.c_size_t, dp, dp, C.c_int]),
+    "vor_predicates": (C.c_int, [C.c_int, dp, C.c_size_t, i32p, u64p, C.c_int]),
+    "vor_last_error": (C.c_char_p, []),
+    "vor_kernel_launches": (C.c_uint64, []),
+    "vor_set_option": (C.c_int, [C.c_char_p, C.c_double]),
+    "vor_tree_set_stream": (None, [tree_p, C.c_void_p]),
+}
+N_STATS = 14
+STAT_NAMES = ("rounds", "attempts", "winners", "owner_resets", "compactions", "stages", "walk_steps", "tests", "killed", "created",
+              "exact_calls", "exact_zero", "duplicates", "simplex_slots")
+
+
+def bind(lib):
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def as_f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(dp)
+
+
+class VorError(RuntimeError):
+    def __init__(self, status, text):
+        super().__init__(f"{STATUS.get(status, status)}: {text}")
+        self.status = status
+
+
+class Tree:
+    """Thin RAII wrapper over a vor_tree handle (host-buffer entry points)."""
+
+    def __init__(self, lib, points=None, device=0, dim=None, set_offsets=None, insert=True):
+        self._lib = lib
+        self._h = tree_p()
+        self.duplicates = False
+        p, pp = as_f64(points)
+        self.dim = p.shape[1] if dim is None else dim
+        self.n = p.shape[0]
+        if set_offsets is None:
+            self._check(lib.vor_tree_create(self.dim, pp, self.n, device, C.byref(self._h)))
+            if insert:
+                self.insert(p)
+        else:
+            off = np.ascontiguousarray(set_offsets, dtype=np.int64)
+            self._off = off
+            self._check(lib.vor_tree_create_batch(self.dim, pp, off.ctypes.data_as(i64p), len(off) - 1, device, C.byref(self._h)))
+            if insert:
+                self._check(lib.vor_tree_insert_batch(self._h, pp, off.ctypes.data_as(i64p)))
+
+    def _check(self, st):
+        if st == 3:
+            self.duplicates = True
+            return
+        if st != 0:
+            raise VorError(st, self._lib.vor_last_error().decode())
+
+    def insert(self, points, mode=1):
+        p, pp = as_f64(points)
+        self._check(self._lib.vor_tree_insert(self._h, pp, p.shape[0], mode))
+
+    def close(self):
+        if self._h:
+            self._lib.vor_tree_destroy(self._h)
+            self._h = tree_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def counts(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.vor_tree_counts(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"vertices": a.value, "simplices": b.value, "max_simplex_id": c.value}
+
+    def edges(self):
+        n = C.c_size_t()
+        self._check(self._lib.vor_tree_edges(self._h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 2), dtype=np.uint32)
+        self._check(self._lib.vor_tree_edges(self._h, out.ctypes.data_as(u32p), n.value, C.byref(n)))
+        return out
+
+    def edge_checksum(self):
+        n, ck, ptr = C.c_size_t(), C.c_uint64(), C.c_void_p()
+        self._check(self._lib.vor_tree_edges_device(self._h, C.byref(ptr), C.byref(n), C.byref(ck)))
+        return n.value, ck.value
+
+    def simplices(self, circumspheres=False):
+        n = C.c_size_t()
+        self._check(self._lib.vor_tree_export_simplices(self._h, None, None, None, None, 0, C.byref(n)))
+        m = self.dim + 1
+        v = np.zeros((n.value, m), dtype=np.int32)
+        nb = np.zeros((n.value, m), dtype=np.int32)
+        c = np.zeros((n.value, self.dim)) if circumspheres else None
+        r = np.zeros(n.value) if circumspheres else None
+        self._check(self._lib.vor_tree_export_simplices(
+            self._h, v.ctypes.data_as(i32p), nb.ctypes.data_as(i32p),
+            c.ctypes.data_as(dp) if circumspheres else None, r.ctypes.data_as(dp) if circumspheres else None, n.value, C.byref(n)))
+        return (v, nb, c, r) if circumspheres else (v, nb)
+
+    def check_delaunay(self):
+        ok = C.c_int()
+        f = np.zeros(5, dtype=np.int32)
+        self._check(self._lib.vor_tree_check_delaunay(self._h, C.byref(ok), f.ctypes.data_as(i32p)))
+        return bool(ok.value), f
+
+    def super_simplex(self, s=0):
+        sv = np.zeros((self.dim + 1, self.dim))
+        c = np.zeros(self.dim)
+        r = C.c_double()
+        self._check(self._lib.vor_tree_super_simplex(self._h, s, sv.ctypes.data_as(dp), c.ctypes.data_as(dp), C.byref(r)))
+        return sv, c, r.value
+
+    def stats(self):
+        s = (C.c_uint64 * N_STATS)()
+        self._check(self._lib.vor_tree_stats(self._h, s))
+        return dict(zip(STAT_NAMES, [int(x) for x in s]))
+
+
+def edge_checksum_host(edges):
+    """Same order-independent checksum as vor_tree_edges_device, computed with numpy."""
+    from .pointgen import splitmix64
+    e = np.ascontiguousarray(edges, dtype=np.uint64)
+    k = (e[:, 0] << np.uint64(32)) | e[:, 1]
+    with np.errstate(over="ignore"):
+        return int(np.sum(splitmix64(k), dtype=np.uint64))

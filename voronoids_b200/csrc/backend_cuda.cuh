@@ -1,0 +1,135 @@
+// backend_cuda.cuh -- device memory, copies, sort and kernel launch for the product build (nvcc, sm_100a).
+// tests/emu/backend_emu.h provides the same interface on the host for kernel-logic unit tests.
+#pragma once
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "vor_common.cuh"
+
+namespace vor {
+namespace be {
+
+typedef cudaStream_t Stream;
+
+struct CudaError : std::runtime_error {
+    int code;
+    CudaError(const std::string &m, int c) : std::runtime_error(m), code(c) {}
+};
+
+inline void check(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) {
+        const int code = (e == cudaErrorMemoryAllocation) ? ERR_OOM : ERR_CUDA;
+        throw CudaError(std::string(what) + ": " + cudaGetErrorString(e), code);
+    }
+}
+#define VOR_CUDA(x) ::vor::be::check((x), #x)
+
+inline void set_device(int dev) { VOR_CUDA(cudaSetDevice(dev)); }
+inline void *dmalloc(size_t bytes) {
+    void *p = nullptr;
+    VOR_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+    return p;
+}
+inline void dfree(void *p) { if (p) cudaFree(p); }
+inline void dmemset(void *p, int byte, size_t n, Stream s) { VOR_CUDA(cudaMemsetAsync(p, byte, n, s)); }
+inline void h2d(void *d, const void *h, size_t n, Stream s) { VOR_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
+inline void d2h(void *h, const void *d, size_t n, Stream s) { VOR_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
+inline void d2d(void *d, const void *s_, size_t n, Stream s) { VOR_CUDA(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s)); }
+inline void sync(Stream s) { VOR_CUDA(cudaStreamSynchronize(s)); }
+inline void *hmalloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    VOR_CUDA(cudaMallocHost(&p, bytes ? bytes : 16));
+    return p;
+}
+inline void hfree_pinned(void *p) { if (p) cudaFreeHost(p); }
+
+// library plumbing (not a hot-path kernel): CUB LSD radix sort of (u64 key, u32 value) pairs
+inline void sort_pairs(uint64_t *keys_in, uint64_t *keys_out, uint32_t *vals_in, uint32_t *vals_out, size_t n, Stream s) {
+    size_t tmp = 0;
+    VOR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 64, s));
+    void *d = dmalloc(tmp);
+    VOR_CUDA(cub::DeviceRadixSort::SortPairs(d, tmp, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 64, s));
+    VOR_CUDA(cudaStreamSynchronize(s));
+    dfree(d);
+}
+inline void sort_keys(uint64_t *keys_in, uint64_t *keys_out, size_t n, Stream s) {
+    size_t tmp = 0;
+    VOR_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys_in, keys_out, (int)n, 0, 64, s));
+    void *d = dmalloc(tmp);
+    VOR_CUDA(cub::DeviceRadixSort::SortKeys(d, tmp, keys_in, keys_out, (int)n, 0, 64, s));
+    VOR_CUDA(cudaStreamSynchronize(s));
+    dfree(d);
+}
+
+extern unsigned long long g_launches;
+
+// per-kernel-class CUDA-event timing on the launching stream (bench.py roofline; off unless option "profile")
+struct Prof {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;   // pairs
+    std::vector<int> cls;
+    double ms[4] = {0, 0, 0, 0};
+    double cnt[4] = {0, 0, 0, 0};
+    void start(int c, Stream s) {
+        if (!on) return;
+        cudaEvent_t a, b;
+        VOR_CUDA(cudaEventCreate(&a));
+        VOR_CUDA(cudaEventCreate(&b));
+        ev.push_back(a); ev.push_back(b); cls.push_back(c);
+        VOR_CUDA(cudaEventRecord(a, s));
+    }
+    void stop(Stream s) {
+        if (!on) return;
+        VOR_CUDA(cudaEventRecord(ev.back(), s));
+    }
+    void resolve(Stream s) {
+        if (!on) return;
+        VOR_CUDA(cudaStreamSynchronize(s));
+        for (size_t i = 0; i < cls.size(); i++) {
+            float t = 0;
+            VOR_CUDA(cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]));
+            ms[cls[i]] += t;
+            cnt[cls[i]] += 1;
+            cudaEventDestroy(ev[2 * i]);
+            cudaEventDestroy(ev[2 * i + 1]);
+        }
+        ev.clear();
+        cls.clear();
+    }
+}; // kernels of this library launched so far (bench.py gpu_launches)
+
+} // namespace be
+
+// generic one-thread-per-item kernel around a body function
+template <class Args, void (*Body)(const Args &, int)>
+__global__ void __launch_bounds__(256) k_items(Args a, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) Body(a, i);
+}
+// variant without early exit (bodies that use full-warp collectives)
+template <class Args, void (*Body)(const Args &, int, bool)>
+__global__ void __launch_bounds__(256) k_items_full(Args a, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    Body(a, i, i < n);
+}
+
+#define VOR_LAUNCH(ArgsT, body, n, args, stream)                                                         \
+    do {                                                                                                 \
+        const int _n = (int)(n);                                                                         \
+        if (_n > 0) {                                                                                    \
+            ::vor::k_items<ArgsT, body><<<(_n + 255) / 256, 256, 0, stream>>>(args, _n);                 \
+            ::vor::be::g_launches++;                                                                     \
+        }                                                                                                \
+    } while (0)
+#define VOR_LAUNCH_FULL(ArgsT, body, n, args, stream)                                                    \
+    do {                                                                                                 \
+        const int _n = (int)(n);                                                                         \
+        if (_n > 0) {                                                                                    \
+            ::vor::k_items_full<ArgsT, body><<<(_n + 255) / 256, 256, 0, stream>>>(args, _n);            \
+            ::vor::be::g_launches++;                                                                     \
+        }                                                                                                \
+    } while (0)
+
+} // namespace vor

@@ -1,0 +1,375 @@
+// capi.inl -- implementation of include/voronoids_b200.h on top of Engine<D>.
+// Included by vor_lib.cu (product, CUDA backend) and by tests/emu/emu_lib.cpp (kernel-logic unit tests).
+#include <memory>
+#include <mutex>
+#include <new>
+
+#include "../../include/voronoids_b200.h"
+
+namespace {
+
+thread_local std::string g_err;
+vor::EngineOptions g_opts;
+bool g_opts_init = false;
+
+vor::EngineOptions current_options() {
+    if (!g_opts_init) { vor::options_from_env(g_opts); g_opts_init = true; }
+    return g_opts;
+}
+
+template <class F> vor_status guarded(F &&f) {
+    try {
+        return f();
+    } catch (const vor::EngineError &e) {
+        g_err = e.msg;
+        return (vor_status)(e.code == vor::ERR_WALK ? VOR_ERR_INTERNAL : e.code);
+    } catch (const vor::be::CudaError &e) {
+        g_err = e.what();
+        return (vor_status)e.code;
+    } catch (const std::bad_alloc &) {
+        g_err = "host allocation failed";
+        return VOR_ERR_OOM;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return VOR_ERR_INTERNAL;
+    }
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    explicit DevBuf(size_t bytes) { p = vor::be::dmalloc(bytes); }
+    ~DevBuf() { vor::be::dfree(p); }
+    DevBuf(const DevBuf &) = delete;
+};
+
+std::vector<int> offsets32(const int64_t *off, size_t n_sets) {
+    std::vector<int> o(n_sets + 1);
+    for (size_t i = 0; i <= n_sets; i++) {
+        if (off[i] < 0 || off[i] > 0x7fffffff || (i && off[i] < off[i - 1])) throw vor::EngineError{vor::ERR_ARG, "bad set offsets"};
+        o[i] = (int)off[i];
+    }
+    return o;
+}
+
+} // namespace
+
+struct vor_tree {
+    int dim = 3;
+    int device = 0;
+    size_t n_sets = 1;
+    vor::be::Stream stream{};
+    std::unique_ptr<vor::Engine<2>> e2;
+    std::unique_ptr<vor::Engine<3>> e3;
+    template <class F> auto visit(F &&f) { return dim == 2 ? f(*e2) : f(*e3); }
+};
+
+extern "C" {
+
+const char *vor_last_error(void) { return g_err.c_str(); }
+uint64_t vor_kernel_launches(void) { return vor::be::g_launches; }
+
+int vor_set_option(const char *name, double value) {
+    current_options();
+    const std::string n(name ? name : "");
+    if (n == "slot_cap") g_opts.slot_cap = (int)value;
+    else if (n == "min_attempt") g_opts.min_attempt = (int)value;
+    else if (n == "attempt_div") g_opts.attempt_div = value;
+    else if (n == "stage0") g_opts.stage0 = (int)value;
+    else if (n == "stats") g_opts.stats = (int)value;
+    else if (n == "verbose") g_opts.verbose = (int)value;
+    else if (n == "profile") g_opts.profile = (int)value;
+    else if (n == "tet_factor") g_opts.tet_factor = value;
+    else if (n == "capk") { g_opts.capk = (int)value; g_opts.capb = 2 * g_opts.capk + 4; }
+    else if (n == "big_slots") g_opts.big_slots = (int)value;
+    else if (n == "big_capk") g_opts.big_capk = (int)value;
+    else return -1;
+    return 0;
+}
+
+vor_status vor_tree_create_batch_device(int dim, const double *d_points, const int64_t *set_offsets, size_t n_sets, int device,
+                                        void *cuda_stream, vor_tree **out) {
+    return guarded([&]() -> vor_status {
+        if (!out || (dim != 2 && dim != 3) || n_sets < 1 || !set_offsets) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(device);
+        std::unique_ptr<vor_tree> t(new vor_tree);
+        t->dim = dim;
+        t->device = device;
+        t->n_sets = n_sets;
+        t->stream = (vor::be::Stream)(uintptr_t)cuda_stream;
+        const std::vector<int> off = offsets32(set_offsets, n_sets);
+        if (dim == 2) { t->e2.reset(new vor::Engine<2>(t->stream, current_options())); t->e2->create(d_points, off.back(), off.data(), (int)n_sets); }
+        else { t->e3.reset(new vor::Engine<3>(t->stream, current_options())); t->e3->create(d_points, off.back(), off.data(), (int)n_sets); }
+        *out = t.release();
+        return VOR_OK;
+    });
+}
+
+vor_status vor_tree_create_device(int dim, const double *d_points, size_t n, int device, void *cuda_stream, vor_tree **out) {
+    const int64_t off[2] = {0, (int64_t)n};
+    return vor_tree_create_batch_device(dim, d_points, off, 1, device, cuda_stream, out);
+}
+
+vor_status vor_tree_create_batch(int dim, const double *points, const int64_t *set_offsets, size_t n_sets, int device, vor_tree **out) {
+    return guarded([&]() -> vor_status {
+        if (!set_offsets || n_sets < 1 || (dim != 2 && dim != 3)) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(device);
+        const size_t n = (size_t)set_offsets[n_sets];
+        DevBuf d(sizeof(double) * n * dim);
+        vor::be::h2d(d.p, points, sizeof(double) * n * dim, vor::be::Stream{});
+        vor::be::sync(vor::be::Stream{});
+        return vor_tree_create_batch_device(dim, (const double *)d.p, set_offsets, n_sets, device, nullptr, out);
+    });
+}
+
+vor_status vor_tree_create(int dim, const double *points, size_t n, int device, vor_tree **out) {
+    const int64_t off[2] = {0, (int64_t)n};
+    return vor_tree_create_batch(dim, points, off, 1, device, out);
+}
+
+void vor_tree_destroy(vor_tree *t) {
+    if (!t) return;
+    try { vor::be::set_device(t->device); } catch (...) {}
+    delete t;
+}
+
+void vor_tree_set_stream(vor_tree *t, void *cuda_stream) {
+    if (!t) return;
+    t->stream = (vor::be::Stream)(uintptr_t)cuda_stream;
+    if (t->e2) t->e2->stream = t->stream;
+    if (t->e3) t->e3->stream = t->stream;
+}
+
+vor_status vor_tree_insert_batch_device(vor_tree *t, const double *d_points, const int64_t *set_offsets) {
+    return guarded([&]() -> vor_status {
+        if (!t || !set_offsets) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        const std::vector<int> off = offsets32(set_offsets, t->n_sets);
+        const int dup0 = t->visit([](auto &e) { return e.hcnt->ndup; });
+        t->visit([&](auto &e) { e.insert(d_points, off.back(), off.data()); return 0; });
+        const int dup1 = t->visit([](auto &e) { return e.hcnt->ndup; });
+        if (dup1 > dup0) { g_err = std::to_string(dup1 - dup0) + " duplicate point(s) dropped"; return VOR_ERR_DUPLICATE_POINT; }
+        return VOR_OK;
+    });
+}
+
+vor_status vor_tree_insert_device(vor_tree *t, const double *d_points, size_t n, vor_insert_mode) {
+    if (!t || t->n_sets != 1) { g_err = "single-set insert on a batch tree"; return VOR_ERR_ARG; }
+    const int64_t off[2] = {0, (int64_t)n};
+    return vor_tree_insert_batch_device(t, d_points, off);
+}
+
+vor_status vor_tree_insert_batch(vor_tree *t, const double *points, const int64_t *set_offsets) {
+    return guarded([&]() -> vor_status {
+        if (!t || !set_offsets) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        const size_t n = (size_t)set_offsets[t->n_sets];
+        DevBuf d(sizeof(double) * n * t->dim);
+        vor::be::h2d(d.p, points, sizeof(double) * n * t->dim, t->stream);
+        vor::be::sync(t->stream);
+        return vor_tree_insert_batch_device(t, (const double *)d.p, set_offsets);
+    });
+}
+
+vor_status vor_tree_insert(vor_tree *t, const double *points, size_t n, vor_insert_mode) {
+    if (!t || t->n_sets != 1) { g_err = "single-set insert on a batch tree"; return VOR_ERR_ARG; }
+    const int64_t off[2] = {0, (int64_t)n};
+    return vor_tree_insert_batch(t, points, off);
+}
+
+vor_status vor_delaunay(int dim, const double *points, size_t n, int device, vor_tree **out) {
+    return guarded([&]() -> vor_status {
+        if (!out || (dim != 2 && dim != 3)) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(device);
+        DevBuf d(sizeof(double) * n * dim);
+        vor::be::h2d(d.p, points, sizeof(double) * n * dim, vor::be::Stream{});
+        vor::be::sync(vor::be::Stream{});
+        vor_tree *t = nullptr;
+        vor_status s = vor_tree_create_device(dim, (const double *)d.p, n, device, nullptr, &t);
+        if (s != VOR_OK) return s;
+        s = vor_tree_insert_device(t, (const double *)d.p, n, VOR_INSERT_PARALLEL);
+        if (s != VOR_OK && s != VOR_ERR_DUPLICATE_POINT) { vor_tree_destroy(t); return s; }
+        *out = t;
+        return s;
+    });
+}
+
+vor_status vor_tree_counts(vor_tree *t, uint64_t *n_vertices, uint64_t *n_simplices, uint64_t *max_simplex_id) {
+    return guarded([&]() -> vor_status {
+        if (!t) { g_err = "null tree"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        return t->visit([&](auto &e) -> vor_status {
+            if (n_vertices) *n_vertices = (uint64_t)e.nsuper * 2 + (uint64_t)e.insertedTotal;
+            if (max_simplex_id) *max_simplex_id = (uint64_t)(e.M * e.nsets) + (uint64_t)(e.hcnt->ntets - e.nsets);
+            if (n_simplices) *n_simplices = (uint64_t)e.export_simplices(nullptr, nullptr, nullptr, nullptr, 0);
+            return VOR_OK;
+        });
+    });
+}
+
+vor_status vor_tree_edges(vor_tree *t, uint32_t *edges, size_t cap, size_t *n_edges) {
+    return guarded([&]() -> vor_status {
+        if (!t) { g_err = "null tree"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        return t->visit([&](auto &e) -> vor_status {
+            const long long m = e.edges();
+            if (n_edges) *n_edges = (size_t)m;
+            if (edges) e.copy_edges(edges, (long long)cap);
+            return VOR_OK;
+        });
+    });
+}
+
+vor_status vor_tree_edges_device(vor_tree *t, const uint32_t **d_edges, size_t *n_edges, uint64_t *checksum) {
+    return guarded([&]() -> vor_status {
+        if (!t) { g_err = "null tree"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        return t->visit([&](auto &e) -> vor_status {
+            const long long m = e.edges();
+            if (n_edges) *n_edges = (size_t)m;
+            if (d_edges) *d_edges = e.d_edges;
+            if (checksum) *checksum = e.edge_checksum();
+            return VOR_OK;
+        });
+    });
+}
+
+vor_status vor_tree_export_simplices(vor_tree *t, int32_t *vertices, int32_t *neighbors, double *centers, double *radii, size_t cap,
+                                     size_t *n_simplices) {
+    return guarded([&]() -> vor_status {
+        if (!t) { g_err = "null tree"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        return t->visit([&](auto &e) -> vor_status {
+            const int n = e.export_simplices(nullptr, nullptr, nullptr, nullptr, 0);
+            if (n_simplices) *n_simplices = (size_t)n;
+            if (!vertices && !neighbors && !centers && !radii) return VOR_OK;
+            if (cap < (size_t)n) { g_err = "export buffer too small"; return VOR_ERR_ARG; }
+            e.export_simplices(vertices, neighbors, centers, radii, 2 * e.M * e.nsets);
+            return VOR_OK;
+        });
+    });
+}
+
+vor_status vor_tree_check_delaunay(vor_tree *t, int *ok, int32_t *fail_counts) {
+    return guarded([&]() -> vor_status {
+        if (!t) { g_err = "null tree"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        return t->visit([&](auto &e) -> vor_status {
+            int f[8];
+            e.validate(f);
+            if (ok) *ok = (f[0] | f[1] | f[2] | f[3] | f[4]) == 0;
+            if (fail_counts) for (int i = 0; i < 5; i++) fail_counts[i] = f[i];
+            return VOR_OK;
+        });
+    });
+}
+
+vor_status vor_tree_super_simplex(vor_tree *t, size_t set, double *super_vertices, double *center, double *radius) {
+    return guarded([&]() -> vor_status {
+        if (!t || set >= t->n_sets) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        return t->visit([&](auto &e) -> vor_status {
+            const int D = e.M - 1;
+            if (super_vertices) memcpy(super_vertices, &e.superXYZ[set * e.M * D], sizeof(double) * e.M * D);
+            if (center) memcpy(center, &e.center[set * D], sizeof(double) * D);
+            if (radius) *radius = e.radius[set];
+            return VOR_OK;
+        });
+    });
+}
+
+vor_status vor_tree_stats(vor_tree *t, uint64_t *s) {
+    return guarded([&]() -> vor_status {
+        if (!t || !s) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        return t->visit([&](auto &e) -> vor_status {
+            e.pull_counters();
+            const vor::Counters &c = *e.hcnt;
+            s[0] = e.rs.rounds; s[1] = e.rs.attempts; s[2] = e.rs.winners; s[3] = e.rs.owner_resets; s[4] = e.rs.compactions; s[5] = e.rs.stages;
+            s[6] = c.walk_steps; s[7] = c.tests; s[8] = c.killed; s[9] = c.created; s[10] = c.exact_calls; s[11] = c.exact_zero;
+            s[12] = (uint64_t)c.ndup; s[13] = (uint64_t)c.ntets;
+            return VOR_OK;
+        });
+    });
+}
+
+vor_status vor_tree_profile(vor_tree *t, double *out) {
+    return guarded([&]() -> vor_status {
+        if (!t || !out) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        return t->visit([&](auto &e) -> vor_status {
+            for (int i = 0; i < 4; i++) { out[i] = e.prof.ms[i]; out[4 + i] = e.prof.cnt[i]; }
+            return VOR_OK;
+        });
+    });
+}
+
+// ---- geometry batches
+vor_status vor_circumsphere(int dim, const double *verts, size_t n, double *centers, double *radii, int device) {
+    return guarded([&]() -> vor_status {
+        if (dim != 2 && dim != 3) { g_err = "bad dim"; return VOR_ERR_ARG; }
+        vor::be::set_device(device);
+        const vor::be::Stream st{};
+        const size_t M = dim + 1;
+        DevBuf dv(sizeof(double) * n * M * dim), dc(sizeof(double) * n * dim), dr(sizeof(double) * n);
+        vor::be::h2d(dv.p, verts, sizeof(double) * n * M * dim, st);
+        if (dim == 3) {
+            vor::CircumBatchArgs<3> a{(const double *)dv.p, (double *)dc.p, (double *)dr.p};
+            VOR_LAUNCH(vor::CircumBatchArgs<3>, vor::circum_batch_body, n, a, st);
+        } else {
+            vor::CircumBatchArgs<2> a{(const double *)dv.p, (double *)dc.p, (double *)dr.p};
+            VOR_LAUNCH(vor::CircumBatchArgs<2>, vor::circum_batch_body, n, a, st);
+        }
+        vor::be::d2h(centers, dc.p, sizeof(double) * n * dim, st);
+        vor::be::d2h(radii, dr.p, sizeof(double) * n, st);
+        vor::be::sync(st);
+        return VOR_OK;
+    });
+}
+
+vor_status vor_in_sphere(int dim, const double *p, const double *c, const double *r, size_t n, int32_t *out, int device) {
+    return guarded([&]() -> vor_status {
+        if (dim != 2 && dim != 3) { g_err = "bad dim"; return VOR_ERR_ARG; }
+        vor::be::set_device(device);
+        const vor::be::Stream st{};
+        DevBuf dp(sizeof(double) * n * dim), dc(sizeof(double) * n * dim), dr(sizeof(double) * n), dout(sizeof(int) * n);
+        vor::be::h2d(dp.p, p, sizeof(double) * n * dim, st);
+        vor::be::h2d(dc.p, c, sizeof(double) * n * dim, st);
+        vor::be::h2d(dr.p, r, sizeof(double) * n, st);
+        vor::InSphereBatchArgs a{(const double *)dp.p, (const double *)dc.p, (const double *)dr.p, (int *)dout.p, dim};
+        VOR_LAUNCH(vor::InSphereBatchArgs, vor::in_sphere_batch_body, n, a, st);
+        vor::be::d2h(out, dout.p, sizeof(int) * n, st);
+        vor::be::sync(st);
+        return VOR_OK;
+    });
+}
+
+vor_status vor_bounding_sphere(int dim, const double *points, size_t n, double *center, double *radius, int device) {
+    vor_tree *t = nullptr;
+    vor_status s = vor_tree_create(dim, points, n, device, &t);
+    if (s != VOR_OK) return s;
+    s = vor_tree_super_simplex(t, 0, nullptr, center, nullptr);
+    if (radius) *radius = t->visit([&](auto &e) { return e.radiusBase[0]; }); // before the 10x of delaunay_tree.rs:393
+    vor_tree_destroy(t);
+    return s;
+}
+
+vor_status vor_predicates(int kind, const double *rows, size_t n, int32_t *out, uint64_t *n_exact, int device) {
+    return guarded([&]() -> vor_status {
+        static const int width[4] = {6, 12, 8, 15};
+        if (kind < 0 || kind > 3) { g_err = "bad kind"; return VOR_ERR_ARG; }
+        vor::be::set_device(device);
+        const vor::be::Stream st{};
+        DevBuf dr(sizeof(double) * n * width[kind]), dout(sizeof(int) * n), dc(sizeof(vor::Counters));
+        vor::be::h2d(dr.p, rows, sizeof(double) * n * width[kind], st);
+        vor::be::dmemset(dc.p, 0, sizeof(vor::Counters), st);
+        vor::PredBatchArgs a{(const double *)dr.p, (int *)dout.p, (vor::Counters *)dc.p, kind};
+        VOR_LAUNCH(vor::PredBatchArgs, vor::pred_batch_body, n, a, st);
+        vor::Counters hc;
+        vor::be::d2h(out, dout.p, sizeof(int) * n, st);
+        vor::be::d2h(&hc, dc.p, sizeof(hc), st);
+        vor::be::sync(st);
+        if (n_exact) *n_exact = hc.exact_calls;
+        if (hc.err == vor::ERR_RANGE) { g_err = "coordinate range exceeds the exact-arithmetic capacity"; return VOR_ERR_RANGE; }
+        return VOR_OK;
+    });
+}
+
+} // extern "C"

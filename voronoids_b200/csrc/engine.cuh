@@ -1,0 +1,652 @@
+// engine.cuh -- host side of the device engine: store management, bootstrap, BRIO ordering, the round loop and
+// the output passes.  Backend-agnostic (backend_cuda.cuh in the product, tests/emu/backend_emu.h in unit tests).
+//
+// Reference counterparts:
+//   Engine::create   DelaunayTree::new          /root/reference/src/delaunay_tree.rs:390-510 (3D), :545-640 (2D)
+//   Engine::insert   add_points_to_tree         /root/reference/src/delaunay_tree.rs:336-386
+//                    (and the sequential loop of lib.rs:110-120: same result, the triangulation is unique)
+//   Engine::edges    Delaunay-graph extraction  SURVEY.md §8a row G (implicit in lib.rs:73-101)
+//   Engine::validate check_delaunay             /root/reference/src/delaunay_tree.rs:512-541
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "output_kernels.cuh"
+#include "setup_kernels.cuh"
+
+namespace vor {
+
+struct EngineOptions {
+    int slot_cap = 1 << 19;      // attempt slots per round (scratch size)
+    int big_slots = 256;         // overflow slots per round
+    int big_capk = 8192;         // killed capacity of an overflow slot
+    int capk = 64;               // killed capacity of a regular slot
+    int capb = 132;              // boundary capacity of a regular slot (2*capk + 4)
+    int min_attempt = 1 << 17;   // attempt at least this many points per round (keeps the SMs busy)
+    double attempt_div = 16.0;   // otherwise attempt about (inserted vertices)/attempt_div points per round
+    int stage0 = 256;            // size of the first stage
+    int stats = 0;               // accumulate W/E/K/C counters (atomics; keep off when timing)
+    int verbose = 0;
+    int profile = 0;             // CUDA-event time per kernel class (attempt / check / retri / setup)
+    double tet_factor = 0.0;     // simplex slots per vertex (0 = default: 30 in 3D, 7 in 2D)
+};
+
+inline void options_from_env(EngineOptions &o) {
+    if (const char *e = getenv("VOR_SLOT_CAP")) o.slot_cap = atoi(e);
+    if (const char *e = getenv("VOR_MIN_ATTEMPT")) o.min_attempt = atoi(e);
+    if (const char *e = getenv("VOR_ATTEMPT_DIV")) o.attempt_div = atof(e);
+    if (const char *e = getenv("VOR_STAGE0")) o.stage0 = atoi(e);
+    if (const char *e = getenv("VOR_STATS")) o.stats = atoi(e);
+    if (const char *e = getenv("VOR_VERBOSE")) o.verbose = atoi(e);
+    if (const char *e = getenv("VOR_TET_FACTOR")) o.tet_factor = atof(e);
+    if (const char *e = getenv("VOR_CAPK")) { o.capk = atoi(e); o.capb = 2 * o.capk + 4; }
+}
+
+struct EngineError {
+    int code;
+    std::string msg;
+};
+
+struct RunStats {
+    unsigned long long rounds = 0, attempts = 0, winners = 0, owner_resets = 0, compactions = 0, stages = 0;
+};
+
+template <int D> class Engine {
+  public:
+    using Pt = typename Dim<D>::Pt;
+    static constexpr int M = D + 1;
+
+    EngineOptions opt;
+    be::Stream stream;
+    int nsets = 1;
+    int nsuper = 0;
+    // host copies of the bootstrap data (per set)
+    std::vector<double> boxLo, boxHi, center, radius, radiusBase, superXYZ;
+    std::vector<int> setInserted;
+    // device store
+    Mesh<D> mesh{};
+    int vcap = 0, nv = 0;
+    int *inputIdx = nullptr, *vidOfInput = nullptr;
+    uint64_t *keysAll = nullptr;
+    int ninput = 0, incap = 0;
+    double *d_boxLo = nullptr, *d_boxHi = nullptr;
+    Counters *hcnt = nullptr; // pinned host mirror
+    // scratch
+    Scratch scr{};
+    int *act = nullptr, *act2 = nullptr, *blockCnt = nullptr;
+    long long *d_misc = nullptr;
+    long long insertedTotal = 0;
+    int actcap = 0;
+    // key layout
+    int setBits = 0, axisBits = 0;
+    // priority / epoch state
+    int bits = 1, epoch = 0, epochMax = 0;
+    // seeding reference stage (vertex range)
+    int refLo = 0, refHi = 0;
+    uint64_t callSalt = 0x5851F42D4C957F2DULL;
+    RunStats rs;
+    be::Prof prof;
+    // cached outputs
+    uint32_t *d_edges = nullptr;
+    long long nedges = -1;
+
+    explicit Engine(be::Stream s, const EngineOptions &o) : opt(o), stream(s) {
+        hcnt = (Counters *)be::hmalloc_pinned(sizeof(Counters));
+        memset(hcnt, 0, sizeof(Counters));
+        d_misc = (long long *)be::dmalloc(sizeof(long long) * 8);
+        prof.on = opt.profile != 0;
+    }
+    ~Engine() {
+        be::dfree(mesh.pts); be::dfree(mesh.tv); be::dfree(mesh.tn); be::dfree(mesh.owner); be::dfree(mesh.seed);
+        be::dfree(mesh.ptTet); be::dfree(mesh.cnt); be::dfree(inputIdx); be::dfree(vidOfInput); be::dfree(keysAll);
+        be::dfree(d_boxLo); be::dfree(d_boxHi); be::dfree(act); be::dfree(act2); be::dfree(blockCnt); be::dfree(d_edges);
+        free_scratch();
+        be::dfree(d_misc);
+        be::hfree_pinned(hcnt);
+    }
+    Engine(const Engine &) = delete;
+    Engine &operator=(const Engine &) = delete;
+
+    [[noreturn]] static void fail(int code, const std::string &m) { throw EngineError{code, m}; }
+
+    // ------------------------------------------------------------------ memory helpers
+    template <class T> void grow(T *&p, size_t oldn, size_t newn) {
+        T *q = (T *)be::dmalloc(sizeof(T) * newn);
+        if (p && oldn) be::d2d(q, p, sizeof(T) * oldn, stream);
+        be::sync(stream);
+        be::dfree(p);
+        p = q;
+    }
+    void fill_i(int *p, int val, size_t n) {
+        size_t done = 0;
+        while (done < n) { // launches are int-indexed
+            const size_t c = std::min(n - done, (size_t)1 << 30);
+            FillArgs a{p + done, val};
+            VOR_LAUNCH(FillArgs, fill_body, c, a, stream);
+            done += c;
+        }
+    }
+    void ensure_vertices(int need) {
+        if (need <= vcap) return;
+        const int nc = std::max(need, vcap + vcap / 2);
+        grow(mesh.pts, (size_t)nv, (size_t)nc);
+        grow(mesh.seed, (size_t)nv, (size_t)nc);
+        grow(mesh.ptTet, (size_t)nv, (size_t)nc);
+        grow(inputIdx, (size_t)nv, (size_t)nc);
+        grow(keysAll, (size_t)std::max(nv - nsuper, 0), (size_t)nc);
+        vcap = nc;
+    }
+    void ensure_inputs(int need) {
+        if (need <= incap) return;
+        const int nc = std::max(need, incap + incap / 2);
+        grow(vidOfInput, (size_t)ninput, (size_t)nc);
+        incap = nc;
+    }
+    void ensure_simplices(long long need) {
+        if (need <= mesh.cap) return;
+        if (need > (1LL << 29) - 1) fail(ERR_OOM, "more than 2^29 simplex slots needed");
+        long long nc = std::max(need, (long long)mesh.cap + mesh.cap / 2);
+        nc = std::min(nc, (1LL << 29) - 1);
+        const int old = mesh.cap;
+        grow(mesh.tv, (size_t)old, (size_t)nc);
+        grow(mesh.tn, (size_t)old, (size_t)nc);
+        grow(mesh.owner, (size_t)old, (size_t)nc);
+        fill_i(mesh.owner + old, OWNER_FREE, (size_t)(nc - old));
+        mesh.cap = (int)nc;
+        if (opt.verbose) fprintf(stderr, "[vor] simplex capacity -> %lld\n", nc);
+    }
+    void free_scratch() {
+        be::dfree(scr.killed); be::dfree(scr.bfacet); be::dfree(scr.bouter); be::dfree(scr.slotAct); be::dfree(scr.slotNk);
+        be::dfree(scr.slotNb); be::dfree(scr.slotStatus); be::dfree(scr.slotBig); be::dfree(scr.bigK); be::dfree(scr.bigF);
+        be::dfree(scr.bigO); be::dfree(scr.winners); be::dfree(scr.wbase);
+        scr = Scratch{};
+    }
+    void ensure_scratch(int nslots) {
+        if (nslots <= scr.nslots) return;
+        free_scratch();
+        scr.nslots = nslots;
+        scr.capk = opt.capk;
+        scr.capb = opt.capb;
+        scr.killed = (int *)be::dmalloc(sizeof(int) * (size_t)scr.capk * nslots);
+        scr.bfacet = (int *)be::dmalloc(sizeof(int) * (size_t)scr.capb * nslots);
+        scr.bouter = (int *)be::dmalloc(sizeof(int) * (size_t)scr.capb * nslots);
+        scr.slotAct = (int *)be::dmalloc(sizeof(int) * (size_t)nslots);
+        scr.slotNk = (int *)be::dmalloc(sizeof(int) * (size_t)nslots);
+        scr.slotNb = (int *)be::dmalloc(sizeof(int) * (size_t)nslots);
+        scr.slotStatus = (int *)be::dmalloc(sizeof(int) * (size_t)nslots);
+        scr.slotBig = (int *)be::dmalloc(sizeof(int) * (size_t)nslots);
+        scr.winners = (int *)be::dmalloc(sizeof(int) * (size_t)nslots);
+        scr.wbase = (int *)be::dmalloc(sizeof(int) * (size_t)nslots);
+        scr.nbig = opt.big_slots;
+        scr.bigCapK = opt.big_capk;
+        scr.bigCapB = 2 * opt.big_capk + 4;
+        scr.bigK = (int *)be::dmalloc(sizeof(int) * (size_t)scr.nbig * scr.bigCapK);
+        scr.bigF = (int *)be::dmalloc(sizeof(int) * (size_t)scr.nbig * scr.bigCapB);
+        scr.bigO = (int *)be::dmalloc(sizeof(int) * (size_t)scr.nbig * scr.bigCapB);
+    }
+    void pull_counters() {
+        be::d2h(hcnt, mesh.cnt, sizeof(Counters), stream);
+        be::sync(stream);
+    }
+    void push_counters() { be::h2d(mesh.cnt, hcnt, sizeof(Counters), stream); }
+    void check_device_error(const char *where) {
+        if (hcnt->err) {
+            static const char *names[] = {"ok", "no conflict", "degenerate", "duplicate point", "cuda", "out of memory",
+                                          "cavity exceeds overflow scratch", "coordinate range exceeds exact arithmetic capacity",
+                                          "point outside the super simplex", "walk did not terminate", "bad argument"};
+            const int c = hcnt->err;
+            fail(c, std::string(where) + ": " + (c >= 0 && c <= 10 ? names[c] : "error"));
+        }
+    }
+
+    // ------------------------------------------------------------------ bootstrap  (DelaunayTree::new)
+    // d_in: n x D points on the device (all the points the tree will ever see, as in the reference);
+    // h_setOff: nsets+1 offsets (nullptr => one set)
+    void create(const double *d_in, int n, const int *h_setOff, int nsets_) {
+        nsets = nsets_ < 1 ? 1 : nsets_;
+        nsuper = nsets * M;
+        std::vector<int> off(nsets + 1);
+        if (h_setOff) off.assign(h_setOff, h_setOff + nsets + 1);
+        else { off[0] = 0; off[1] = n; }
+        // chunk table
+        std::vector<ChunkDesc> chunks;
+        for (int s = 0; s < nsets; s++)
+            for (int lo = off[s]; lo < off[s + 1]; lo += BBOX_CHUNK) chunks.push_back(ChunkDesc{s, lo, std::min(lo + BBOX_CHUNK, off[s + 1])});
+        const int nch = (int)chunks.size();
+        ChunkDesc *d_chunks = (ChunkDesc *)be::dmalloc(sizeof(ChunkDesc) * (size_t)std::max(nch, 1));
+        double *d_partial = (double *)be::dmalloc(sizeof(double) * 2 * D * (size_t)std::max(nch, 1));
+        be::h2d(d_chunks, chunks.data(), sizeof(ChunkDesc) * (size_t)nch, stream);
+        BboxArgs<D> ba{d_in, d_chunks, d_partial};
+        VOR_LAUNCH(BboxArgs<D>, bbox_chunk_body<D>, nch, ba, stream);
+        std::vector<double> partial((size_t)nch * 2 * D);
+        be::d2h(partial.data(), d_partial, sizeof(double) * partial.size(), stream);
+        be::sync(stream);
+        boxLo.assign((size_t)nsets * D, INFINITY);
+        boxHi.assign((size_t)nsets * D, -INFINITY);
+        for (int c = 0; c < nch; c++)
+            for (int k = 0; k < D; k++) {
+                const int s = chunks[c].set;
+                boxLo[(size_t)s * D + k] = std::fmin(boxLo[(size_t)s * D + k], partial[(size_t)c * 2 * D + k]);
+                boxHi[(size_t)s * D + k] = std::fmax(boxHi[(size_t)s * D + k], partial[(size_t)c * 2 * D + D + k]);
+            }
+        // bounding sphere (geometry.rs:99-142): centre, half diagonal, then the 1.5x rule
+        center.assign((size_t)nsets * D, 0.0);
+        radius.assign((size_t)nsets, 0.0);
+        radiusBase.assign((size_t)nsets, 0.0);
+        for (int s = 0; s < nsets; s++) {
+            double ud = 0.0, ld = 0.0;
+            for (int k = 0; k < D; k++) center[(size_t)s * D + k] = (boxHi[(size_t)s * D + k] + boxLo[(size_t)s * D + k]) / 2.0;
+            for (int k = 0; k < D; k++) { const double d = boxHi[(size_t)s * D + k] - center[(size_t)s * D + k]; ud += d * d; }
+            for (int k = 0; k < D; k++) { const double d = boxLo[(size_t)s * D + k] - center[(size_t)s * D + k]; ld += d * d; }
+            ud = std::sqrt(ud);
+            ld = std::sqrt(ld);
+            radius[s] = ud > ld ? ud : ld;
+        }
+        double *d_center = (double *)be::dmalloc(sizeof(double) * (size_t)nsets * D);
+        double *d_radius = (double *)be::dmalloc(sizeof(double) * (size_t)nsets);
+        int *d_outside = (int *)be::dmalloc(sizeof(int) * (size_t)nsets);
+        be::h2d(d_center, center.data(), sizeof(double) * (size_t)nsets * D, stream);
+        be::h2d(d_radius, radius.data(), sizeof(double) * (size_t)nsets, stream);
+        be::dmemset(d_outside, 0, sizeof(int) * (size_t)nsets, stream);
+        OutsideArgs<D> oa{d_in, d_chunks, d_center, d_radius, d_outside};
+        VOR_LAUNCH(OutsideArgs<D>, count_outside_body<D>, nch, oa, stream);
+        std::vector<int> outside(nsets);
+        be::d2h(outside.data(), d_outside, sizeof(int) * (size_t)nsets, stream);
+        be::sync(stream);
+        be::dfree(d_chunks); be::dfree(d_partial); be::dfree(d_center); be::dfree(d_radius); be::dfree(d_outside);
+        // super simplex (delaunay_tree.rs:392-406 / :547-558); host libm cos/sin as rustc's f64::cos/sin
+        superXYZ.assign((size_t)nsets * M * D, 0.0);
+        const double PI = 3.14159265358979323846264338327950288;
+        const double a1 = 2. * PI / 3., a2 = 4. * PI / 3.;
+        for (int s = 0; s < nsets; s++) {
+            if (outside[s] > 0) radius[s] = radius[s] * 1.5;
+            radiusBase[s] = radius[s];
+            radius[s] *= 10.0;
+            // a single point / coincident points / empty set: zero or non-finite radius, the super simplex collapses
+            // (the reference panics there with "No simplex found", delaunay_tree.rs:47-54)
+            if (!(radius[s] > 0.0) || !std::isfinite(radius[s])) fail(ERR_DEGENERATE, "bounding sphere of the point set has zero or non-finite radius");
+            const double r = radius[s];
+            const double *c = &center[(size_t)s * D];
+            double *sv = &superXYZ[(size_t)s * M * D];
+            if (D == 3) {
+                sv[0] = c[0]; sv[1] = c[1]; sv[2] = c[2] + r;
+                sv[3] = c[0] + r; sv[4] = c[1]; sv[5] = c[2] - r;
+                sv[6] = c[0] + r * std::cos(a1); sv[7] = c[1] + r * std::sin(a1); sv[8] = c[2] - r;
+                sv[9] = c[0] + r * std::cos(a2); sv[10] = c[1] + r * std::sin(a2); sv[11] = c[2] - r;
+            } else {
+                sv[0] = c[0] + r; sv[1] = c[1];
+                sv[2] = c[0] + r * std::cos(a1); sv[3] = c[1] + r * std::sin(a1);
+                sv[4] = c[0] + r * std::cos(a2); sv[5] = c[1] + r * std::sin(a2);
+            }
+        }
+        // store
+        setInserted.assign(nsets, 0);
+        setBits = 0;
+        while ((1 << setBits) < nsets) setBits++;
+        axisBits = std::min(D == 3 ? 19 : 28, (STAGE_SHIFT - setBits) / D);
+        mesh.nsuper = nsuper;
+        mesh.cnt = (Counters *)be::dmalloc(sizeof(Counters));
+        ensure_vertices(nsuper + n + 16);
+        ensure_inputs(n + 16);
+        const double tf = opt.tet_factor > 0 ? opt.tet_factor : (D == 3 ? 30.0 : 7.0);
+        ensure_simplices((long long)(tf * (double)(n + 64)) + 4LL * nsets + 1024);
+        d_boxLo = (double *)be::dmalloc(sizeof(double) * (size_t)nsets * D);
+        d_boxHi = (double *)be::dmalloc(sizeof(double) * (size_t)nsets * D);
+        be::h2d(d_boxLo, boxLo.data(), sizeof(double) * (size_t)nsets * D, stream);
+        be::h2d(d_boxHi, boxHi.data(), sizeof(double) * (size_t)nsets * D, stream);
+        // super vertices + root simplices (simplex s = root of set s), positively oriented
+        std::vector<Pt> sp((size_t)nsuper);
+        std::vector<int4> rtv((size_t)nsets), rtn((size_t)nsets);
+        std::vector<int> rseed((size_t)nsuper, -1);
+        Counters dummy;
+        memset(&dummy, 0, sizeof(dummy));
+        PredCtx cx{&dummy};
+        for (int s = 0; s < nsets; s++) {
+            for (int k = 0; k < M; k++) set_host_pt(sp[(size_t)s * M + k], &superXYZ[((size_t)s * M + k) * D]);
+            int4 v;
+            v.x = s * M; v.y = s * M + 1; v.z = s * M + 2; v.w = (D == 3) ? s * M + 3 : -1;
+            if (orient_host(cx, &sp[(size_t)s * M]) < 0) std::swap(v.x, v.y);
+            rtv[s] = v;
+            rtn[s] = int4{-1, -1, -1, -1};
+        }
+        be::h2d(mesh.pts, sp.data(), sizeof(Pt) * (size_t)nsuper, stream);
+        be::h2d(mesh.tv, rtv.data(), sizeof(int4) * (size_t)nsets, stream);
+        be::h2d(mesh.tn, rtn.data(), sizeof(int4) * (size_t)nsets, stream);
+        be::h2d(mesh.seed, rseed.data(), sizeof(int) * (size_t)nsuper, stream);
+        fill_i(mesh.ptTet, 0, (size_t)nsuper);
+        fill_i(inputIdx, -1, (size_t)nsuper);
+        nv = nsuper;
+        memset(hcnt, 0, sizeof(Counters));
+        hcnt->ntets = nsets;
+        push_counters();
+        be::sync(stream);
+    }
+    static void set_host_pt(double4 &p, const double *s) { p.x = s[0]; p.y = s[1]; p.z = s[2]; p.w = 0.0; }
+    static void set_host_pt(double2 &p, const double *s) { p.x = s[0]; p.y = s[1]; }
+    static int orient_host(PredCtx &cx, const double4 *p) { return orient3d(cx, p[0], p[1], p[2], p[3]); }
+    static int orient_host(PredCtx &cx, const double2 *p) { return orient2d(cx, p[0], p[1], p[2]); }
+
+    // ------------------------------------------------------------------ insertion  (add_points_to_tree)
+    // d_in: n x D points on the device; h_setOff: nsets+1 offsets into d_in (nullptr => one set)
+    void insert(const double *d_in, int n, const int *h_setOff) {
+        if (n <= 0) return;
+        invalidate_outputs();
+        std::vector<int> off(nsets + 1);
+        if (h_setOff) off.assign(h_setOff, h_setOff + nsets + 1);
+        else { off[0] = 0; off[1] = n; }
+        ensure_vertices(nv + n);
+        ensure_inputs(ninput + n);
+        const double tf = opt.tet_factor > 0 ? opt.tet_factor : (D == 3 ? 30.0 : 7.0);
+        ensure_simplices((long long)hcnt->ntets + (long long)(tf * (double)(n + 64)));
+
+        // ---- keys, sort, gather
+        std::vector<int> s0(nsets);
+        for (int s = 0; s < nsets; s++) s0[s] = std::max(opt.stage0, setInserted[s]);
+        int *d_off = (int *)be::dmalloc(sizeof(int) * (size_t)(nsets + 1));
+        int *d_s0 = (int *)be::dmalloc(sizeof(int) * (size_t)nsets);
+        uint64_t *k0 = (uint64_t *)be::dmalloc(sizeof(uint64_t) * (size_t)n);
+        uint32_t *v0 = (uint32_t *)be::dmalloc(sizeof(uint32_t) * (size_t)n);
+        uint32_t *v1 = (uint32_t *)be::dmalloc(sizeof(uint32_t) * (size_t)n);
+        be::h2d(d_off, off.data(), sizeof(int) * (size_t)(nsets + 1), stream);
+        be::h2d(d_s0, s0.data(), sizeof(int) * (size_t)nsets, stream);
+        callSalt = mix64(callSalt + (uint64_t)ninput);
+        prof.start(3, stream);
+        KeyArgs<D> ka{d_in, d_off, d_boxLo, d_boxHi, d_s0, k0, v0, nsets, setBits, axisBits, callSalt};
+        VOR_LAUNCH(KeyArgs<D>, keys_body<D>, n, ka, stream);
+        uint64_t *kdst = keysAll + (nv - nsuper);
+        be::sort_pairs(k0, kdst, v0, v1, (size_t)n, stream);
+        GatherArgs<D> ga{d_in, v1, mesh.pts, inputIdx, vidOfInput, mesh.seed, mesh.ptTet, nv, ninput};
+        VOR_LAUNCH(GatherArgs<D>, gather_body<D>, n, ga, stream);
+        int *d_stageLo = (int *)be::dmalloc(sizeof(int) * 64);
+        be::dmemset(d_stageLo, 0xff, sizeof(int) * 64, stream);
+        StageBoundsArgs sa{kdst, d_stageLo};
+        VOR_LAUNCH(StageBoundsArgs, stage_bounds_body, n, sa, stream);
+        prof.stop(stream);
+        int stageLo[65];
+        be::d2h(stageLo, d_stageLo, sizeof(int) * 64, stream);
+        be::sync(stream);
+        be::dfree(d_off); be::dfree(d_s0); be::dfree(k0); be::dfree(v0); be::dfree(v1); be::dfree(d_stageLo);
+        stageLo[64] = n;
+        for (int st = 63; st >= 0; st--)
+            if (stageLo[st] < 0) stageLo[st] = stageLo[st + 1]; // empty stage
+
+        const int vbase = nv;
+        nv += n;
+        const int inputBase = ninput;
+        ninput += n;
+        (void)inputBase;
+
+        // ---- priority bits: wide enough for the largest stage of this call
+        int maxStage = 1;
+        for (int st = 0; st < 64; st++) maxStage = std::max(maxStage, stageLo[st + 1] - stageLo[st]);
+        bits = 1;
+        while ((1 << bits) < maxStage) bits++;
+        if (bits + 1 > 28) fail(ERR_ARG, "stage too large for the priority key");
+        epochMax = (1 << (30 - (bits + 1))) - 1;
+        reset_owners();
+        ensure_scratch(std::min(maxStage, opt.slot_cap));
+        if (maxStage > actcap) {
+            be::dfree(act); be::dfree(act2); be::dfree(blockCnt);
+            actcap = maxStage;
+            act = (int *)be::dmalloc(sizeof(int) * (size_t)actcap);
+            act2 = (int *)be::dmalloc(sizeof(int) * (size_t)actcap);
+            blockCnt = (int *)be::dmalloc(sizeof(int) * (size_t)(actcap / 256 + 2));
+        }
+
+        // ---- stages
+        for (int st = 0; st < 64; st++) {
+            const int lo = vbase + stageLo[st], hi = vbase + stageLo[st + 1];
+            if (hi <= lo) continue;
+            run_stage(lo, hi);
+            refLo = lo;
+            refHi = hi;
+            rs.stages++;
+        }
+        for (int s = 0; s < nsets; s++) setInserted[s] += off[s + 1] - off[s];
+        pull_counters();
+        prof.resolve(stream);
+        check_device_error("insert");
+    }
+
+    void reset_owners() {
+        ResetOwnerArgs ra{mesh.owner};
+        VOR_LAUNCH(ResetOwnerArgs, reset_owner_body, hcnt->ntets, ra, stream);
+        epoch = epochMax;
+        rs.owner_resets++;
+    }
+
+    void run_stage(int lo, int hi) {
+        int nact = hi - lo;
+        int pending = nact;
+        SeedArgs sd{keysAll, mesh.ptTet, mesh.seed, nsuper, lo, refLo, refHi, D * axisBits};
+        VOR_LAUNCH(SeedArgs, init_seeds_body, nact, sd, stream);
+        IotaArgs ia{act, lo};
+        VOR_LAUNCH(IotaArgs, iota_body, nact, ia, stream);
+        int stall = 0;
+        uint32_t roundSalt = (uint32_t)mix64((uint64_t)lo * 0x9E37u + rs.rounds);
+        while (pending > 0) {
+            if (epoch <= 0) reset_owners();
+            const double target = std::max((double)opt.min_attempt, (double)insertedTotal / opt.attempt_div);
+            uint32_t thr = 1u << bits;
+            if ((double)pending > target) {
+                // priorities are uniform over [0, 2^bits); `nact` of them are in use
+                const double f = target / (double)pending;
+                thr = (uint32_t)std::max(1.0, f * (double)(1u << bits));
+            }
+            roundSalt = roundSalt * 1664525u + 1013904223u;
+            const int keybase = epoch << (bits + 1);
+            hcnt->nslots = 0; hcnt->nwinners = 0; hcnt->nbig = 0;
+            const int ndup0 = hcnt->ndup;
+            // only the round-local counters are rewritten (the allocator and statistics live on the device)
+            be::h2d(&mesh.cnt->nslots, &hcnt->nslots, sizeof(int) * 3, stream);
+            AttemptArgs<D> aa{mesh, scr, act, bits, roundSalt, thr, keybase, opt.stats};
+            prof.start(0, stream);
+            VOR_LAUNCH(AttemptArgs<D>, attempt_body<D>, nact, aa, stream);
+            prof.stop(stream);
+            const int maxSlots = std::min(nact, scr.nslots);
+            CheckArgs<D> ca{mesh, scr, bits, roundSalt, keybase};
+            prof.start(1, stream);
+            VOR_LAUNCH_FULL(CheckArgs<D>, check_body<D>, maxSlots, ca, stream);
+            prof.stop(stream);
+            pull_counters();
+            check_device_error("round");
+            const int nw = hcnt->nwinners;
+            const int used = std::min(hcnt->nslots, scr.nslots);
+            ensure_simplices((long long)hcnt->ntets);
+            if (opt.verbose > 2) debug_footprints(nw);
+            RetriArgs<D> ra{mesh, scr, act, opt.stats};
+            prof.start(2, stream);
+            VOR_LAUNCH(RetriArgs<D>, retri_body<D>, nw, ra, stream);
+            prof.stop(stream);
+            const int dropped = hcnt->ndup - ndup0;
+            pending -= nw + dropped;
+            insertedTotal += nw;
+            rs.rounds++;
+            rs.attempts += (unsigned long long)used;
+            rs.winners += (unsigned long long)nw;
+            epoch--;
+            if (opt.verbose > 1)
+                fprintf(stderr, "[vor] stage [%d,%d) round %llu: nact %d pending %d attempts %d winners %d ntets %d\n", lo, hi, rs.rounds, nact,
+                        pending, used, nw, hcnt->ntets);
+            if (opt.verbose > 2) {
+                int f[8];
+                validate(f);
+                if (f[0] | f[1] | f[2] | f[3] | f[4]) {
+                    fprintf(stderr, "[vor] VALIDATION FAILED after round %llu: %d %d %d %d %d\n", rs.rounds, f[0], f[1], f[2], f[3], f[4]);
+                    fail(ERR_CUDA, "debug validation failed");
+                }
+            }
+            if (nw + dropped == 0) {
+                if (++stall > 64) fail(ERR_WALK, "no progress in 64 consecutive rounds");
+            } else stall = 0;
+            if (pending > 0 && nact > 4096 && pending < nact / 2) {
+                nact = compact_active(nact);
+                if (nact != pending) fail(ERR_CUDA, "active list compaction lost points");
+            }
+        }
+        if (opt.verbose)
+            fprintf(stderr, "[vor] stage [%d,%d) done: rounds so far %llu, simplices %d\n", lo, hi, rs.rounds, hcnt->ntets);
+    }
+
+    // debug: winners' footprints must be pairwise disjoint (host check, small cases only)
+    void debug_footprints(int nw) {
+        std::vector<int> win(nw), wb(nw);
+        be::d2h(win.data(), scr.winners, sizeof(int) * nw, stream);
+        be::sync(stream);
+        std::vector<std::pair<int, int>> seen; // (tet, winner)
+        for (int w = 0; w < nw; w++) {
+            int slot = win[w], nk, nb, big;
+            be::d2h(&nk, scr.slotNk + slot, 4, stream); be::d2h(&nb, scr.slotNb + slot, 4, stream); be::d2h(&big, scr.slotBig + slot, 4, stream);
+            be::sync(stream);
+            ScrView sv = scr_view(scr, slot, big);
+            { int a; be::d2h(&a, scr.slotAct + slot, 4, stream); be::sync(stream); int v; be::d2h(&v, act + a, 4, stream); be::sync(stream);
+              fprintf(stderr, "[vor] winner %d slot %d a %d v %d nk %d nb %d big %d\n", w, slot, a, v, nk, nb, big); }
+            for (int j = 0; j < nk; j++) { int t; be::d2h(&t, sv.k + (size_t)j * sv.stride, 4, stream); be::sync(stream); seen.push_back({t, w}); }
+            for (int j = 0; j < nb; j++) { int c; be::d2h(&c, sv.o + (size_t)j * sv.stride, 4, stream); be::sync(stream); if (c >= 0) seen.push_back({c >> 2, w}); }
+        }
+        std::sort(seen.begin(), seen.end());
+        for (size_t i = 1; i < seen.size(); i++)
+            if (seen[i].first == seen[i - 1].first && seen[i].second != seen[i - 1].second)
+                fprintf(stderr, "[vor] OVERLAP: simplex %d in footprints of winners %d and %d\n", seen[i].first, seen[i - 1].second, seen[i].second);
+    }
+
+    int compact_active(int nact) {
+        const int chunk = 256;
+        const int nb = (nact + chunk - 1) / chunk;
+        CompactArgs ca{act, mesh.seed, act2, blockCnt, nact, chunk};
+        VOR_LAUNCH(CompactArgs, compact_count_body, nb, ca, stream);
+        ScanArgs sa{nullptr, blockCnt, 0, 0, nb, d_misc};
+        VOR_LAUNCH(ScanArgs, scan_serial_body, 1, sa, stream);
+        VOR_LAUNCH(CompactArgs, compact_scatter_body, nb, ca, stream);
+        long long total = 0;
+        be::d2h(&total, d_misc, sizeof(long long), stream);
+        be::sync(stream);
+        std::swap(act, act2);
+        rs.compactions++;
+        return (int)total;
+    }
+
+    // ------------------------------------------------------------------ outputs
+    void invalidate_outputs() {
+        be::dfree(d_edges);
+        d_edges = nullptr;
+        nedges = -1;
+    }
+
+    // exclusive scan of a[0..n) in place; returns the total
+    long long scan_exclusive(int *a, int n) {
+        const int chunk = 1024;
+        const int nch = (n + chunk - 1) / chunk;
+        int *sums = (int *)be::dmalloc(sizeof(int) * (size_t)std::max(nch, 1));
+        long long *d_total = (long long *)be::dmalloc(sizeof(long long));
+        ScanArgs sa{a, sums, n, chunk, nch, d_total};
+        VOR_LAUNCH(ScanArgs, scan_sum_body, nch, sa, stream);
+        VOR_LAUNCH(ScanArgs, scan_serial_body, 1, sa, stream);
+        VOR_LAUNCH(ScanArgs, scan_apply_body, nch, sa, stream);
+        long long total = 0;
+        be::d2h(&total, d_total, sizeof(long long), stream);
+        be::sync(stream);
+        be::dfree(sums);
+        be::dfree(d_total);
+        return total;
+    }
+
+    // canonical edge list on the device; returns the number of edges
+    long long edges() {
+        if (nedges >= 0) return nedges;
+        const int nt = hcnt->ntets;
+        int *deg = (int *)be::dmalloc(sizeof(int) * (size_t)(ninput + 1));
+        int *cursor = (int *)be::dmalloc(sizeof(int) * (size_t)(ninput + 1));
+        be::dmemset(deg, 0, sizeof(int) * (size_t)(ninput + 1), stream);
+        be::dmemset(cursor, 0, sizeof(int) * (size_t)(ninput + 1), stream);
+        EdgeArgs<D> ea{mesh, inputIdx, deg, cursor, nullptr, 0};
+        VOR_LAUNCH(EdgeArgs<D>, edges_body<D>, nt, ea, stream);
+        const long long total = scan_exclusive(deg, ninput + 1);
+        if (total > 0x7fffffffLL) fail(ERR_OOM, "more than 2^31 edges");
+        uint32_t *hi = (uint32_t *)be::dmalloc(sizeof(uint32_t) * (size_t)std::max(total, 1LL));
+        d_edges = (uint32_t *)be::dmalloc(sizeof(uint32_t) * 2 * (size_t)std::max(total, 1LL));
+        ea.hi = hi;
+        ea.pass = 1;
+        VOR_LAUNCH(EdgeArgs<D>, edges_body<D>, nt, ea, stream);
+        RowSortArgs ra{deg, hi, d_edges, ninput};
+        VOR_LAUNCH(RowSortArgs, row_sort_body, ninput, ra, stream);
+        be::sync(stream);
+        be::dfree(deg); be::dfree(cursor); be::dfree(hi);
+        nedges = total;
+        return nedges;
+    }
+    void copy_edges(uint32_t *h_out, long long cap) {
+        const long long m = edges();
+        be::d2h(h_out, d_edges, sizeof(uint32_t) * 2 * (size_t)std::min(m, cap), stream);
+        be::sync(stream);
+    }
+    unsigned long long edge_checksum() {
+        const long long m = edges();
+        unsigned long long *d_sum = (unsigned long long *)be::dmalloc(sizeof(unsigned long long));
+        be::dmemset(d_sum, 0, sizeof(unsigned long long), stream);
+        EdgeSumArgs ea{d_edges, d_sum};
+        VOR_LAUNCH(EdgeSumArgs, edge_sum_body, m, ea, stream);
+        unsigned long long h = 0;
+        be::d2h(&h, d_sum, sizeof(h), stream);
+        be::sync(stream);
+        be::dfree(d_sum);
+        return h;
+    }
+
+    // fail[0..4] as in ValidateArgs; returns number of live simplices
+    unsigned long long validate(int *fail_out) {
+        int *d_fail = (int *)be::dmalloc(sizeof(int) * 8);
+        unsigned long long *d_live = (unsigned long long *)be::dmalloc(sizeof(unsigned long long));
+        be::dmemset(d_fail, 0, sizeof(int) * 8, stream);
+        be::dmemset(d_live, 0, sizeof(unsigned long long), stream);
+        ValidateArgs<D> va{mesh, d_fail, d_live};
+        VOR_LAUNCH(ValidateArgs<D>, validate_body<D>, hcnt->ntets, va, stream);
+        unsigned long long live = 0;
+        be::d2h(fail_out, d_fail, sizeof(int) * 8, stream);
+        be::d2h(&live, d_live, sizeof(live), stream);
+        be::sync(stream);
+        be::dfree(d_fail);
+        be::dfree(d_live);
+        pull_counters();
+        return live;
+    }
+
+    // compact export of live simplices; vertex ids: super k -> k, input i -> idOffset + i.  Returns the count.
+    // Any output pointer may be null.  Two-phase use: call with all null to get the count.
+    int export_simplices(int *h_verts, int *h_nbrs, double *h_center, double *h_radius, int idOffset) {
+        const int nt = hcnt->ntets;
+        int *d_count = (int *)be::dmalloc(sizeof(int));
+        int *liveId = (int *)be::dmalloc(sizeof(int) * (size_t)nt);
+        int *compactOf = (int *)be::dmalloc(sizeof(int) * (size_t)nt);
+        be::dmemset(d_count, 0, sizeof(int), stream);
+        ExportArgs<D> xa{mesh, d_count, liveId, compactOf};
+        VOR_LAUNCH(ExportArgs<D>, export_mark_body<D>, nt, xa, stream);
+        int n = 0;
+        be::d2h(&n, d_count, sizeof(int), stream);
+        be::sync(stream);
+        if (h_verts || h_nbrs || h_center || h_radius) {
+            int *d_verts = (int *)be::dmalloc(sizeof(int) * (size_t)n * M);
+            int *d_nbrs = (int *)be::dmalloc(sizeof(int) * (size_t)n * M);
+            double *d_c = h_center ? (double *)be::dmalloc(sizeof(double) * (size_t)n * D) : nullptr;
+            double *d_r = h_center ? (double *)be::dmalloc(sizeof(double) * (size_t)n) : nullptr;
+            ExportFillArgs<D> fa{mesh, liveId, compactOf, inputIdx, d_verts, d_nbrs, d_c, d_r, idOffset};
+            VOR_LAUNCH(ExportFillArgs<D>, export_fill_body<D>, n, fa, stream);
+            if (h_verts) be::d2h(h_verts, d_verts, sizeof(int) * (size_t)n * M, stream);
+            if (h_nbrs) be::d2h(h_nbrs, d_nbrs, sizeof(int) * (size_t)n * M, stream);
+            if (h_center) be::d2h(h_center, d_c, sizeof(double) * (size_t)n * D, stream);
+            if (h_radius && d_r) be::d2h(h_radius, d_r, sizeof(double) * (size_t)n, stream);
+            be::sync(stream);
+            be::dfree(d_verts); be::dfree(d_nbrs); be::dfree(d_c); be::dfree(d_r);
+        }
+        be::dfree(d_count); be::dfree(liveId); be::dfree(compactOf);
+        return n;
+    }
+};
+
+} // namespace vor

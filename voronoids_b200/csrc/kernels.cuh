@@ -1,0 +1,456 @@
+// kernels.cuh -- kernel bodies of the parallel incremental Delaunay engine
+// (dimension-generic: D=3 tetrahedra / in-sphere, D=2 triangles / in-circle).
+//
+// Hot path named by BASELINE.json north_star, reference side:
+//   locate + find_all_neighbors   /root/reference/src/delaunay_tree.rs:33-75     -> attempt_body (walk + flood)
+//   make_queue / find_placement   /root/reference/src/scheduler.rs:6-55          -> atomicMin reservation in attempt_body,
+//                                                                                   ownership check in check_body
+//   get_new_simplices             /root/reference/src/delaunay_tree.rs:77-123    -> boundary facets recorded by the flood
+//   insert_points_parallel        /root/reference/src/delaunay_tree.rs:213-334   -> check_body (allocator) + retri_body
+//   pair_simplices                /root/reference/src/delaunay_tree.rs:674-695   -> edge/vertex pivot inside the cavity (retri_body)
+//
+// Store (SoA, all in HBM):
+//   pts[v]    coordinates (double4 in 3D: one 32 B sector per vertex; double2 in 2D)
+//   tv[t]     int4 vertex ids of simplex t (2D uses x,y,z)
+//   tn[t]     int4 neighbour codes: (neighbour << 2 | slot in neighbour that points back), -1 = outside the
+//             super simplex; slot i is opposite vertex i.  The reference keeps an unordered Vec (delaunay_tree.rs:15).
+//   owner[t]  >= 0: reservation key of the current round (OWNER_FREE when untouched)
+//             <  0: simplex is dead, ~owner = a simplex created by the insertion that killed it (forwarding)
+//   seed[v]   pending point: a simplex to start its walk from; -1 once inserted
+//   ptTet[v]  a simplex created by v's insertion (seed for later points near v)
+//
+// A round (host loop in engine.cuh):
+//   attempt  one thread per pending point selected this round: follow forwarding, visibility walk to the
+//            containing simplex, flood the conflict region with exact in-sphere tests, atomicMin the point's
+//            priority key on every killed simplex (key) and every surviving neighbour across the cavity
+//            boundary (key|1); give up as soon as a better key is seen.
+//   check    a point wins iff it still owns its whole footprint; winners are compacted and get a block of new
+//            simplex slots from the bump allocator (warp prefix sum + one atomic per warp).
+//   retri    winners only: write new simplices, patch outer back-pointers, link siblings by pivoting around the
+//            shared edge (3D) / vertex (2D) through the dead cavity, then mark the cavity dead with forwarding.
+// Two winners of one round have disjoint footprints (killed + outer ring), so their writes never overlap and the
+// conflict region of one is unchanged by the other (new circumspheres lie inside the union of the two old ones).
+#pragma once
+#include "predicates.cuh"
+
+namespace vor {
+
+template <int D> struct Dim;
+template <> struct Dim<3> { using Pt = double4; static constexpr int M = 4; };
+template <> struct Dim<2> { using Pt = double2; static constexpr int M = 3; };
+
+template <int D> struct Mesh {
+    typename Dim<D>::Pt *pts;
+    int4 *tv;
+    int4 *tn;
+    int *owner;
+    int *seed;
+    int *ptTet;
+    Counters *cnt;
+    int cap;      // simplex slots allocated
+    int nsuper;   // vertices [0, nsuper) are super vertices
+};
+
+struct Scratch {
+    int *killed, *bfacet, *bouter;     // interleaved: entry j of slot s at [j * nslots + s]
+    int *slotAct, *slotNk, *slotNb, *slotStatus, *slotBig;
+    int nslots, capk, capb;
+    int *bigK, *bigF, *bigO;           // overflow slots, contiguous per slot
+    int nbig, bigCapK, bigCapB;
+    int *winners, *wbase;
+};
+
+enum : int { ST_LOST = 0, ST_OK = 1 };
+
+struct ScrView { int *k, *f, *o; int stride, capk, capb; };
+VOR_HD ScrView scr_view(const Scratch &s, int slot, int big) {
+    ScrView v;
+    if (big < 0) {
+        v.k = s.killed + slot; v.f = s.bfacet + slot; v.o = s.bouter + slot;
+        v.stride = s.nslots; v.capk = s.capk; v.capb = s.capb;
+    } else {
+        v.k = s.bigK + (size_t)big * s.bigCapK; v.f = s.bigF + (size_t)big * s.bigCapB; v.o = s.bigO + (size_t)big * s.bigCapB;
+        v.stride = 1; v.capk = s.bigCapK; v.capb = s.bigCapB;
+    }
+    return v;
+}
+
+// warp-aggregated increment of a global counter (one atomic per warp)
+VOR_HD int agg_inc(int *ctr) {
+#ifdef __CUDA_ARCH__
+    const unsigned mask = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(ctr, __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+#else
+    return atomic_add_i(ctr, 1);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// geometry helpers on the store
+// ------------------------------------------------------------------------------------------
+template <int D> struct Geo;
+
+template <> struct Geo<3> {
+    using Pt = double4;
+    struct Verts { Pt p0, p1, p2, p3; };
+    static VOR_HD Verts load(const Mesh<3> &m, const int4 &v) {
+        Verts r; r.p0 = m.pts[v.x]; r.p1 = m.pts[v.y]; r.p2 = m.pts[v.z]; r.p3 = m.pts[v.w]; return r;
+    }
+    // bit i set <=> p is strictly beyond face i (orientation with vertex i replaced by p is negative)
+    static VOR_HD int beyond_mask(PredCtx &cx, const Verts &t, const Pt &p) {
+        int mk = 0;
+        if (orient3d(cx, p, t.p1, t.p2, t.p3) < 0) mk |= 1;
+        if (orient3d(cx, t.p0, p, t.p2, t.p3) < 0) mk |= 2;
+        if (orient3d(cx, t.p0, t.p1, p, t.p3) < 0) mk |= 4;
+        if (orient3d(cx, t.p0, t.p1, t.p2, p) < 0) mk |= 8;
+        return mk;
+    }
+    static VOR_HD int conflict(PredCtx &cx, const Verts &t, const Pt &p) { return insphere(cx, t.p0, t.p1, t.p2, t.p3, p) > 0; }
+    static VOR_HD int orient(PredCtx &cx, const Verts &t) { return orient3d(cx, t.p0, t.p1, t.p2, t.p3); }
+};
+
+template <> struct Geo<2> {
+    using Pt = double2;
+    struct Verts { Pt p0, p1, p2; };
+    static VOR_HD Verts load(const Mesh<2> &m, const int4 &v) {
+        Verts r; r.p0 = m.pts[v.x]; r.p1 = m.pts[v.y]; r.p2 = m.pts[v.z]; return r;
+    }
+    static VOR_HD int beyond_mask(PredCtx &cx, const Verts &t, const Pt &p) {
+        int mk = 0;
+        if (orient2d(cx, p, t.p1, t.p2) < 0) mk |= 1;
+        if (orient2d(cx, t.p0, p, t.p2) < 0) mk |= 2;
+        if (orient2d(cx, t.p0, t.p1, p) < 0) mk |= 4;
+        return mk;
+    }
+    static VOR_HD int conflict(PredCtx &cx, const Verts &t, const Pt &p) { return incircle(cx, t.p0, t.p1, t.p2, p) > 0; }
+    static VOR_HD int orient(PredCtx &cx, const Verts &t) { return orient2d(cx, t.p0, t.p1, t.p2); }
+};
+
+// ------------------------------------------------------------------------------------------
+// attempt: locate + conflict region + reservation
+// ------------------------------------------------------------------------------------------
+template <int D> struct AttemptArgs {
+    Mesh<D> m;
+    Scratch scr;
+    const int *act;     // pending vertex ids of this stage
+    int bits;           // priority bits (2^bits >= number of active entries)
+    uint32_t salt;      // per-round salt of the priority hash
+    uint32_t thr;       // attempt iff priority < thr
+    int keybase;        // epoch << (bits + 1)
+    int stats;          // accumulate W/E counters
+};
+
+template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
+    constexpr int M = Dim<D>::M;
+    using G = Geo<D>;
+    const Mesh<D> &m = A.m;
+    const int v = A.act[a];
+    int s = m.seed[v];
+    if (s < 0) return;                                   // already inserted
+    const uint32_t q = bij_hash((uint32_t)a, A.bits, A.salt);
+    if (q >= A.thr) return;                              // not selected this round
+    const int slot = agg_inc(&m.cnt->nslots);
+    if (slot >= A.scr.nslots) return;                    // scratch exhausted: wait for a later round
+    A.scr.slotAct[slot] = a;
+    A.scr.slotStatus[slot] = ST_LOST;
+    A.scr.slotBig[slot] = -1;
+    PredCtx cx{m.cnt};
+    const typename G::Pt p = m.pts[v];
+
+    // -- forwarding: a dead seed points at a simplex created by its killer
+    int o;
+    while ((o = m.owner[s]) < 0) s = ~o;
+
+    // -- visibility walk
+    unsigned rot = (unsigned)v * 2654435761u;
+    unsigned steps = 0;
+    typename G::Verts tvv = G::load(m, m.tv[s]);
+    for (;;) {
+        const int mk = G::beyond_mask(cx, tvv, p);
+        if (mk == 0) break;
+        int go = 0;
+        const int r0 = (int)((rot >> 16) % (unsigned)M);
+        for (int k = 0; k < M; k++) {
+            const int i = (r0 + k) % M;
+            if ((mk >> i) & 1) { go = i; break; }
+        }
+        const int code = get4(m.tn[s], go);
+        if (code < 0) { set_err(m.cnt, ERR_OUTSIDE); return; }
+        s = code >> 2;
+        rot = rot * 1664525u + 1013904223u;
+        if (++steps > (1u << 22)) { set_err(m.cnt, ERR_WALK); return; }
+        tvv = G::load(m, m.tv[s]);
+    }
+    m.seed[v] = s;
+
+    // -- conflict region with reservation
+    const int key_k = A.keybase | (int)(q << 1);
+    const int key_o = key_k | 1;
+    unsigned tests = 1;
+    if (!G::conflict(cx, tvv, p)) {
+        // p coincides with a vertex of its containing simplex: duplicate input point.  Drop it.
+        m.seed[v] = -1;
+        atomic_add_i(&m.cnt->ndup, 1);
+        return;
+    }
+    if (atomic_min_i(&m.owner[s], key_k) < key_k) goto lost;
+    {
+        ScrView sv = scr_view(A.scr, slot, -1);
+        int big = -1;
+        int nk = 1, nb = 0;
+        sv.k[0] = s;
+        for (int head = 0; head < nk; head++) {
+            const int t = sv.k[(size_t)head * sv.stride];
+            const int4 nbr = m.tn[t];
+            for (int i = 0; i < M; i++) {
+                const int code = get4(nbr, i);
+                int isout = 1;
+                if (code >= 0) {
+                    const int n = code >> 2;
+                    const int ow = m.owner[n];
+                    if (ow == key_k) continue;               // already in my cavity
+                    if (ow < key_k) goto lost;               // a better point holds it
+                    if (ow != key_o) {                       // not yet classified by me
+                        tests++;
+                        const typename G::Verts nv = G::load(m, m.tv[n]);
+                        if (G::conflict(cx, nv, p)) {
+                            if (atomic_min_i(&m.owner[n], key_k) < key_k) goto lost;
+                            isout = 0;
+                            if (nk == sv.capk) {
+                                if (big >= 0) { set_err(m.cnt, ERR_CAPACITY); goto lost; }
+                                big = atomic_add_i(&m.cnt->nbig, 1);
+                                if (big >= A.scr.nbig) goto lost;
+                                const ScrView bv = scr_view(A.scr, slot, big);
+                                for (int j = 0; j < nk; j++) bv.k[j] = sv.k[(size_t)j * sv.stride];
+                                for (int j = 0; j < nb; j++) { bv.f[j] = sv.f[(size_t)j * sv.stride]; bv.o[j] = sv.o[(size_t)j * sv.stride]; }
+                                sv = bv;
+                                A.scr.slotBig[slot] = big;
+                            }
+                            sv.k[(size_t)nk * sv.stride] = n;
+                            nk++;
+                        } else {
+                            if (atomic_min_i(&m.owner[n], key_o) < key_k) goto lost;
+                        }
+                    }
+                }
+                if (isout) {
+                    if (nb == sv.capb) {
+                        if (big >= 0) { set_err(m.cnt, ERR_CAPACITY); goto lost; }
+                        big = atomic_add_i(&m.cnt->nbig, 1);
+                        if (big >= A.scr.nbig) goto lost;
+                        const ScrView bv = scr_view(A.scr, slot, big);
+                        for (int j = 0; j < nk; j++) bv.k[j] = sv.k[(size_t)j * sv.stride];
+                        for (int j = 0; j < nb; j++) { bv.f[j] = sv.f[(size_t)j * sv.stride]; bv.o[j] = sv.o[(size_t)j * sv.stride]; }
+                        sv = bv;
+                        A.scr.slotBig[slot] = big;
+                    }
+                    sv.f[(size_t)nb * sv.stride] = t * 4 + i;
+                    sv.o[(size_t)nb * sv.stride] = code;
+                    nb++;
+                }
+            }
+        }
+        A.scr.slotNk[slot] = nk;
+        A.scr.slotNb[slot] = nb;
+        A.scr.slotStatus[slot] = ST_OK;
+        if (A.stats) {
+            atomic_add_ull(&m.cnt->walk_steps, steps);
+            atomic_add_ull(&m.cnt->tests, tests);
+            atomic_add_ull(&m.cnt->attempts, 1ULL);
+        }
+        return;
+    }
+lost:
+    if (A.stats) {
+        atomic_add_ull(&m.cnt->walk_steps, steps);
+        atomic_add_ull(&m.cnt->tests, tests);
+        atomic_add_ull(&m.cnt->attempts, 1ULL);
+        atomic_add_ull(&m.cnt->aborted, 1ULL);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// check: ownership of the whole footprint -> winners, simplex slot allocation
+// ------------------------------------------------------------------------------------------
+template <int D> struct CheckArgs {
+    Mesh<D> m;
+    Scratch scr;
+    int bits;
+    uint32_t salt;
+    int keybase;
+};
+
+// `valid` = tid addresses a claimed slot.  No early return before the allocation so that whole warps reach it.
+template <int D> VOR_HD void check_body(const CheckArgs<D> &A, int slot, bool valid) {
+    const Mesh<D> &m = A.m;
+    int win = 0, nb = 0;
+    // the launch covers an upper bound of slots; only those claimed THIS round hold current data
+    if (valid && slot < m.cnt->nslots && slot < A.scr.nslots && A.scr.slotStatus[slot] == ST_OK) {
+        const int a = A.scr.slotAct[slot];
+        const uint32_t q = bij_hash((uint32_t)a, A.bits, A.salt);
+        const int key_k = A.keybase | (int)(q << 1);
+        const int key_o = key_k | 1;
+        const ScrView sv = scr_view(A.scr, slot, A.scr.slotBig[slot]);
+        const int nk = A.scr.slotNk[slot];
+        nb = A.scr.slotNb[slot];
+        win = 1;
+        for (int j = 0; j < nk && win; j++)
+            if (m.owner[sv.k[(size_t)j * sv.stride]] != key_k) win = 0;
+        for (int j = 0; j < nb && win; j++) {
+            const int code = sv.o[(size_t)j * sv.stride];
+            if (code >= 0 && m.owner[code >> 2] != key_o) win = 0;
+        }
+    }
+#ifdef __CUDA_ARCH__
+    // warp prefix sums of (win, nb) -> one atomic pair per warp
+    const int lane = threadIdx.x & 31;
+    const unsigned wmask = __ballot_sync(0xffffffffu, win);
+    if (wmask == 0) return;
+    int incl = win ? nb : 0;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int wb = 0, tb = 0;
+    if (lane == 0) {
+        wb = atomicAdd(&m.cnt->nwinners, __popc(wmask));
+        tb = atomicAdd(&m.cnt->ntets, total);
+    }
+    wb = __shfl_sync(0xffffffffu, wb, 0);
+    tb = __shfl_sync(0xffffffffu, tb, 0);
+    if (win) {
+        const int w = wb + __popc(wmask & ((1u << lane) - 1u));
+        A.scr.winners[w] = slot;
+        A.scr.wbase[w] = tb + incl - nb;
+    }
+#else
+    if (win) {
+        const int w = atomic_add_i(&m.cnt->nwinners, 1);
+        A.scr.winners[w] = slot;
+        A.scr.wbase[w] = atomic_add_i(&m.cnt->ntets, nb);
+    }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// retriangulate: winners write their new simplices and repair adjacency
+// ------------------------------------------------------------------------------------------
+template <int D> struct RetriArgs {
+    Mesh<D> m;
+    Scratch scr;
+    const int *act;
+    int stats;
+};
+
+template <int D> VOR_HD void retri_body(const RetriArgs<D> &A, int w) {
+    constexpr int M = Dim<D>::M;
+    const Mesh<D> &m = A.m;
+    const int slot = A.scr.winners[w];
+    const int base = A.scr.wbase[w];
+    const int a = A.scr.slotAct[slot];
+    const int v = A.act[a];
+    const ScrView sv = scr_view(A.scr, slot, A.scr.slotBig[slot]);
+    const int nk = A.scr.slotNk[slot];
+    const int nb = A.scr.slotNb[slot];
+    if (base + nb > m.cap) { set_err(m.cnt, ERR_OOM); return; }
+
+    // phase A: new simplex j hangs on boundary facet j; link it to the outer simplex and leave a marker
+    // -(code)-2 in the dead simplex so that the pivots of phase B can find it.
+    int *tn_i = reinterpret_cast<int *>(m.tn);
+    for (int j = 0; j < nb; j++) {
+        const int fc = sv.f[(size_t)j * sv.stride];
+        const int t = fc >> 2, i = fc & 3;
+        const int outer = sv.o[(size_t)j * sv.stride];
+        const int T = base + j;
+        int4 verts = m.tv[t];
+        set4(verts, i, v);
+        m.tv[T] = verts;
+        tn_i[(size_t)T * 4 + i] = outer;
+        if (M == 3) tn_i[(size_t)T * 4 + 3] = -1;
+        if (outer >= 0) tn_i[(size_t)(outer >> 2) * 4 + (outer & 3)] = T * 4 + i;
+        tn_i[(size_t)t * 4 + i] = -(T * 4 + i) - 2;
+    }
+    // phase B: sibling links.  The face of T opposite slot k (k != i) contains v and the ridge R = T's vertices
+    // other than slots i,k.  Pivot around R through the dead cavity until a marker is met.
+    for (int j = 0; j < nb; j++) {
+        const int fc = sv.f[(size_t)j * sv.stride];
+        const int t = fc >> 2, i = fc & 3;
+        const int T = base + j;
+        const int4 tverts = m.tv[t];
+        for (int k = 0; k < M; k++) {
+            if (k == i) continue;
+            int cur = t, enter = i, exitf = k;
+            int4 cv = tverts;
+            // ridge vertices (D-1 of them): slots of t other than i,k
+            int r0 = -1, r1 = -1;
+            for (int sidx = 0; sidx < M; sidx++) {
+                if (sidx == i || sidx == k) continue;
+                if (r0 < 0) r0 = get4(cv, sidx); else r1 = get4(cv, sidx);
+            }
+            for (;;) {
+                const int e = tn_i[(size_t)cur * 4 + exitf];
+                if (e <= -2) {
+                    const int sc = -(e + 2);
+                    tn_i[(size_t)T * 4 + k] = (sc >> 2) * 4 + enter;
+                    break;
+                }
+                const int nxt = e >> 2, jb = e & 3;
+                cv = m.tv[nxt];
+                int y = -1;
+                for (int sidx = 0; sidx < M; sidx++) {
+                    if (sidx == jb) continue;
+                    const int vv = get4(cv, sidx);
+                    if (vv != r0 && vv != r1) y = sidx;
+                }
+                cur = nxt; enter = jb; exitf = y;
+            }
+        }
+    }
+    // phase C: the cavity dies; dead simplices forward to a new one
+    for (int j = 0; j < nk; j++) m.owner[sv.k[(size_t)j * sv.stride]] = ~base;
+    m.ptTet[v] = base;
+    m.seed[v] = -1;
+    if (A.stats) {
+        atomic_add_ull(&m.cnt->killed, (unsigned long long)nk);
+        atomic_add_ull(&m.cnt->created, (unsigned long long)nb);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// small maintenance kernels
+// ------------------------------------------------------------------------------------------
+struct ResetOwnerArgs { int *owner; };
+VOR_HD void reset_owner_body(const ResetOwnerArgs &A, int t) {
+    if (A.owner[t] >= 0) A.owner[t] = OWNER_FREE;
+}
+
+struct FillArgs { int *p; int val; };
+VOR_HD void fill_body(const FillArgs &A, int i) { A.p[i] = A.val; }
+
+struct IotaArgs { int *p; int first; };
+VOR_HD void iota_body(const IotaArgs &A, int i) { A.p[i] = A.first + i; }
+
+// order-preserving compaction of the active list (3 passes: count, scan of block counts, scatter)
+struct CompactArgs { const int *act; const int *seed; int *out; int *blockCnt; int n; int chunk; };
+VOR_HD void compact_count_body(const CompactArgs &A, int b) {
+    const int lo = b * A.chunk, hi = lo + A.chunk < A.n ? lo + A.chunk : A.n;
+    int c = 0;
+    for (int i = lo; i < hi; i++) c += A.seed[A.act[i]] >= 0;
+    A.blockCnt[b] = c;
+}
+VOR_HD void compact_scatter_body(const CompactArgs &A, int b) {
+    const int lo = b * A.chunk, hi = lo + A.chunk < A.n ? lo + A.chunk : A.n;
+    int w = A.blockCnt[b]; // exclusive prefix after the scan
+    for (int i = lo; i < hi; i++) {
+        const int v = A.act[i];
+        if (A.seed[v] >= 0) A.out[w++] = v;
+    }
+}
+
+} // namespace vor

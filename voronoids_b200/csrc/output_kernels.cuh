@@ -1,0 +1,281 @@
+// output_kernels.cuh -- Delaunay-graph extraction, validation and export.
+//
+//   edges      SURVEY.md §8a row G.  The reference has no extraction function: the graph is implicit in
+//              DelaunayTree.simplices[*].vertices and rebuilt as Python dicts on every getter call
+//              (/root/reference/src/lib.rs:73-101).  Definition adopted: {lo,hi} input indices of two real vertices that
+//              share a live simplex, lo<hi, lexicographically sorted, unique, little-endian u32 pairs.
+//              Each edge is emitted once, by the lowest-numbered simplex of the ring around it (3D: pivot around
+//              the edge; 2D: the lower of the two triangles), into CSR rows keyed by lo, then rows are sorted.
+//   validate   structural + local-Delaunay check of every live simplex (local Delaunay on every interior facet is
+//              equivalent to the reference's brute-force check_delaunay, delaunay_tree.rs:512-541, but O(S)).
+//   circumsphere / export: the reference caches center/radius per simplex (delaunay_tree.rs:11-16); here they are
+//              computed on demand for the Python getters with the reference's own formulas (geometry.rs:2-56).
+#pragma once
+#include "kernels.cuh"
+
+namespace vor {
+
+template <int D> VOR_HD bool simplex_live(const Mesh<D> &m, int t) { return m.owner[t] >= 0; }
+
+template <int D> struct EdgeArgs {
+    Mesh<D> m;
+    const int *inputIdx;   // vertex -> global input index
+    int *deg;              // [nInput+1] row sizes, then exclusive offsets
+    int *cursor;           // [nInput] fill cursors
+    uint32_t *hi;          // CSR column array
+    int pass;              // 0 = count, 1 = fill
+};
+
+// true if simplex t is the lowest-numbered simplex around edge (slots sa, sb) -- 3D pivot around the edge
+VOR_HD bool edge_owner3(const Mesh<3> &m, int t, const int4 &tv, int sa, int sb) {
+    const int a = get4(tv, sa), b = get4(tv, sb);
+    // leave t through the face opposite the first of the two other slots
+    int exitf = -1, enterf = -1;
+    for (int s = 0; s < 4; s++) {
+        if (s == sa || s == sb) continue;
+        if (exitf < 0) exitf = s; else enterf = s;
+    }
+    (void)enterf;
+    int cur = t;
+    for (int guard = 0; guard < (1 << 20); guard++) {
+        const int code = get4(m.tn[cur], exitf);
+        if (code < 0) return false; // cannot happen for an edge of two real vertices
+        const int nxt = code >> 2, jb = code & 3;
+        if (nxt == t) return true;
+        if (nxt < t) return false;
+        const int4 nv = m.tv[nxt];
+        int y = -1;
+        for (int s = 0; s < 4; s++) {
+            if (s == jb) continue;
+            const int vv = get4(nv, s);
+            if (vv != a && vv != b) y = s;
+        }
+        cur = nxt;
+        exitf = y;
+    }
+    return false;
+}
+
+template <int D> VOR_HD void edge_emit(const EdgeArgs<D> &A, int va, int vb) {
+    const int ia = A.inputIdx[va], ib = A.inputIdx[vb];
+    const int lo = ia < ib ? ia : ib, hi = ia < ib ? ib : ia;
+    if (A.pass == 0) atomic_add_i(&A.deg[lo], 1);
+    else {
+        const int w = atomic_add_i(&A.cursor[lo], 1);
+        A.hi[(size_t)A.deg[lo] + w] = (uint32_t)hi;
+    }
+}
+
+template <int D> VOR_HD void edges_body(const EdgeArgs<D> &A, int t) {
+    constexpr int M = Dim<D>::M;
+    const Mesh<D> &m = A.m;
+    if (!simplex_live(m, t)) return;
+    const int4 tv = m.tv[t];
+    if constexpr (D == 3) {
+        for (int sa = 0; sa < M; sa++)
+            for (int sb = sa + 1; sb < M; sb++) {
+                const int va = get4(tv, sa), vb = get4(tv, sb);
+                if (va < m.nsuper || vb < m.nsuper) continue;
+                if (edge_owner3(m, t, tv, sa, sb)) edge_emit(A, va, vb);
+            }
+    } else {
+        const int4 tn = m.tn[t];
+        for (int i = 0; i < 3; i++) { // edge opposite slot i
+            const int va = get4(tv, (i + 1) % 3), vb = get4(tv, (i + 2) % 3);
+            if (va < m.nsuper || vb < m.nsuper) continue;
+            const int code = get4(tn, i);
+            if (code < 0 || t < (code >> 2)) edge_emit(A, va, vb);
+        }
+    }
+}
+
+struct RowSortArgs { const int *off; uint32_t *hi; uint32_t *out; int n; };
+// sort each CSR row (insertion sort: rows hold ~8 entries in 3D, ~3 in 2D) and write (lo,hi) pairs
+VOR_HD void row_sort_body(const RowSortArgs &A, int r) {
+    const int lo = A.off[r], hi = A.off[r + 1];
+    for (int i = lo + 1; i < hi; i++) {
+        const uint32_t x = A.hi[i];
+        int j = i - 1;
+        while (j >= lo && A.hi[j] > x) { A.hi[j + 1] = A.hi[j]; j--; }
+        A.hi[j + 1] = x;
+    }
+    for (int i = lo; i < hi; i++) { A.out[2 * (size_t)i] = (uint32_t)r; A.out[2 * (size_t)i + 1] = A.hi[i]; }
+}
+
+// order-independent checksum of the canonical edge list (bench: result read-back without copying every edge)
+struct EdgeSumArgs { const uint32_t *edges; unsigned long long *sum; };
+VOR_HD void edge_sum_body(const EdgeSumArgs &A, int i) {
+    const uint64_t k = ((uint64_t)A.edges[2 * (size_t)i] << 32) | A.edges[2 * (size_t)i + 1];
+    atomic_add_ull(A.sum, mix64(k));
+}
+
+// ---- validation
+template <int D> struct ValidateArgs {
+    Mesh<D> m;
+    int *fail;   // [8] failure counters: 0 orientation, 1 dead neighbour, 2 asymmetric adjacency, 3 facet mismatch, 4 not Delaunay
+    unsigned long long *nlive;
+};
+template <int D> VOR_HD void validate_body(const ValidateArgs<D> &A, int t) {
+    constexpr int M = Dim<D>::M;
+    using G = Geo<D>;
+    const Mesh<D> &m = A.m;
+    if (!simplex_live(m, t)) return;
+    atomic_add_ull(A.nlive, 1ULL);
+    PredCtx cx{m.cnt};
+    const int4 tv = m.tv[t];
+    const int4 tn = m.tn[t];
+    const typename G::Verts vt = G::load(m, tv);
+    if (G::orient(cx, vt) <= 0) atomic_add_i(&A.fail[0], 1);
+    for (int i = 0; i < M; i++) {
+        const int code = get4(tn, i);
+        if (code < 0) continue;
+        const int nb = code >> 2, jb = code & 3;
+        if (!simplex_live(m, nb)) { atomic_add_i(&A.fail[1], 1); continue; }
+        const int back = get4(m.tn[nb], jb);
+        if (back != t * 4 + i) { atomic_add_i(&A.fail[2], 1); continue; }
+        const int4 nv = m.tv[nb];
+        bool ok = true;
+        for (int k = 0; k < M; k++) {
+            if (k == jb) continue;
+            const int x = get4(nv, k);
+            bool found = false;
+            for (int q = 0; q < M; q++) found |= (q != i && get4(tv, q) == x);
+            ok &= found;
+        }
+        if (!ok) { atomic_add_i(&A.fail[3], 1); continue; }
+        if (G::conflict(cx, vt, m.pts[get4(nv, jb)])) atomic_add_i(&A.fail[4], 1);
+    }
+}
+
+// ---- export of live simplices (compact, unordered)
+template <int D> struct ExportArgs {
+    Mesh<D> m;
+    int *count;      // number of live simplices
+    int *liveId;     // compact index -> simplex slot
+    int *compactOf;  // simplex slot -> compact index (or -1)
+};
+template <int D> VOR_HD void export_mark_body(const ExportArgs<D> &A, int t) {
+    if (!simplex_live(A.m, t)) { A.compactOf[t] = -1; return; }
+    const int c = agg_inc(A.count);
+    A.liveId[c] = t;
+    A.compactOf[t] = c;
+}
+template <int D> struct ExportFillArgs {
+    Mesh<D> m;
+    const int *liveId;
+    const int *compactOf;
+    const int *inputIdx;
+    int *verts;      // [n x M] vertex ids: super vertex k -> k, input point i -> idOffset + i
+    int *nbrs;       // [n x M] compact neighbour index, hull facets -> -1 - (slot)  (resolved by the host)
+    double *center;  // [n x D] reference circumcentre (geometry.rs), may be null
+    double *radius;  // [n]
+    int idOffset;
+};
+VOR_HD void circum_ref(const Geo<3>::Verts &t, double *c, double *r) {
+    // geometry.rs:24-56 restated (LU with partial pivoting as in nalgebra; see oracle/ref_geometry.h)
+    const double v[12] = {t.p0.x, t.p0.y, t.p0.z, t.p1.x, t.p1.y, t.p1.z, t.p2.x, t.p2.y, t.p2.z, t.p3.x, t.p3.y, t.p3.z};
+    double a[3][3], b[3];
+    for (int i = 0; i < 3; i++) {
+        double s = 0.0;
+        for (int k = 0; k < 3; k++) {
+            a[i][k] = v[3 * (i + 1) + k] - v[k];
+            const double mid = (v[3 * (i + 1) + k] + v[k]) / 2.0;
+            s += a[i][k] * mid;
+        }
+        b[i] = s;
+    }
+    int perm[3] = {0, 1, 2};
+    for (int i = 0; i < 3; i++) {
+        int piv = i;
+        double best = fabs(a[i][i]);
+        for (int q = i + 1; q < 3; q++) if (fabs(a[q][i]) > best) { best = fabs(a[q][i]); piv = q; }
+        const double diag = a[piv][i];
+        if (diag == 0.0) continue;
+        if (piv != i) {
+            for (int k = 0; k < 3; k++) { const double tmp = a[i][k]; a[i][k] = a[piv][k]; a[piv][k] = tmp; }
+            const int tp = perm[i]; perm[i] = perm[piv]; perm[piv] = tp;
+        }
+        const double inv = 1.0 / diag;
+        for (int q = i + 1; q < 3; q++) a[q][i] *= inv;
+        for (int k = i + 1; k < 3; k++)
+            for (int q = i + 1; q < 3; q++) a[q][k] = (-a[i][k]) * a[q][i] + a[q][k];
+    }
+    double x[3] = {b[perm[0]], b[perm[1]], b[perm[2]]};
+    for (int i = 0; i < 3; i++) { const double cf = x[i]; for (int q = i + 1; q < 3; q++) x[q] = (-cf) * a[q][i] + x[q]; }
+    for (int i = 2; i >= 0; i--) { const double cf = x[i] / a[i][i]; x[i] = cf; for (int q = 0; q < i; q++) x[q] = (-cf) * a[q][i] + x[q]; }
+    c[0] = x[0]; c[1] = x[1]; c[2] = x[2];
+    *r = sqrt((v[0] - x[0]) * (v[0] - x[0]) + (v[1] - x[1]) * (v[1] - x[1]) + (v[2] - x[2]) * (v[2] - x[2]));
+}
+VOR_HD void circum_ref(const Geo<2>::Verts &t, double *c, double *r) {
+    // geometry.rs:2-22 restated
+    const double x1 = t.p0.x, y1 = t.p0.y, x2 = t.p1.x, y2 = t.p1.y, x3 = t.p2.x, y3 = t.p2.y;
+    const double d0 = (x1 + x2) / 2.0, d1 = (y1 + y2) / 2.0, e0 = (x2 + x3) / 2.0, e1 = (y2 + y3) / 2.0;
+    const double m_ab = (y2 - y1) / (x2 - x1), m_bc = (y3 - y2) / (x3 - x2);
+    const double m_d = -1. / m_ab, m_e = -1. / m_bc;
+    const double x = (m_d * d0 - m_e * e0 + e1 - d1) / (m_d - m_e);
+    const double y = m_d * (x - d0) + d1;
+    c[0] = x; c[1] = y;
+    *r = sqrt((x - x1) * (x - x1) + (y - y1) * (y - y1));
+}
+template <int D> VOR_HD void export_fill_body(const ExportFillArgs<D> &A, int c) {
+    constexpr int M = Dim<D>::M;
+    const Mesh<D> &m = A.m;
+    const int t = A.liveId[c];
+    const int4 tv = m.tv[t];
+    const int4 tn = m.tn[t];
+    for (int k = 0; k < M; k++) {
+        const int v = get4(tv, k);
+        A.verts[(size_t)c * M + k] = v < m.nsuper ? v : A.idOffset + A.inputIdx[v];
+        const int code = get4(tn, k);
+        A.nbrs[(size_t)c * M + k] = code < 0 ? -1 : A.compactOf[code >> 2];
+    }
+    if (A.center) {
+        const typename Geo<D>::Verts vt = Geo<D>::load(m, tv);
+        circum_ref(vt, A.center + (size_t)c * D, A.radius + c);
+    }
+}
+
+// ---- batched geometry entry points (reference API: geometry::{circumsphere, in_sphere})
+template <int D> struct CircumBatchArgs { const double *verts; double *center; double *radius; };
+VOR_HD void circum_batch_body(const CircumBatchArgs<3> &A, int i) {
+    const double *v = A.verts + (size_t)i * 12;
+    Geo<3>::Verts t;
+    t.p0 = double4{v[0], v[1], v[2], 0}; t.p1 = double4{v[3], v[4], v[5], 0}; t.p2 = double4{v[6], v[7], v[8], 0}; t.p3 = double4{v[9], v[10], v[11], 0};
+    circum_ref(t, A.center + (size_t)i * 3, A.radius + i);
+}
+VOR_HD void circum_batch_body(const CircumBatchArgs<2> &A, int i) {
+    const double *v = A.verts + (size_t)i * 6;
+    Geo<2>::Verts t;
+    t.p0 = double2{v[0], v[1]}; t.p1 = double2{v[2], v[3]}; t.p2 = double2{v[4], v[5]};
+    circum_ref(t, A.center + (size_t)i * 2, A.radius + i);
+}
+struct InSphereBatchArgs { const double *p; const double *c; const double *r; int *out; int dim; };
+VOR_HD void in_sphere_batch_body(const InSphereBatchArgs &A, int i) {
+    double dist = 0.0;
+    for (int k = 0; k < A.dim; k++) {
+        const double d = A.c[(size_t)i * A.dim + k] - A.p[(size_t)i * A.dim + k];
+        dist += d * d;
+    }
+    A.out[i] = dist < A.r[i] * A.r[i];
+}
+// exact predicate batches (K1/K2 of SURVEY.md §2.3): rows of M+1 (insphere) or M (orient) points
+struct PredBatchArgs { const double *rows; int *out; Counters *cnt; int kind; }; // kind: 0 orient2d 1 orient3d 2 incircle 3 insphere
+VOR_HD void pred_batch_body(const PredBatchArgs &A, int i) {
+    PredCtx cx{A.cnt};
+    if (A.kind == 0) {
+        const double *r = A.rows + (size_t)i * 6;
+        A.out[i] = orient2d(cx, double2{r[0], r[1]}, double2{r[2], r[3]}, double2{r[4], r[5]});
+    } else if (A.kind == 1) {
+        const double *r = A.rows + (size_t)i * 12;
+        A.out[i] = orient3d(cx, double4{r[0], r[1], r[2], 0}, double4{r[3], r[4], r[5], 0}, double4{r[6], r[7], r[8], 0}, double4{r[9], r[10], r[11], 0});
+    } else if (A.kind == 2) {
+        const double *r = A.rows + (size_t)i * 8;
+        A.out[i] = incircle(cx, double2{r[0], r[1]}, double2{r[2], r[3]}, double2{r[4], r[5]}, double2{r[6], r[7]});
+    } else {
+        const double *r = A.rows + (size_t)i * 15;
+        A.out[i] = insphere(cx, double4{r[0], r[1], r[2], 0}, double4{r[3], r[4], r[5], 0}, double4{r[6], r[7], r[8], 0}, double4{r[9], r[10], r[11], 0},
+                            double4{r[12], r[13], r[14], 0});
+    }
+}
+
+} // namespace vor

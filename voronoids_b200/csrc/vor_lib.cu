@@ -1,0 +1,8 @@
+// vor_lib.cu -- the single translation unit of libvoronoids_b200.so (sm_100a).
+// nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo ... (see voronoids_b200/build.py)
+#include "backend_cuda.cuh"
+#include "engine.cuh"
+
+namespace vor { namespace be { unsigned long long g_launches = 0; } }
+
+#include "capi.inl"
