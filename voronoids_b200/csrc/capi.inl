@@ -78,6 +78,9 @@ int vor_set_option(const char *name, double value) {
     else if (n == "stats") g_opts.stats = (int)value;
     else if (n == "verbose") g_opts.verbose = (int)value;
     else if (n == "profile") g_opts.profile = (int)value;
+    else if (n == "coop") g_opts.coop = (int)value;
+    else if (n == "group") g_opts.group = (int)value;
+    else if (n == "coop_switch") g_opts.coop_switch = (int)value;
     else if (n == "tet_factor") g_opts.tet_factor = value;
     else if (n == "capk") { g_opts.capk = (int)value; g_opts.capb = 2 * g_opts.capk + 4; }
     else if (n == "big_slots") g_opts.big_slots = (int)value;

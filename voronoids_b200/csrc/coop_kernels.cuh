@@ -1,0 +1,343 @@
+// coop_kernels.cuh -- lane-group-cooperative versions of the three round kernels (CUDA only).
+//
+// G lanes (G = 32: a whole warp, north_star's "one warp per point"; G = 8 when a round has many points) work on ONE
+// pending point.  The serial dependency chain of the thread-per-point bodies in kernels.cuh (one in-sphere test after
+// the other: ~60-100 tests x 3-4 dependent gathers each) becomes one chain per BFS LEVEL of the conflict region:
+//   attempt  walk: lane k evaluates the orientation of facet k (ballot -> facet to cross);
+//            flood: each lane takes one (frontier simplex, facet) item: gathers the neighbour code, its owner word, its
+//            4 vertex records (32 B sectors) and evaluates the exact in-sphere test; reservation by atomicMin; new killed
+//            simplices / boundary facets are appended with ballot + popc prefix sums into the point's contiguous scratch.
+//   check    lanes stride over the footprint and vote.
+//   retri    lanes stride over the boundary facets (new simplices), then over the (new simplex, facet) pivot items.
+// Same scratch format and same semantics as kernels.cuh (reference: delaunay_tree.rs:33-123, :213-334, scheduler.rs:6-55),
+// so the two implementations are interchangeable (option "coop"); tests/emu exercises the thread-per-point bodies on
+// the CPU, tests/test_gpu_* exercise these against the oracle on the B200.
+#pragma once
+#include "kernels.cuh"
+
+#if VOR_GPU
+namespace vor {
+
+template <int G> __device__ __forceinline__ unsigned group_mask() {
+    if (G == 32) return 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    return ((1u << G) - 1u) << ((lane / G) * G);
+}
+
+// ---- select: thread per active entry -> compact list of the entries that attempt this round
+struct SelectArgs {
+    const int *act;
+    const int *seed;
+    int *slotAct;
+    Counters *cnt;
+    int bits;
+    uint32_t salt, thr;
+    int cap;
+};
+VOR_HD void select_body(const SelectArgs &A, int a) {
+    const int v = A.act[a];
+    if (A.seed[v] < 0) return;
+    if (bij_hash((uint32_t)a, A.bits, A.salt) >= A.thr) return;
+    const int slot = agg_inc(&A.cnt->nslots);
+    if (slot < A.cap) A.slotAct[slot] = a;
+}
+
+template <int D> struct GeoCoop;
+template <> struct GeoCoop<3> {
+    // orientation of the simplex with vertex `k` replaced by p (lane k of the group evaluates facet k)
+    static __device__ __forceinline__ int orient_repl(PredCtx &cx, const Geo<3>::Verts &t, const double4 &p, int k) {
+        const double4 a = k == 0 ? p : t.p0, b = k == 1 ? p : t.p1, c = k == 2 ? p : t.p2, d = k == 3 ? p : t.p3;
+        return orient3d(cx, a, b, c, d);
+    }
+};
+template <> struct GeoCoop<2> {
+    static __device__ __forceinline__ int orient_repl(PredCtx &cx, const Geo<2>::Verts &t, const double2 &p, int k) {
+        const double2 a = k == 0 ? p : t.p0, b = k == 1 ? p : t.p1, c = k == 2 ? p : t.p2;
+        return orient2d(cx, a, b, c);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// attempt
+// ------------------------------------------------------------------------------------------
+template <int D, int G>
+__global__ void __launch_bounds__(256) k_attempt_coop(AttemptArgs<D> A, int nlaunched) {
+    constexpr int M = Dim<D>::M;
+    using Gm = Geo<D>;
+    const Mesh<D> &m = A.m;
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;   // group = attempt slot
+    const int gl = threadIdx.x & (G - 1);                          // lane inside the group
+    const unsigned gmask = group_mask<G>();
+    const int gshift = (threadIdx.x & 31) & ~(G - 1);              // first lane of the group inside the warp
+    int nsel = m.cnt->nslots;
+    nsel = nsel < A.scr.nslots ? nsel : A.scr.nslots;
+    nsel = nsel < nlaunched ? nsel : nlaunched;
+    if (gid >= nsel) return;
+    const int slot = gid;
+    const int a = A.scr.slotAct[slot];
+    const int v = A.act[a];
+    PredCtx cx{m.cnt};
+    const typename Gm::Pt p = m.pts[v];
+    const uint32_t q = bij_hash((uint32_t)a, A.bits, A.salt);
+    const int key_k = A.keybase | (int)(q << 1);
+    const int key_o = key_k | 1;
+    int *tn_i = reinterpret_cast<int *>(m.tn);
+
+    int status = ST_LOST, nk = 0, nb = 0, big = -1;
+    unsigned steps = 0, tests = 0;
+
+    // -- forwarding (all lanes follow the same chain: broadcast loads)
+    int s = m.seed[v];
+    int o;
+    while ((o = __ldcg(&m.owner[s])) < 0) s = ~o;
+
+    // -- visibility walk: lane k < M tests facet k
+    unsigned rot = (unsigned)v * 2654435761u;
+    typename Gm::Verts tvv = Gm::load(m, m.tv[s]);
+    bool fail = false;
+    for (;;) {
+        const int ok = gl < M ? GeoCoop<D>::orient_repl(cx, tvv, p, gl) : 1;
+        const unsigned bal = (__ballot_sync(gmask, ok < 0) >> gshift) & ((1u << M) - 1u);
+        if (bal == 0) break;
+        int go = 0;
+        const int r0 = (int)((rot >> 16) % (unsigned)M);
+        for (int k = 0; k < M; k++) {
+            const int i = (r0 + k) % M;
+            if ((bal >> i) & 1) { go = i; break; }
+        }
+        const int code = tn_i[(size_t)s * 4 + go];
+        if (code < 0) { if (gl == 0) set_err(m.cnt, ERR_OUTSIDE); fail = true; break; }
+        s = code >> 2;
+        rot = rot * 1664525u + 1013904223u;
+        if (++steps > (1u << 22)) { if (gl == 0) set_err(m.cnt, ERR_WALK); fail = true; break; }
+        tvv = Gm::load(m, m.tv[s]);
+    }
+
+    if (!fail) {
+        if (gl == 0) m.seed[v] = s;
+        // -- containing simplex must be in conflict, otherwise p duplicates one of its vertices
+        int c0 = 0;
+        if (gl == 0) c0 = Gm::conflict(cx, tvv, p);
+        c0 = __shfl_sync(gmask, c0, gshift);
+        tests = 1;
+        if (!c0) {
+            if (gl == 0) { m.seed[v] = -1; atomicAdd(&m.cnt->ndup, 1); }
+            fail = true;
+        }
+    }
+    if (!fail) {
+        int old0 = 0;
+        if (gl == 0) old0 = atomicMin(&m.owner[s], key_k);
+        old0 = __shfl_sync(gmask, old0, gshift);
+        if (old0 < key_k) fail = true;
+    }
+    if (!fail) {
+        ScrView sv = scr_view(A.scr, slot, -1);
+        if (gl == 0) sv.k[0] = s;
+        __syncwarp(gmask);
+        nk = 1;
+        int head = 0;
+        bool lost = false;
+        while (head < nk && !lost) {
+            const int tail = nk;
+            const int items = (tail - head) * M;
+            for (int base = 0; base < items && !lost; base += G) {
+                const int j = base + gl;
+                bool pushK = false, pushB = false, lostLane = false;
+                int newT = 0, fcode = 0, ocode = 0;
+                if (j < items) {
+                    const int t = sv.k[head + j / M];
+                    const int i = j % M;
+                    const int code = tn_i[(size_t)t * 4 + i];
+                    if (code < 0) {
+                        pushB = true; fcode = t * 4 + i; ocode = code;
+                    } else {
+                        const int n = code >> 2;
+                        const int ow = __ldcg(&m.owner[n]);
+                        if (ow == key_k) {
+                            // already in my cavity
+                        } else if (ow < key_k) {
+                            lostLane = true;
+                        } else if (ow == key_o) {
+                            pushB = true; fcode = t * 4 + i; ocode = code;
+                        } else {
+                            tests++;
+                            const typename Gm::Verts nv = Gm::load(m, m.tv[n]);
+                            if (Gm::conflict(cx, nv, p)) {
+                                const int old = atomicMin(&m.owner[n], key_k);
+                                if (old < key_k) lostLane = true;
+                                else if (old != key_k) { pushK = true; newT = n; }   // first lane to claim it appends it
+                            } else {
+                                const int old = atomicMin(&m.owner[n], key_o);
+                                if (old < key_k) lostLane = true;
+                                else { pushB = true; fcode = t * 4 + i; ocode = code; }
+                            }
+                        }
+                    }
+                }
+                if (__any_sync(gmask, lostLane)) { lost = true; break; }
+                const unsigned mk = (__ballot_sync(gmask, pushK) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+                const unsigned mb = (__ballot_sync(gmask, pushB) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+                const int ck = __popc(mk), cb = __popc(mb);
+                if (nk + ck > sv.capk || nb + cb > sv.capb) {
+                    // spill to an overflow slot (contiguous, much larger)
+                    if (big >= 0) { if (gl == 0) set_err(m.cnt, ERR_CAPACITY); lost = true; break; }
+                    if (gl == 0) big = atomicAdd(&m.cnt->nbig, 1);
+                    big = __shfl_sync(gmask, big, gshift);
+                    if (big >= A.scr.nbig) { lost = true; break; }
+                    const ScrView bv = scr_view(A.scr, slot, big);
+                    for (int x = gl; x < nk; x += G) bv.k[x] = sv.k[x];
+                    for (int x = gl; x < nb; x += G) { bv.f[x] = sv.f[x]; bv.o[x] = sv.o[x]; }
+                    sv = bv;
+                    if (gl == 0) A.scr.slotBig[slot] = big;
+                    __syncwarp(gmask);
+                    if (nk + ck > sv.capk || nb + cb > sv.capb) { if (gl == 0) set_err(m.cnt, ERR_CAPACITY); lost = true; break; }
+                }
+                const unsigned lt = (1u << gl) - 1u;
+                if (pushK) sv.k[nk + __popc(mk & lt)] = newT;
+                if (pushB) { const int pos = nb + __popc(mb & lt); sv.f[pos] = fcode; sv.o[pos] = ocode; }
+                nk += ck;
+                nb += cb;
+                __syncwarp(gmask);
+            }
+            head = tail;
+        }
+        if (!lost) status = ST_OK;
+    }
+    if (gl == 0) {
+        A.scr.slotStatus[slot] = status;
+        A.scr.slotNk[slot] = nk;
+        A.scr.slotNb[slot] = nb;
+        if (big < 0) A.scr.slotBig[slot] = -1;
+    }
+    if (A.stats) {
+        // every lane counted its own tests
+        for (int d = G / 2; d > 0; d >>= 1) tests += __shfl_xor_sync(gmask, tests, d);
+        if (gl == 0) {
+            atomicAdd(&m.cnt->walk_steps, (unsigned long long)steps);
+            atomicAdd(&m.cnt->tests, (unsigned long long)tests);
+            atomicAdd(&m.cnt->attempts, 1ULL);
+            if (status != ST_OK) atomicAdd(&m.cnt->aborted, 1ULL);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// check
+// ------------------------------------------------------------------------------------------
+template <int D, int G>
+__global__ void __launch_bounds__(256) k_check_coop(CheckArgs<D> A, int nlaunched) {
+    const Mesh<D> &m = A.m;
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gl = threadIdx.x & (G - 1);
+    const unsigned gmask = group_mask<G>();
+    int nsel = m.cnt->nslots;
+    nsel = nsel < A.scr.nslots ? nsel : A.scr.nslots;
+    nsel = nsel < nlaunched ? nsel : nlaunched;
+    if (gid >= nsel) return;
+    const int slot = gid;
+    if (A.scr.slotStatus[slot] != ST_OK) return;
+    const int a = A.scr.slotAct[slot];
+    const uint32_t q = bij_hash((uint32_t)a, A.bits, A.salt);
+    const int key_k = A.keybase | (int)(q << 1);
+    const int key_o = key_k | 1;
+    const ScrView sv = scr_view(A.scr, slot, A.scr.slotBig[slot]);
+    const int nk = A.scr.slotNk[slot], nb = A.scr.slotNb[slot];
+    bool bad = false;
+    for (int j = gl; j < nk; j += G)
+        if (__ldcg(&m.owner[sv.k[j]]) != key_k) bad = true;
+    for (int j = gl; j < nb; j += G) {
+        const int code = sv.o[j];
+        if (code >= 0 && __ldcg(&m.owner[code >> 2]) != key_o) bad = true;
+    }
+    if (__any_sync(gmask, bad)) return;
+    if (gl == 0) {
+        const int w = atomicAdd(&m.cnt->nwinners, 1);
+        A.scr.winners[w] = slot;
+        A.scr.wbase[w] = atomicAdd(&m.cnt->ntets, nb);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// retriangulate
+// ------------------------------------------------------------------------------------------
+template <int D, int G>
+__global__ void __launch_bounds__(256) k_retri_coop(RetriArgs<D> A, int nw) {
+    constexpr int M = Dim<D>::M;
+    const Mesh<D> &m = A.m;
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gl = threadIdx.x & (G - 1);
+    const unsigned gmask = group_mask<G>();
+    if (gid >= nw) return;
+    const int slot = A.scr.winners[gid];
+    const int base = A.scr.wbase[gid];
+    const int a = A.scr.slotAct[slot];
+    const int v = A.act[a];
+    const ScrView sv = scr_view(A.scr, slot, A.scr.slotBig[slot]);
+    const int nk = A.scr.slotNk[slot], nb = A.scr.slotNb[slot];
+    if (base + nb > m.cap) { if (gl == 0) set_err(m.cnt, ERR_OOM); return; }
+    int *tn_i = reinterpret_cast<int *>(m.tn);
+
+    // phase A: one lane per boundary facet
+    for (int j = gl; j < nb; j += G) {
+        const int fc = sv.f[j];
+        const int t = fc >> 2, i = fc & 3;
+        const int outer = sv.o[j];
+        const int T = base + j;
+        int4 verts = m.tv[t];
+        set4(verts, i, v);
+        m.tv[T] = verts;
+        tn_i[(size_t)T * 4 + i] = outer;
+        if (M == 3) tn_i[(size_t)T * 4 + 3] = -1;
+        if (outer >= 0) tn_i[(size_t)(outer >> 2) * 4 + (outer & 3)] = T * 4 + i;
+        tn_i[(size_t)t * 4 + i] = -(T * 4 + i) - 2;
+    }
+    __syncwarp(gmask);
+    // phase B: one lane per (new simplex, facet containing v) pivot
+    const int nitems = nb * (M - 1);
+    for (int it = gl; it < nitems; it += G) {
+        const int j = it / (M - 1);
+        const int fc = sv.f[j];
+        const int t = fc >> 2, i = fc & 3;
+        int k = it % (M - 1);
+        if (k >= i) k++;                         // the (M-1) facets other than i
+        const int T = base + j;
+        int4 cv = m.tv[t];
+        int r0 = -1, r1 = -1;
+        for (int sidx = 0; sidx < M; sidx++) {
+            if (sidx == i || sidx == k) continue;
+            if (r0 < 0) r0 = get4(cv, sidx); else r1 = get4(cv, sidx);
+        }
+        int cur = t, enter = i, exitf = k;
+        for (;;) {
+            const int e = tn_i[(size_t)cur * 4 + exitf];   // plain load: markers were written by this group (phase A)
+            if (e <= -2) {
+                const int sc = -(e + 2);
+                tn_i[(size_t)T * 4 + k] = (sc >> 2) * 4 + enter;
+                break;
+            }
+            const int nxt = e >> 2, jb = e & 3;
+            cv = m.tv[nxt];
+            int y = -1;
+            for (int sidx = 0; sidx < M; sidx++) {
+                if (sidx == jb) continue;
+                const int vv = get4(cv, sidx);
+                if (vv != r0 && vv != r1) y = sidx;
+            }
+            cur = nxt; enter = jb; exitf = y;
+        }
+    }
+    // phase C: the cavity dies (forwarding to the first new simplex)
+    for (int j = gl; j < nk; j += G) m.owner[sv.k[j]] = ~base;
+    if (gl == 0) {
+        m.ptTet[v] = base;
+        m.seed[v] = -1;
+        if (A.stats) {
+            atomicAdd(&m.cnt->killed, (unsigned long long)nk);
+            atomicAdd(&m.cnt->created, (unsigned long long)nb);
+        }
+    }
+}
+
+} // namespace vor
+#endif

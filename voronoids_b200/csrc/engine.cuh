@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "coop_kernels.cuh"
 #include "output_kernels.cuh"
 #include "setup_kernels.cuh"
 
@@ -34,6 +35,9 @@ struct EngineOptions {
     int stats = 0;               // accumulate W/E/K/C counters (atomics; keep off when timing)
     int verbose = 0;
     int profile = 0;             // CUDA-event time per kernel class (attempt / check / retri / setup)
+    int coop = 1;                // lane-group cooperative kernels (GPU build); 0 = thread-per-point bodies
+    int group = 0;               // lanes per point: 0 = choose per round (32 for small rounds, 8 for large), else 8 or 32
+    int coop_switch = 12288;     // rounds with more selected points than this use 8 lanes per point
     double tet_factor = 0.0;     // simplex slots per vertex (0 = default: 30 in 3D, 7 in 2D)
 };
 
@@ -45,6 +49,9 @@ inline void options_from_env(EngineOptions &o) {
     if (const char *e = getenv("VOR_STATS")) o.stats = atoi(e);
     if (const char *e = getenv("VOR_VERBOSE")) o.verbose = atoi(e);
     if (const char *e = getenv("VOR_TET_FACTOR")) o.tet_factor = atof(e);
+    if (const char *e = getenv("VOR_COOP")) o.coop = atoi(e);
+    if (const char *e = getenv("VOR_GROUP")) o.group = atoi(e);
+    if (const char *e = getenv("VOR_COOP_SWITCH")) o.coop_switch = atoi(e);
     if (const char *e = getenv("VOR_CAPK")) { o.capk = atoi(e); o.capb = 2 * o.capk + 4; }
 }
 
@@ -446,24 +453,60 @@ template <int D> class Engine {
             // only the round-local counters are rewritten (the allocator and statistics live on the device)
             be::h2d(&mesh.cnt->nslots, &hcnt->nslots, sizeof(int) * 3, stream);
             AttemptArgs<D> aa{mesh, scr, act, bits, roundSalt, thr, keybase, opt.stats};
-            prof.start(0, stream);
-            VOR_LAUNCH(AttemptArgs<D>, attempt_body<D>, nact, aa, stream);
-            prof.stop(stream);
-            const int maxSlots = std::min(nact, scr.nslots);
             CheckArgs<D> ca{mesh, scr, bits, roundSalt, keybase};
-            prof.start(1, stream);
-            VOR_LAUNCH_FULL(CheckArgs<D>, check_body<D>, maxSlots, ca, stream);
-            prof.stop(stream);
-            pull_counters();
-            check_device_error("round");
-            const int nw = hcnt->nwinners;
-            const int used = std::min(hcnt->nslots, scr.nslots);
-            ensure_simplices((long long)hcnt->ntets);
-            if (opt.verbose > 2) debug_footprints(nw);
-            RetriArgs<D> ra{mesh, scr, act, opt.stats};
-            prof.start(2, stream);
-            VOR_LAUNCH(RetriArgs<D>, retri_body<D>, nw, ra, stream);
-            prof.stop(stream);
+            int nw = 0, used = 0;
+#if VOR_GPU
+            if (opt.coop) {
+                // expected number of selected points (+25% and a constant); surplus selections wait for a later round
+                const double fsel = (double)thr / (double)(1u << bits);
+                long long bound = (long long)(fsel * (double)pending * 1.25) + 2048;
+                bound = std::min<long long>(bound, std::min(nact, scr.nslots));
+                const int nl = (int)bound;
+                SelectArgs sl{act, mesh.seed, scr.slotAct, mesh.cnt, bits, roundSalt, thr, scr.nslots};
+                prof.start(0, stream);
+                VOR_LAUNCH(SelectArgs, select_body, nact, sl, stream);
+                const int G = opt.group ? opt.group : (nl > opt.coop_switch ? 8 : 32);
+                if (G == 32) k_attempt_coop<D, 32><<<(unsigned)(((long long)nl * 32 + 255) / 256), 256, 0, stream>>>(aa, nl);
+                else k_attempt_coop<D, 8><<<(unsigned)(((long long)nl * 8 + 255) / 256), 256, 0, stream>>>(aa, nl);
+                be::g_launches++;
+                prof.stop(stream);
+                prof.start(1, stream);
+                k_check_coop<D, 8><<<(unsigned)(((long long)nl * 8 + 255) / 256), 256, 0, stream>>>(ca, nl);
+                be::g_launches++;
+                prof.stop(stream);
+                pull_counters();
+                check_device_error("round");
+                nw = hcnt->nwinners;
+                used = std::min(hcnt->nslots, nl);
+                ensure_simplices((long long)hcnt->ntets);
+                RetriArgs<D> ra{mesh, scr, act, opt.stats};
+                prof.start(2, stream);
+                if (nw > 0) {
+                    if (nw > opt.coop_switch) k_retri_coop<D, 8><<<(unsigned)(((long long)nw * 8 + 255) / 256), 256, 0, stream>>>(ra, nw);
+                    else k_retri_coop<D, 32><<<(unsigned)(((long long)nw * 32 + 255) / 256), 256, 0, stream>>>(ra, nw);
+                    be::g_launches++;
+                }
+                prof.stop(stream);
+            } else
+#endif
+            {
+                prof.start(0, stream);
+                VOR_LAUNCH(AttemptArgs<D>, attempt_body<D>, nact, aa, stream);
+                prof.stop(stream);
+                const int maxSlots = std::min(nact, scr.nslots);
+                prof.start(1, stream);
+                VOR_LAUNCH_FULL(CheckArgs<D>, check_body<D>, maxSlots, ca, stream);
+                prof.stop(stream);
+                pull_counters();
+                check_device_error("round");
+                nw = hcnt->nwinners;
+                used = std::min(hcnt->nslots, scr.nslots);
+                ensure_simplices((long long)hcnt->ntets);
+                RetriArgs<D> ra{mesh, scr, act, opt.stats};
+                prof.start(2, stream);
+                VOR_LAUNCH(RetriArgs<D>, retri_body<D>, nw, ra, stream);
+                prof.stop(stream);
+            }
             const int dropped = hcnt->ndup - ndup0;
             pending -= nw + dropped;
             insertedTotal += nw;

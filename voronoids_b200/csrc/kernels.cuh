@@ -52,7 +52,7 @@ template <int D> struct Mesh {
 };
 
 struct Scratch {
-    int *killed, *bfacet, *bouter;     // interleaved: entry j of slot s at [j * nslots + s]
+    int *killed, *bfacet, *bouter;     // contiguous per slot: entry j of slot s at [s * cap + j] (coalesced for a lane group)
     int *slotAct, *slotNk, *slotNb, *slotStatus, *slotBig;
     int nslots, capk, capb;
     int *bigK, *bigF, *bigO;           // overflow slots, contiguous per slot
@@ -66,8 +66,8 @@ struct ScrView { int *k, *f, *o; int stride, capk, capb; };
 VOR_HD ScrView scr_view(const Scratch &s, int slot, int big) {
     ScrView v;
     if (big < 0) {
-        v.k = s.killed + slot; v.f = s.bfacet + slot; v.o = s.bouter + slot;
-        v.stride = s.nslots; v.capk = s.capk; v.capb = s.capb;
+        v.k = s.killed + (size_t)slot * s.capk; v.f = s.bfacet + (size_t)slot * s.capb; v.o = s.bouter + (size_t)slot * s.capb;
+        v.stride = 1; v.capk = s.capk; v.capb = s.capb;
     } else {
         v.k = s.bigK + (size_t)big * s.bigCapK; v.f = s.bigF + (size_t)big * s.bigCapB; v.o = s.bigO + (size_t)big * s.bigCapB;
         v.stride = 1; v.capk = s.bigCapK; v.capb = s.bigCapB;
