@@ -81,6 +81,8 @@ int vor_set_option(const char *name, double value) {
     else if (n == "coop") g_opts.coop = (int)value;
     else if (n == "group") g_opts.group = (int)value;
     else if (n == "coop_switch") g_opts.coop_switch = (int)value;
+    else if (n == "rounds_per_sync") g_opts.rounds_per_sync = (int)value;
+    else if (n == "select_mode") g_opts.select_mode = (int)value;
     else if (n == "tet_factor") g_opts.tet_factor = value;
     else if (n == "capk") { g_opts.capk = (int)value; g_opts.capb = 2 * g_opts.capk + 4; }
     else if (n == "big_slots") g_opts.big_slots = (int)value;

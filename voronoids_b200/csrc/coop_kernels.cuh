@@ -7,8 +7,8 @@
 //            flood: each lane takes one (frontier simplex, facet) item: gathers the neighbour code, its owner word, its
 //            4 vertex records (32 B sectors) and evaluates the exact in-sphere test; reservation by atomicMin; new killed
 //            simplices / boundary facets are appended with ballot + popc prefix sums into the point's contiguous scratch.
-//   check    lanes stride over the footprint and vote.
-//   retri    lanes stride over the boundary facets (new simplices), then over the (new simplex, facet) pivot items.
+//   commit   (check + retriangulate fused) lanes stride over the footprint and vote; a winner allocates its block of
+//            simplex slots and lanes stride over the boundary facets (new simplices), then over the pivot items.
 // Same scratch format and same semantics as kernels.cuh (reference: delaunay_tree.rs:33-123, :213-334, scheduler.rs:6-55),
 // so the two implementations are interchangeable (option "coop"); tests/emu exercises the thread-per-point bodies on
 // the CPU, tests/test_gpu_* exercise these against the oracle on the B200.
@@ -24,23 +24,11 @@ template <int G> __device__ __forceinline__ unsigned group_mask() {
     return ((1u << G) - 1u) << ((lane / G) * G);
 }
 
-// ---- select: thread per active entry -> compact list of the entries that attempt this round
-struct SelectArgs {
-    const int *act;
-    const int *seed;
-    int *slotAct;
-    Counters *cnt;
-    int bits;
-    uint32_t salt, thr;
-    int cap;
-};
-VOR_HD void select_body(const SelectArgs &A, int a) {
-    const int v = A.act[a];
-    if (A.seed[v] < 0) return;
-    if (bij_hash((uint32_t)a, A.bits, A.salt) >= A.thr) return;
-    const int slot = agg_inc(&A.cnt->nslots);
-    if (slot < A.cap) A.slotAct[slot] = a;
-}
+// Selection is implicit and stratified: slot g of a round attempts active entry a = g * stride + offset, i.e. one
+// point per run of `stride` consecutive entries of the Morton-ordered active list (rotating offset), so no selection
+// kernel and no compaction of the selected set are needed.  A round is two launches: attempt, commit.
+struct RoundSel { int nact; int stride; int offset; int nsel; };
+__device__ __forceinline__ int slot_entry(const RoundSel &rs, int slot) { return slot * rs.stride + rs.offset; }
 
 template <int D> struct GeoCoop;
 template <> struct GeoCoop<3> {
@@ -61,7 +49,7 @@ template <> struct GeoCoop<2> {
 // attempt
 // ------------------------------------------------------------------------------------------
 template <int D, int G>
-__global__ void __launch_bounds__(256) k_attempt_coop(AttemptArgs<D> A, int nlaunched) {
+__global__ void __launch_bounds__(256) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
     constexpr int M = Dim<D>::M;
     using Gm = Geo<D>;
     const Mesh<D> &m = A.m;
@@ -69,13 +57,12 @@ __global__ void __launch_bounds__(256) k_attempt_coop(AttemptArgs<D> A, int nlau
     const int gl = threadIdx.x & (G - 1);                          // lane inside the group
     const unsigned gmask = group_mask<G>();
     const int gshift = (threadIdx.x & 31) & ~(G - 1);              // first lane of the group inside the warp
-    int nsel = m.cnt->nslots;
-    nsel = nsel < A.scr.nslots ? nsel : A.scr.nslots;
-    nsel = nsel < nlaunched ? nsel : nlaunched;
-    if (gid >= nsel) return;
+    if (gid >= rsel.nsel) return;
     const int slot = gid;
-    const int a = A.scr.slotAct[slot];
+    const int a = slot_entry(rsel, slot);
+    if (a >= rsel.nact) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }
     const int v = A.act[a];
+    if (m.seed[v] < 0) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }   // already inserted
     PredCtx cx{m.cnt};
     const typename Gm::Pt p = m.pts[v];
     const uint32_t q = bij_hash((uint32_t)a, A.bits, A.salt);
@@ -223,21 +210,26 @@ __global__ void __launch_bounds__(256) k_attempt_coop(AttemptArgs<D> A, int nlau
 }
 
 // ------------------------------------------------------------------------------------------
-// check
+// commit = ownership check + allocation + retriangulation, fused
 // ------------------------------------------------------------------------------------------
+// A group whose point still owns its whole footprint is a winner: it takes a block of simplex slots from the bump
+// allocator (one atomicAdd) and retriangulates at once.  This is safe while other groups are still checking: a check
+// only reads owner[] of its own footprint, and a winner only changes owner[] on its own killed simplices, which any
+// group that shares them has lost anyway (it reads the winner's key or the dead mark, never its own key).
 template <int D, int G>
-__global__ void __launch_bounds__(256) k_check_coop(CheckArgs<D> A, int nlaunched) {
+__global__ void __launch_bounds__(256) k_commit_coop(CheckArgs<D> A, const int *act, RoundSel rsel, int stats) {
+    constexpr int M = Dim<D>::M;
     const Mesh<D> &m = A.m;
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int gl = threadIdx.x & (G - 1);
     const unsigned gmask = group_mask<G>();
-    int nsel = m.cnt->nslots;
-    nsel = nsel < A.scr.nslots ? nsel : A.scr.nslots;
-    nsel = nsel < nlaunched ? nsel : nlaunched;
-    if (gid >= nsel) return;
+    const int gshift = (threadIdx.x & 31) & ~(G - 1);
+    if (gid == 0 && gl == 0) m.cnt->nbig = 0;           // overflow slots are per round (attempt is over)
+    if (gid >= rsel.nsel) return;
     const int slot = gid;
     if (A.scr.slotStatus[slot] != ST_OK) return;
-    const int a = A.scr.slotAct[slot];
+    const int a = slot_entry(rsel, slot);
+    const int v = act[a];
     const uint32_t q = bij_hash((uint32_t)a, A.bits, A.salt);
     const int key_k = A.keybase | (int)(q << 1);
     const int key_o = key_k | 1;
@@ -251,34 +243,20 @@ __global__ void __launch_bounds__(256) k_check_coop(CheckArgs<D> A, int nlaunche
         if (code >= 0 && __ldcg(&m.owner[code >> 2]) != key_o) bad = true;
     }
     if (__any_sync(gmask, bad)) return;
-    if (gl == 0) {
-        const int w = atomicAdd(&m.cnt->nwinners, 1);
-        A.scr.winners[w] = slot;
-        A.scr.wbase[w] = atomicAdd(&m.cnt->ntets, nb);
+    int base = 0;
+    if (gl == 0) base = atomicAdd(&m.cnt->ntets, nb);
+    base = __shfl_sync(gmask, base, gshift);
+    if (base + nb > m.cap) {
+        // no room: leave the mesh untouched (the point stays pending), retire the part of the block that exists and
+        // tell the host to grow the store
+        for (int j = gl; j < nb; j += G)
+            if (base + j < m.cap) m.owner[base + j] = -1;
+        if (gl == 0) m.cnt->oom_soft = 1;
+        return;
     }
-}
-
-// ------------------------------------------------------------------------------------------
-// retriangulate
-// ------------------------------------------------------------------------------------------
-template <int D, int G>
-__global__ void __launch_bounds__(256) k_retri_coop(RetriArgs<D> A, int nw) {
-    constexpr int M = Dim<D>::M;
-    const Mesh<D> &m = A.m;
-    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const int gl = threadIdx.x & (G - 1);
-    const unsigned gmask = group_mask<G>();
-    if (gid >= nw) return;
-    const int slot = A.scr.winners[gid];
-    const int base = A.scr.wbase[gid];
-    const int a = A.scr.slotAct[slot];
-    const int v = A.act[a];
-    const ScrView sv = scr_view(A.scr, slot, A.scr.slotBig[slot]);
-    const int nk = A.scr.slotNk[slot], nb = A.scr.slotNb[slot];
-    if (base + nb > m.cap) { if (gl == 0) set_err(m.cnt, ERR_OOM); return; }
     int *tn_i = reinterpret_cast<int *>(m.tn);
 
-    // phase A: one lane per boundary facet
+    // phase A: one lane per boundary facet: new simplex, outer back-pointer, marker in the dead simplex
     for (int j = gl; j < nb; j += G) {
         const int fc = sv.f[j];
         const int t = fc >> 2, i = fc & 3;
@@ -293,14 +271,14 @@ __global__ void __launch_bounds__(256) k_retri_coop(RetriArgs<D> A, int nw) {
         tn_i[(size_t)t * 4 + i] = -(T * 4 + i) - 2;
     }
     __syncwarp(gmask);
-    // phase B: one lane per (new simplex, facet containing v) pivot
+    // phase B: one lane per (new simplex, facet containing v): pivot around the ridge through the dead cavity
     const int nitems = nb * (M - 1);
     for (int it = gl; it < nitems; it += G) {
         const int j = it / (M - 1);
         const int fc = sv.f[j];
         const int t = fc >> 2, i = fc & 3;
         int k = it % (M - 1);
-        if (k >= i) k++;                         // the (M-1) facets other than i
+        if (k >= i) k++;
         const int T = base + j;
         int4 cv = m.tv[t];
         int r0 = -1, r1 = -1;
@@ -332,7 +310,8 @@ __global__ void __launch_bounds__(256) k_retri_coop(RetriArgs<D> A, int nw) {
     if (gl == 0) {
         m.ptTet[v] = base;
         m.seed[v] = -1;
-        if (A.stats) {
+        atomicAdd(&m.cnt->win_total, 1ULL);
+        if (stats) {
             atomicAdd(&m.cnt->killed, (unsigned long long)nk);
             atomicAdd(&m.cnt->created, (unsigned long long)nb);
         }

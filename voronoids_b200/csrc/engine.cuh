@@ -9,6 +9,7 @@
 //   Engine::validate check_delaunay             /root/reference/src/delaunay_tree.rs:512-541
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -38,7 +39,9 @@ struct EngineOptions {
     int coop = 1;                // lane-group cooperative kernels (GPU build); 0 = thread-per-point bodies
     int group = 0;               // lanes per point: 0 = choose per round (32 for small rounds, 8 for large), else 8 or 32
     int coop_switch = 12288;     // rounds with more selected points than this use 8 lanes per point
-    double tet_factor = 0.0;     // simplex slots per vertex (0 = default: 30 in 3D, 7 in 2D)
+    int select_mode = 1;         // 1 = stratified selection along the Morton-ordered active list, 0 = random subset
+    int rounds_per_sync = 4;     // rounds launched back to back between two host read-backs of the counters
+    double tet_factor = 0.0;     // simplex slots per vertex (0 = default: 31 in 3D, 7.5 in 2D)
 };
 
 inline void options_from_env(EngineOptions &o) {
@@ -52,6 +55,8 @@ inline void options_from_env(EngineOptions &o) {
     if (const char *e = getenv("VOR_COOP")) o.coop = atoi(e);
     if (const char *e = getenv("VOR_GROUP")) o.group = atoi(e);
     if (const char *e = getenv("VOR_COOP_SWITCH")) o.coop_switch = atoi(e);
+    if (const char *e = getenv("VOR_ROUNDS_PER_SYNC")) o.rounds_per_sync = atoi(e);
+    if (const char *e = getenv("VOR_SELECT_MODE")) o.select_mode = atoi(e);
     if (const char *e = getenv("VOR_CAPK")) { o.capk = atoi(e); o.capb = 2 * o.capk + 4; }
 }
 
@@ -89,6 +94,7 @@ template <int D> class Engine {
     int *act = nullptr, *act2 = nullptr, *blockCnt = nullptr;
     long long *d_misc = nullptr;
     long long insertedTotal = 0;
+    long long remainingInCall = 0;   // points of the current insert call not inserted yet
     int actcap = 0;
     // key layout
     int setBits = 0, axisBits = 0;
@@ -301,7 +307,7 @@ template <int D> class Engine {
         mesh.cnt = (Counters *)be::dmalloc(sizeof(Counters));
         ensure_vertices(nsuper + n + 16);
         ensure_inputs(n + 16);
-        const double tf = opt.tet_factor > 0 ? opt.tet_factor : (D == 3 ? 30.0 : 7.0);
+        const double tf = opt.tet_factor > 0 ? opt.tet_factor : (D == 3 ? 31.0 : 7.5);
         ensure_simplices((long long)(tf * (double)(n + 64)) + 4LL * nsets + 1024);
         d_boxLo = (double *)be::dmalloc(sizeof(double) * (size_t)nsets * D);
         d_boxHi = (double *)be::dmalloc(sizeof(double) * (size_t)nsets * D);
@@ -343,13 +349,14 @@ template <int D> class Engine {
     // d_in: n x D points on the device; h_setOff: nsets+1 offsets into d_in (nullptr => one set)
     void insert(const double *d_in, int n, const int *h_setOff) {
         if (n <= 0) return;
+        const auto tins0 = std::chrono::steady_clock::now();
         invalidate_outputs();
         std::vector<int> off(nsets + 1);
         if (h_setOff) off.assign(h_setOff, h_setOff + nsets + 1);
         else { off[0] = 0; off[1] = n; }
         ensure_vertices(nv + n);
         ensure_inputs(ninput + n);
-        const double tf = opt.tet_factor > 0 ? opt.tet_factor : (D == 3 ? 30.0 : 7.0);
+        const double tf = opt.tet_factor > 0 ? opt.tet_factor : (D == 3 ? 31.0 : 7.5);
         ensure_simplices((long long)hcnt->ntets + (long long)(tf * (double)(n + 64)));
 
         // ---- keys, sort, gather
@@ -406,11 +413,25 @@ template <int D> class Engine {
             blockCnt = (int *)be::dmalloc(sizeof(int) * (size_t)(actcap / 256 + 2));
         }
 
+        remainingInCall = n;
+        if (opt.verbose) {
+            be::sync(stream);
+            fprintf(stderr, "[vor] insert: %d points, setup (alloc + keys + sort + gather) %.3f ms\n", n,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tins0).count());
+        }
         // ---- stages
         for (int st = 0; st < 64; st++) {
             const int lo = vbase + stageLo[st], hi = vbase + stageLo[st + 1];
             if (hi <= lo) continue;
+            const auto t0 = std::chrono::steady_clock::now();
+            const unsigned long long r0 = rs.rounds;
             run_stage(lo, hi);
+            if (opt.verbose) {
+                be::sync(stream);
+                const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                fprintf(stderr, "[vor] stage %d: %d points, %llu rounds, %.3f ms (%.1f us/round, %.1f ns/point)\n", st, hi - lo, rs.rounds - r0, ms,
+                        1e3 * ms / (double)std::max<unsigned long long>(rs.rounds - r0, 1), 1e6 * ms / (double)(hi - lo));
+            }
             refLo = lo;
             refHi = hi;
             rs.stages++;
@@ -422,13 +443,113 @@ template <int D> class Engine {
     }
 
     void reset_owners() {
-        ResetOwnerArgs ra{mesh.owner};
-        VOR_LAUNCH(ResetOwnerArgs, reset_owner_body, hcnt->ntets, ra, stream);
+        ResetOwnerArgs ra{mesh.owner, mesh.cnt};
+        VOR_LAUNCH(ResetOwnerArgs, reset_owner_body, mesh.cap, ra, stream);
         epoch = epochMax;
         rs.owner_resets++;
     }
 
+    // ------------------------------------------------------------------ pipelined stage (GPU, cooperative kernels)
+    // `rounds_per_sync` rounds are launched back to back; every kernel sizes itself from device-side counters, the
+    // host reads the counters once per batch (pending count, allocator, errors) and grows / compacts there.
+#if VOR_GPU
+    // simplex slots to keep free for a batch of R rounds: every attempted point could win, but never more than the
+    // points of this insert call that are still pending
+    long long batch_margin(int R, int nsel, double newPerPoint) const {
+        const double byRounds = (double)R * (double)nsel * newPerPoint;
+        const double byRemaining = (double)remainingInCall * (newPerPoint * 0.85) + 65536.0;
+        return (long long)std::min(byRounds, byRemaining) + 4096;
+    }
+    template <int G> void launch_round(const AttemptArgs<D> &aa, const CheckArgs<D> &ca, const RoundSel &sel) {
+        const unsigned grid = (unsigned)(((long long)sel.nsel * G + 255) / 256);
+        prof.start(0, stream);
+        k_attempt_coop<D, G><<<grid, 256, 0, stream>>>(aa, sel);
+        prof.stop(stream);
+        prof.start(2, stream);
+        k_commit_coop<D, G><<<grid, 256, 0, stream>>>(ca, act, sel, opt.stats);
+        prof.stop(stream);
+        be::g_launches += 2;
+    }
+    void run_stage_pipelined(int lo, int hi) {
+        const int total = hi - lo;
+        int nact = total, pending = total;
+        SeedArgs sd{keysAll, mesh.ptTet, mesh.seed, nsuper, lo, refLo, refHi, D * axisBits};
+        VOR_LAUNCH(SeedArgs, init_seeds_body, nact, sd, stream);
+        IotaArgs ia{act, lo};
+        VOR_LAUNCH(IotaArgs, iota_body, nact, ia, stream);
+        pull_counters();
+        const unsigned long long win0 = hcnt->win_total;
+        const int dup0 = hcnt->ndup;
+        int stall = 0;
+        uint32_t roundSalt = (uint32_t)mix64((uint64_t)lo * 0x9E37u + rs.rounds);
+        const double newPerPoint = D == 3 ? 36.0 : 9.0;   // allocator margin per attempted point (mean is 27 / 6)
+        while (pending > 0) {
+            const int R = opt.verbose > 2 ? 1 : std::max(1, opt.rounds_per_sync);
+            // attempt about max(min_attempt, inserted/attempt_div) of the pending points per round, one per run of
+            // `stride` consecutive entries of the active list (which also holds the entries inserted since the last
+            // compaction)
+            const double target = std::max((double)opt.min_attempt, (double)insertedTotal / opt.attempt_div);
+            int stride = 1;
+            if ((double)pending > target) stride = std::max(1, (int)std::floor((double)pending / target));
+            stride = std::max(stride, (nact + scr.nslots - 1) / scr.nslots);
+            const int nsel = (nact + stride - 1) / stride;
+            ensure_simplices((long long)hcnt->ntets + batch_margin(R, std::min(nsel, pending), newPerPoint));
+            for (int r = 0; r < R; r++) {
+                if (epoch <= 0) reset_owners();
+                roundSalt = roundSalt * 1664525u + 1013904223u;
+                const int keybase = epoch << (bits + 1);
+                const RoundSel sel{nact, stride, (int)((roundSalt >> 8) % (uint32_t)stride), nsel};
+                AttemptArgs<D> aa{mesh, scr, act, bits, roundSalt, 0u, stride, sel.offset, keybase, opt.stats};
+                CheckArgs<D> ca{mesh, scr, bits, roundSalt, keybase};
+                const int G = opt.group ? opt.group : (nsel > opt.coop_switch ? 8 : 32);
+                if (G == 32) launch_round<32>(aa, ca, sel); else launch_round<8>(aa, ca, sel);
+                epoch--;
+                rs.rounds++;
+            }
+            pull_counters();
+            check_device_error("round");
+            const long long done = (long long)(hcnt->win_total - win0) + (long long)(hcnt->ndup - dup0);
+            const int newPending = total - (int)done;
+            insertedTotal += (long long)(pending - newPending);
+            remainingInCall -= (long long)(pending - newPending);
+            if (newPending == pending) { if (++stall > 64) fail(ERR_WALK, "no progress in 64 consecutive batches of rounds"); }
+            else stall = 0;
+            pending = newPending;
+            if (hcnt->oom_soft) {
+                // some winners found no room: retire the slots handed out beyond the old capacity and grow
+                const int oldcap = mesh.cap;
+                ensure_simplices((long long)hcnt->ntets + batch_margin(R, nsel, newPerPoint));
+                if (hcnt->ntets > oldcap) fill_i(mesh.owner + oldcap, -1, (size_t)(std::min(hcnt->ntets, mesh.cap) - oldcap));
+                hcnt->oom_soft = 0;
+                be::h2d(&mesh.cnt->oom_soft, &hcnt->oom_soft, sizeof(int), stream);
+            }
+            if (opt.verbose > 1)
+                fprintf(stderr, "[vor] stage [%d,%d) rounds %llu: nact %d pending %d stride %d nsel %d simplices %d\n", lo, hi, rs.rounds, nact,
+                        pending, stride, nsel, hcnt->ntets);
+            if (opt.verbose > 2) {
+                int f[8];
+                validate(f);
+                if (f[0] | f[1] | f[2] | f[3] | f[4]) {
+                    fprintf(stderr, "[vor] VALIDATION FAILED after round %llu: %d %d %d %d %d\n", rs.rounds, f[0], f[1], f[2], f[3], f[4]);
+                    fail(ERR_CUDA, "debug validation failed");
+                }
+            }
+            if (pending > 0 && nact > 4096 && pending < nact / 2) {
+                nact = compact_active(nact);
+                if (nact != pending) fail(ERR_CUDA, "active list compaction lost points");
+            }
+        }
+        rs.attempts = hcnt->attempts;
+        rs.winners = hcnt->win_total;
+        if (opt.verbose)
+            fprintf(stderr, "[vor] stage [%d,%d) done: rounds so far %llu, simplices %d\n", lo, hi, rs.rounds, hcnt->ntets);
+    }
+#endif
+
     void run_stage(int lo, int hi) {
+#if VOR_GPU
+        if (opt.coop) { run_stage_pipelined(lo, hi); return; }
+#endif
         int nact = hi - lo;
         int pending = nact;
         SeedArgs sd{keysAll, mesh.ptTet, mesh.seed, nsuper, lo, refLo, refHi, D * axisBits};
@@ -452,43 +573,12 @@ template <int D> class Engine {
             const int ndup0 = hcnt->ndup;
             // only the round-local counters are rewritten (the allocator and statistics live on the device)
             be::h2d(&mesh.cnt->nslots, &hcnt->nslots, sizeof(int) * 3, stream);
-            AttemptArgs<D> aa{mesh, scr, act, bits, roundSalt, thr, keybase, opt.stats};
+            const double fsel0 = (double)thr / (double)(1u << bits);
+            const int stride = (opt.select_mode == 1 && thr < (1u << bits)) ? std::max(1, (int)std::lround(1.0 / fsel0)) : 0;
+            const int offset = stride > 0 ? (int)(roundSalt % (uint32_t)stride) : 0;
+            AttemptArgs<D> aa{mesh, scr, act, bits, roundSalt, thr, stride, offset, keybase, opt.stats};
             CheckArgs<D> ca{mesh, scr, bits, roundSalt, keybase};
             int nw = 0, used = 0;
-#if VOR_GPU
-            if (opt.coop) {
-                // expected number of selected points (+25% and a constant); surplus selections wait for a later round
-                const double fsel = (double)thr / (double)(1u << bits);
-                long long bound = (long long)(fsel * (double)pending * 1.25) + 2048;
-                bound = std::min<long long>(bound, std::min(nact, scr.nslots));
-                const int nl = (int)bound;
-                SelectArgs sl{act, mesh.seed, scr.slotAct, mesh.cnt, bits, roundSalt, thr, scr.nslots};
-                prof.start(0, stream);
-                VOR_LAUNCH(SelectArgs, select_body, nact, sl, stream);
-                const int G = opt.group ? opt.group : (nl > opt.coop_switch ? 8 : 32);
-                if (G == 32) k_attempt_coop<D, 32><<<(unsigned)(((long long)nl * 32 + 255) / 256), 256, 0, stream>>>(aa, nl);
-                else k_attempt_coop<D, 8><<<(unsigned)(((long long)nl * 8 + 255) / 256), 256, 0, stream>>>(aa, nl);
-                be::g_launches++;
-                prof.stop(stream);
-                prof.start(1, stream);
-                k_check_coop<D, 8><<<(unsigned)(((long long)nl * 8 + 255) / 256), 256, 0, stream>>>(ca, nl);
-                be::g_launches++;
-                prof.stop(stream);
-                pull_counters();
-                check_device_error("round");
-                nw = hcnt->nwinners;
-                used = std::min(hcnt->nslots, nl);
-                ensure_simplices((long long)hcnt->ntets);
-                RetriArgs<D> ra{mesh, scr, act, opt.stats};
-                prof.start(2, stream);
-                if (nw > 0) {
-                    if (nw > opt.coop_switch) k_retri_coop<D, 8><<<(unsigned)(((long long)nw * 8 + 255) / 256), 256, 0, stream>>>(ra, nw);
-                    else k_retri_coop<D, 32><<<(unsigned)(((long long)nw * 32 + 255) / 256), 256, 0, stream>>>(ra, nw);
-                    be::g_launches++;
-                }
-                prof.stop(stream);
-            } else
-#endif
             {
                 prof.start(0, stream);
                 VOR_LAUNCH(AttemptArgs<D>, attempt_body<D>, nact, aa, stream);

@@ -140,7 +140,9 @@ template <int D> struct AttemptArgs {
     const int *act;     // pending vertex ids of this stage
     int bits;           // priority bits (2^bits >= number of active entries)
     uint32_t salt;      // per-round salt of the priority hash
-    uint32_t thr;       // attempt iff priority < thr
+    uint32_t thr;       // random selection: attempt iff priority < thr
+    int stride;         // stratified selection (stride > 0): attempt iff (a + offset) % stride == 0 -- one point per
+    int offset;         //   run of `stride` consecutive (Morton-ordered) active entries, rotating every round
     int keybase;        // epoch << (bits + 1)
     int stats;          // accumulate W/E counters
 };
@@ -153,7 +155,7 @@ template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
     int s = m.seed[v];
     if (s < 0) return;                                   // already inserted
     const uint32_t q = bij_hash((uint32_t)a, A.bits, A.salt);
-    if (q >= A.thr) return;                              // not selected this round
+    if (A.stride > 0 ? ((a + A.offset) % A.stride != 0) : (q >= A.thr)) return;   // not selected this round
     const int slot = agg_inc(&m.cnt->nslots);
     if (slot >= A.scr.nslots) return;                    // scratch exhausted: wait for a later round
     A.scr.slotAct[slot] = a;
@@ -416,6 +418,7 @@ template <int D> VOR_HD void retri_body(const RetriArgs<D> &A, int w) {
     for (int j = 0; j < nk; j++) m.owner[sv.k[(size_t)j * sv.stride]] = ~base;
     m.ptTet[v] = base;
     m.seed[v] = -1;
+    atomic_add_ull(&m.cnt->win_total, 1ULL);
     if (A.stats) {
         atomic_add_ull(&m.cnt->killed, (unsigned long long)nk);
         atomic_add_ull(&m.cnt->created, (unsigned long long)nb);
@@ -425,8 +428,9 @@ template <int D> VOR_HD void retri_body(const RetriArgs<D> &A, int w) {
 // ------------------------------------------------------------------------------------------
 // small maintenance kernels
 // ------------------------------------------------------------------------------------------
-struct ResetOwnerArgs { int *owner; };
+struct ResetOwnerArgs { int *owner; const Counters *cnt; };
 VOR_HD void reset_owner_body(const ResetOwnerArgs &A, int t) {
+    if (t >= A.cnt->ntets) return;   // the launch covers the whole store: the host's simplex count may be a batch behind
     if (A.owner[t] >= 0) A.owner[t] = OWNER_FREE;
 }
 

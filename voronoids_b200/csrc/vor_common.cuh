@@ -122,7 +122,7 @@ struct Counters {
     int err;          // first error code
     int ndup;         // duplicate points dropped
     int nact_out;     // compaction output count
-    int pad0;
+    int oom_soft;     // a winner could not get simplex slots (host grows the store at the next sync)
     unsigned long long walk_steps;   // W: visibility-walk steps
     unsigned long long tests;        // E: in-sphere tests
     unsigned long long killed;       // K: simplices killed
@@ -131,6 +131,8 @@ struct Counters {
     unsigned long long exact_zero;   // exact predicates that evaluated to zero
     unsigned long long attempts;     // attempt slots used (all rounds)
     unsigned long long aborted;      // attempts that lost during the flood
+    unsigned long long win_total;    // points inserted (all rounds)
+    unsigned long long sel_total;    // attempt slots claimed (all rounds)
 };
 
 VOR_HD void set_err(Counters *c, int code) { atomic_cas_i(&c->err, 0, code); }
