@@ -125,6 +125,7 @@ vor_status vor_predicates(int kind, const double *rows, size_t n, int32_t *out, 
 /* ---- misc ------------------------------------------------------------------------------------------------------ */
 const char *vor_last_error(void);          /* thread-local text of the last failure */
 uint64_t vor_kernel_launches(void);        /* kernels of this library launched so far in this process */
+void vor_release_memory(void);             /* return the caching device allocator's free blocks to the driver */
 int vor_set_option(const char *name, double value); /* engine options for trees created afterwards */
 void vor_tree_set_stream(vor_tree *t, void *cuda_stream);
 

@@ -21,6 +21,7 @@ struct CudaError : std::runtime_error {
 inline void set_device(int) {}
 inline void *dmalloc(size_t bytes) { return std::malloc(bytes ? bytes : 16); }
 inline void dfree(void *p) { std::free(p); }
+inline void release_cached() {}
 inline void dmemset(void *p, int byte, size_t n, Stream) { std::memset(p, byte, n); }
 inline void h2d(void *d, const void *h, size_t n, Stream) { std::memcpy(d, h, n); }
 inline void d2h(void *h, const void *d, size_t n, Stream) { std::memcpy(h, d, n); }

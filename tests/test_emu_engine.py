@@ -44,7 +44,7 @@ def test_emu_overflow_scratch_and_compaction(emu_lib, oracle):
         assert st["compactions"] > 0
     finally:
         emu_lib.vor_set_option(b"capk", 64.0)
-        emu_lib.vor_set_option(b"min_attempt", float(1 << 17))
+        emu_lib.vor_set_option(b"min_attempt", 8192.0)
 
 
 def test_emu_capacity_error_is_loud(emu_lib):

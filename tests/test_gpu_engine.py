@@ -46,7 +46,7 @@ def test_gpu_overflow_scratch(gpu_lib, oracle):
         assert st["compactions"] > 0
     finally:
         gpu_lib.vor_set_option(b"capk", 64.0)
-        gpu_lib.vor_set_option(b"min_attempt", float(1 << 17))
+        gpu_lib.vor_set_option(b"min_attempt", 8192.0)
 
 
 def test_gpu_errors_are_loud(gpu_lib):

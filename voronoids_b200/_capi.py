@@ -40,6 +40,7 @@ SYMBOLS = {
     "vor_predicates": (C.c_int, [C.c_int, dp, C.c_size_t, i32p, u64p, C.c_int]),
     "vor_last_error": (C.c_char_p, []),
     "vor_kernel_launches": (C.c_uint64, []),
+    "vor_release_memory": (None, []),
     "vor_set_option": (C.c_int, [C.c_char_p, C.c_double]),
     "vor_tree_set_stream": (None, [tree_p, C.c_void_p]),
 }

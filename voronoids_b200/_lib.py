@@ -6,7 +6,7 @@ import os
 from . import _capi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libvoronoids_b200.so")
+SO_PATH = os.environ.get("VOR_SO", os.path.join(_HERE, "libvoronoids_b200.so"))  # VOR_SO: tuning builds of the same sources
 _LIB = None
 
 

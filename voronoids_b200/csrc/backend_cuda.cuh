@@ -4,7 +4,10 @@
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <stdexcept>
+#include <map>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "vor_common.cuh"
 
@@ -27,12 +30,69 @@ inline void check(cudaError_t e, const char *what) {
 #define VOR_CUDA(x) ::vor::be::check((x), #x)
 
 inline void set_device(int dev) { VOR_CUDA(cudaSetDevice(dev)); }
-inline void *dmalloc(size_t bytes) {
-    void *p = nullptr;
-    VOR_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
-    return p;
-}
-inline void dfree(void *p) { if (p) cudaFree(p); }
+// Caching device allocator (per process, per device): a triangulation allocates ~1.2 KB per 3D point in a handful of
+// large arrays; cudaMalloc / cudaFree of multi-GB blocks cost tens of milliseconds, so freed blocks are kept and
+// handed out again to the next tree (vor_release_memory() returns them to the driver).
+struct Pool {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void *> cache;   // (device, size) -> block
+    std::unordered_map<void *, std::pair<int, size_t>> live;
+    size_t cached = 0;
+    size_t limit = (size_t)96 << 30;
+    static size_t round_up(size_t b) {
+        const size_t g = b >= ((size_t)1 << 20) ? ((size_t)2 << 20) : 512;
+        return (b + g - 1) / g * g;
+    }
+    void *alloc(size_t bytes) {
+        const size_t need = round_up(bytes ? bytes : 16);
+        int dev = 0;
+        VOR_CUDA(cudaGetDevice(&dev));
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = cache.lower_bound({dev, need});
+            if (it != cache.end() && it->first.first == dev && it->first.second <= need + need / 4 + ((size_t)2 << 20)) {
+                void *p = it->second;
+                live[p] = it->first;
+                cached -= it->first.second;
+                cache.erase(it);
+                return p;
+            }
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaErrorMemoryAllocation) {   // give the cache back and retry once
+            cudaGetLastError();
+            release();
+            e = cudaMalloc(&p, need);
+        }
+        check(e, "cudaMalloc");
+        std::lock_guard<std::mutex> lk(mu);
+        live[p] = {dev, need};
+        return p;
+    }
+    void free(void *p) {
+        if (!p) return;
+        cudaDeviceSynchronize();   // same guarantee as cudaFree: no kernel still uses the block
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = live.find(p);
+        if (it == live.end()) { cudaFree(p); return; }
+        const auto key = it->second;
+        live.erase(it);
+        if (cached + key.second > limit) { cudaFree(p); return; }
+        cache.emplace(key, p);
+        cached += key.second;
+    }
+    void release() {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto &kv : cache) cudaFree(kv.second);
+        cache.clear();
+        cached = 0;
+    }
+};
+extern Pool g_pool;
+inline void *dmalloc(size_t bytes) { return g_pool.alloc(bytes); }
+inline void dfree(void *p) { g_pool.free(p); }
+inline void release_cached() { g_pool.release(); }
 inline void dmemset(void *p, int byte, size_t n, Stream s) { VOR_CUDA(cudaMemsetAsync(p, byte, n, s)); }
 inline void h2d(void *d, const void *h, size_t n, Stream s) { VOR_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
 inline void d2h(void *h, const void *d, size_t n, Stream s) { VOR_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }

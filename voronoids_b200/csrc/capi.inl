@@ -67,6 +67,7 @@ extern "C" {
 
 const char *vor_last_error(void) { return g_err.c_str(); }
 uint64_t vor_kernel_launches(void) { return vor::be::g_launches; }
+void vor_release_memory(void) { vor::be::release_cached(); }
 
 int vor_set_option(const char *name, double value) {
     current_options();

@@ -48,8 +48,11 @@ template <> struct GeoCoop<2> {
 // ------------------------------------------------------------------------------------------
 // attempt
 // ------------------------------------------------------------------------------------------
+#ifndef VOR_ATTEMPT_MINBLOCKS
+#define VOR_ATTEMPT_MINBLOCKS 4   // 64 registers: 4 blocks/SM; measured best of 3/4/5 on the 10M-point run
+#endif
 template <int D, int G>
-__global__ void __launch_bounds__(256) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
+__global__ void __launch_bounds__(256, VOR_ATTEMPT_MINBLOCKS) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
     constexpr int M = Dim<D>::M;
     using Gm = Geo<D>;
     const Mesh<D> &m = A.m;
@@ -68,7 +71,6 @@ __global__ void __launch_bounds__(256) k_attempt_coop(AttemptArgs<D> A, RoundSel
     const uint32_t q = bij_hash((uint32_t)a, A.bits, A.salt);
     const int key_k = A.keybase | (int)(q << 1);
     const int key_o = key_k | 1;
-    int *tn_i = reinterpret_cast<int *>(m.tn);
 
     int status = ST_LOST, nk = 0, nb = 0, big = -1;
     unsigned steps = 0, tests = 0;
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(256) k_attempt_coop(AttemptArgs<D> A, RoundSel
 
     // -- visibility walk: lane k < M tests facet k
     unsigned rot = (unsigned)v * 2654435761u;
-    typename Gm::Verts tvv = Gm::load(m, m.tv[s]);
+    typename Gm::Verts tvv = Gm::load(m, TV(m, s));
     bool fail = false;
     for (;;) {
         const int ok = gl < M ? GeoCoop<D>::orient_repl(cx, tvv, p, gl) : 1;
@@ -92,12 +94,12 @@ __global__ void __launch_bounds__(256) k_attempt_coop(AttemptArgs<D> A, RoundSel
             const int i = (r0 + k) % M;
             if ((bal >> i) & 1) { go = i; break; }
         }
-        const int code = tn_i[(size_t)s * 4 + go];
+        const int code = TNI(m, s, go);
         if (code < 0) { if (gl == 0) set_err(m.cnt, ERR_OUTSIDE); fail = true; break; }
         s = code >> 2;
         rot = rot * 1664525u + 1013904223u;
         if (++steps > (1u << 22)) { if (gl == 0) set_err(m.cnt, ERR_WALK); fail = true; break; }
-        tvv = Gm::load(m, m.tv[s]);
+        tvv = Gm::load(m, TV(m, s));
     }
 
     if (!fail) {
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(256) k_attempt_coop(AttemptArgs<D> A, RoundSel
                 if (j < items) {
                     const int t = sv.k[head + j / M];
                     const int i = j % M;
-                    const int code = tn_i[(size_t)t * 4 + i];
+                    const int code = TNI(m, t, i);
                     if (code < 0) {
                         pushB = true; fcode = t * 4 + i; ocode = code;
                     } else {
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(256) k_attempt_coop(AttemptArgs<D> A, RoundSel
                             pushB = true; fcode = t * 4 + i; ocode = code;
                         } else {
                             tests++;
-                            const typename Gm::Verts nv = Gm::load(m, m.tv[n]);
+                            const typename Gm::Verts nv = Gm::load(m, TV(m, n));
                             if (Gm::conflict(cx, nv, p)) {
                                 const int old = atomicMin(&m.owner[n], key_k);
                                 if (old < key_k) lostLane = true;
@@ -254,7 +256,6 @@ __global__ void __launch_bounds__(256) k_commit_coop(CheckArgs<D> A, const int *
         if (gl == 0) m.cnt->oom_soft = 1;
         return;
     }
-    int *tn_i = reinterpret_cast<int *>(m.tn);
 
     // phase A: one lane per boundary facet: new simplex, outer back-pointer, marker in the dead simplex
     for (int j = gl; j < nb; j += G) {
@@ -262,13 +263,13 @@ __global__ void __launch_bounds__(256) k_commit_coop(CheckArgs<D> A, const int *
         const int t = fc >> 2, i = fc & 3;
         const int outer = sv.o[j];
         const int T = base + j;
-        int4 verts = m.tv[t];
+        int4 verts = TV(m, t);
         set4(verts, i, v);
-        m.tv[T] = verts;
-        tn_i[(size_t)T * 4 + i] = outer;
-        if (M == 3) tn_i[(size_t)T * 4 + 3] = -1;
-        if (outer >= 0) tn_i[(size_t)(outer >> 2) * 4 + (outer & 3)] = T * 4 + i;
-        tn_i[(size_t)t * 4 + i] = -(T * 4 + i) - 2;
+        TV(m, T) = verts;
+        TNI(m, T, i) = outer;
+        if (M == 3) TNI(m, T, 3) = -1;
+        if (outer >= 0) TNI(m, outer >> 2, outer & 3) = T * 4 + i;
+        TNI(m, t, i) = -(T * 4 + i) - 2;
     }
     __syncwarp(gmask);
     // phase B: one lane per (new simplex, facet containing v): pivot around the ridge through the dead cavity
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(256) k_commit_coop(CheckArgs<D> A, const int *
         int k = it % (M - 1);
         if (k >= i) k++;
         const int T = base + j;
-        int4 cv = m.tv[t];
+        int4 cv = TV(m, t);
         int r0 = -1, r1 = -1;
         for (int sidx = 0; sidx < M; sidx++) {
             if (sidx == i || sidx == k) continue;
@@ -288,14 +289,14 @@ __global__ void __launch_bounds__(256) k_commit_coop(CheckArgs<D> A, const int *
         }
         int cur = t, enter = i, exitf = k;
         for (;;) {
-            const int e = tn_i[(size_t)cur * 4 + exitf];   // plain load: markers were written by this group (phase A)
+            const int e = TNI(m, cur, exitf);   // plain load: markers were written by this group (phase A)
             if (e <= -2) {
                 const int sc = -(e + 2);
-                tn_i[(size_t)T * 4 + k] = (sc >> 2) * 4 + enter;
+                TNI(m, T, k) = (sc >> 2) * 4 + enter;
                 break;
             }
             const int nxt = e >> 2, jb = e & 3;
-            cv = m.tv[nxt];
+            cv = TV(m, nxt);
             int y = -1;
             for (int sidx = 0; sidx < M; sidx++) {
                 if (sidx == jb) continue;

@@ -30,15 +30,18 @@ struct EngineOptions {
     int big_capk = 8192;         // killed capacity of an overflow slot
     int capk = 64;               // killed capacity of a regular slot
     int capb = 132;              // boundary capacity of a regular slot (2*capk + 4)
-    int min_attempt = 1 << 17;   // attempt at least this many points per round (keeps the SMs busy)
-    double attempt_div = 16.0;   // otherwise attempt about (inserted vertices)/attempt_div points per round
+    int min_attempt = 8192;      // attempt at least this many points per round (keeps the SMs busy)
+    double attempt_div = 64.0;   // otherwise attempt about (inserted vertices)/attempt_div points per round: about n/60
+                                 // disjoint footprints fit into a mesh of n vertices, so denser attempts only lose (measured)
     int stage0 = 256;            // size of the first stage
     int stats = 0;               // accumulate W/E/K/C counters (atomics; keep off when timing)
     int verbose = 0;
     int profile = 0;             // CUDA-event time per kernel class (attempt / check / retri / setup)
     int coop = 1;                // lane-group cooperative kernels (GPU build); 0 = thread-per-point bodies
-    int group = 0;               // lanes per point: 0 = choose per round (32 for small rounds, 8 for large), else 8 or 32
-    int coop_switch = 12288;     // rounds with more selected points than this use 8 lanes per point
+    int group = 32;              // lanes per point: 32 (a warp per point, fastest at every round size measured) or 8;
+                                 // 0 = 32 for rounds up to coop_switch points, group_big above
+    int coop_switch = 12288;
+    int group_big = 8;
     int select_mode = 1;         // 1 = stratified selection along the Morton-ordered active list, 0 = random subset
     int rounds_per_sync = 4;     // rounds launched back to back between two host read-backs of the counters
     double tet_factor = 0.0;     // simplex slots per vertex (0 = default: 31 in 3D, 7.5 in 2D)
@@ -54,6 +57,7 @@ inline void options_from_env(EngineOptions &o) {
     if (const char *e = getenv("VOR_TET_FACTOR")) o.tet_factor = atof(e);
     if (const char *e = getenv("VOR_COOP")) o.coop = atoi(e);
     if (const char *e = getenv("VOR_GROUP")) o.group = atoi(e);
+    if (const char *e = getenv("VOR_GROUP_BIG")) o.group_big = atoi(e);
     if (const char *e = getenv("VOR_COOP_SWITCH")) o.coop_switch = atoi(e);
     if (const char *e = getenv("VOR_ROUNDS_PER_SYNC")) o.rounds_per_sync = atoi(e);
     if (const char *e = getenv("VOR_SELECT_MODE")) o.select_mode = atoi(e);
@@ -116,7 +120,7 @@ template <int D> class Engine {
         prof.on = opt.profile != 0;
     }
     ~Engine() {
-        be::dfree(mesh.pts); be::dfree(mesh.tv); be::dfree(mesh.tn); be::dfree(mesh.owner); be::dfree(mesh.seed);
+        be::dfree(mesh.pts); be::dfree(mesh.tet); be::dfree(mesh.owner); be::dfree(mesh.seed);
         be::dfree(mesh.ptTet); be::dfree(mesh.cnt); be::dfree(inputIdx); be::dfree(vidOfInput); be::dfree(keysAll);
         be::dfree(d_boxLo); be::dfree(d_boxHi); be::dfree(act); be::dfree(act2); be::dfree(blockCnt); be::dfree(d_edges);
         free_scratch();
@@ -167,8 +171,7 @@ template <int D> class Engine {
         long long nc = std::max(need, (long long)mesh.cap + mesh.cap / 2);
         nc = std::min(nc, (1LL << 29) - 1);
         const int old = mesh.cap;
-        grow(mesh.tv, (size_t)old, (size_t)nc);
-        grow(mesh.tn, (size_t)old, (size_t)nc);
+        grow(mesh.tet, 2 * (size_t)old, 2 * (size_t)nc);
         grow(mesh.owner, (size_t)old, (size_t)nc);
         fill_i(mesh.owner + old, OWNER_FREE, (size_t)(nc - old));
         mesh.cap = (int)nc;
@@ -315,7 +318,7 @@ template <int D> class Engine {
         be::h2d(d_boxHi, boxHi.data(), sizeof(double) * (size_t)nsets * D, stream);
         // super vertices + root simplices (simplex s = root of set s), positively oriented
         std::vector<Pt> sp((size_t)nsuper);
-        std::vector<int4> rtv((size_t)nsets), rtn((size_t)nsets);
+        std::vector<int4> rtet(2 * (size_t)nsets);
         std::vector<int> rseed((size_t)nsuper, -1);
         Counters dummy;
         memset(&dummy, 0, sizeof(dummy));
@@ -325,12 +328,11 @@ template <int D> class Engine {
             int4 v;
             v.x = s * M; v.y = s * M + 1; v.z = s * M + 2; v.w = (D == 3) ? s * M + 3 : -1;
             if (orient_host(cx, &sp[(size_t)s * M]) < 0) std::swap(v.x, v.y);
-            rtv[s] = v;
-            rtn[s] = int4{-1, -1, -1, -1};
+            rtet[2 * (size_t)s] = v;
+            rtet[2 * (size_t)s + 1] = int4{-1, -1, -1, -1};
         }
         be::h2d(mesh.pts, sp.data(), sizeof(Pt) * (size_t)nsuper, stream);
-        be::h2d(mesh.tv, rtv.data(), sizeof(int4) * (size_t)nsets, stream);
-        be::h2d(mesh.tn, rtn.data(), sizeof(int4) * (size_t)nsets, stream);
+        be::h2d(mesh.tet, rtet.data(), sizeof(int4) * 2 * (size_t)nsets, stream);
         be::h2d(mesh.seed, rseed.data(), sizeof(int) * (size_t)nsuper, stream);
         fill_i(mesh.ptTet, 0, (size_t)nsuper);
         fill_i(inputIdx, -1, (size_t)nsuper);
@@ -501,8 +503,8 @@ template <int D> class Engine {
                 const RoundSel sel{nact, stride, (int)((roundSalt >> 8) % (uint32_t)stride), nsel};
                 AttemptArgs<D> aa{mesh, scr, act, bits, roundSalt, 0u, stride, sel.offset, keybase, opt.stats};
                 CheckArgs<D> ca{mesh, scr, bits, roundSalt, keybase};
-                const int G = opt.group ? opt.group : (nsel > opt.coop_switch ? 8 : 32);
-                if (G == 32) launch_round<32>(aa, ca, sel); else launch_round<8>(aa, ca, sel);
+                const int G = opt.group ? opt.group : (nsel > opt.coop_switch ? opt.group_big : 32);
+                if (G == 8) launch_round<8>(aa, ca, sel); else launch_round<32>(aa, ca, sel);
                 epoch--;
                 rs.rounds++;
             }

@@ -11,9 +11,10 @@
 //
 // Store (SoA, all in HBM):
 //   pts[v]    coordinates (double4 in 3D: one 32 B sector per vertex; double2 in 2D)
-//   tv[t]     int4 vertex ids of simplex t (2D uses x,y,z)
-//   tn[t]     int4 neighbour codes: (neighbour << 2 | slot in neighbour that points back), -1 = outside the
-//             super simplex; slot i is opposite vertex i.  The reference keeps an unordered Vec (delaunay_tree.rs:15).
+//   tet[2t]   int4 vertex ids of simplex t (2D uses x,y,z)                      } one 32 B record (sector) per simplex:
+//   tet[2t+1] int4 neighbour codes: (neighbour << 2 | slot in neighbour that    } testing a simplex also brings its
+//             points back), -1 = outside the super simplex; slot i is opposite  } adjacency into L1/L2 for the next
+//             vertex i.  The reference keeps an unordered Vec (delaunay_tree.rs:15).   BFS level / walk step
 //   owner[t]  >= 0: reservation key of the current round (OWNER_FREE when untouched)
 //             <  0: simplex is dead, ~owner = a simplex created by the insertion that killed it (forwarding)
 //   seed[v]   pending point: a simplex to start its walk from; -1 once inserted
@@ -41,8 +42,7 @@ template <> struct Dim<2> { using Pt = double2; static constexpr int M = 3; };
 
 template <int D> struct Mesh {
     typename Dim<D>::Pt *pts;
-    int4 *tv;
-    int4 *tn;
+    int4 *tet;    // interleaved records: tet[2t] = vertex ids, tet[2t+1] = neighbour codes (one 32 B sector per simplex)
     int *owner;
     int *seed;
     int *ptTet;
@@ -50,6 +50,10 @@ template <int D> struct Mesh {
     int cap;      // simplex slots allocated
     int nsuper;   // vertices [0, nsuper) are super vertices
 };
+
+template <int D> VOR_HD int4 &TV(const Mesh<D> &m, int t) { return m.tet[2 * (size_t)t]; }
+template <int D> VOR_HD int4 &TN(const Mesh<D> &m, int t) { return m.tet[2 * (size_t)t + 1]; }
+template <int D> VOR_HD int &TNI(const Mesh<D> &m, int t, int i) { return reinterpret_cast<int *>(m.tet)[8 * (size_t)t + 4 + i]; }
 
 struct Scratch {
     int *killed, *bfacet, *bouter;     // contiguous per slot: entry j of slot s at [s * cap + j] (coalesced for a lane group)
@@ -171,7 +175,7 @@ template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
     // -- visibility walk
     unsigned rot = (unsigned)v * 2654435761u;
     unsigned steps = 0;
-    typename G::Verts tvv = G::load(m, m.tv[s]);
+    typename G::Verts tvv = G::load(m, TV(m, s));
     for (;;) {
         const int mk = G::beyond_mask(cx, tvv, p);
         if (mk == 0) break;
@@ -181,12 +185,12 @@ template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
             const int i = (r0 + k) % M;
             if ((mk >> i) & 1) { go = i; break; }
         }
-        const int code = get4(m.tn[s], go);
+        const int code = get4(TN(m, s), go);
         if (code < 0) { set_err(m.cnt, ERR_OUTSIDE); return; }
         s = code >> 2;
         rot = rot * 1664525u + 1013904223u;
         if (++steps > (1u << 22)) { set_err(m.cnt, ERR_WALK); return; }
-        tvv = G::load(m, m.tv[s]);
+        tvv = G::load(m, TV(m, s));
     }
     m.seed[v] = s;
 
@@ -208,7 +212,7 @@ template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
         sv.k[0] = s;
         for (int head = 0; head < nk; head++) {
             const int t = sv.k[(size_t)head * sv.stride];
-            const int4 nbr = m.tn[t];
+            const int4 nbr = TN(m, t);
             for (int i = 0; i < M; i++) {
                 const int code = get4(nbr, i);
                 int isout = 1;
@@ -219,7 +223,7 @@ template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
                     if (ow < key_k) goto lost;               // a better point holds it
                     if (ow != key_o) {                       // not yet classified by me
                         tests++;
-                        const typename G::Verts nv = G::load(m, m.tv[n]);
+                        const typename G::Verts nv = G::load(m, TV(m, n));
                         if (G::conflict(cx, nv, p)) {
                             if (atomic_min_i(&m.owner[n], key_k) < key_k) goto lost;
                             isout = 0;
@@ -364,19 +368,18 @@ template <int D> VOR_HD void retri_body(const RetriArgs<D> &A, int w) {
 
     // phase A: new simplex j hangs on boundary facet j; link it to the outer simplex and leave a marker
     // -(code)-2 in the dead simplex so that the pivots of phase B can find it.
-    int *tn_i = reinterpret_cast<int *>(m.tn);
     for (int j = 0; j < nb; j++) {
         const int fc = sv.f[(size_t)j * sv.stride];
         const int t = fc >> 2, i = fc & 3;
         const int outer = sv.o[(size_t)j * sv.stride];
         const int T = base + j;
-        int4 verts = m.tv[t];
+        int4 verts = TV(m, t);
         set4(verts, i, v);
-        m.tv[T] = verts;
-        tn_i[(size_t)T * 4 + i] = outer;
-        if (M == 3) tn_i[(size_t)T * 4 + 3] = -1;
-        if (outer >= 0) tn_i[(size_t)(outer >> 2) * 4 + (outer & 3)] = T * 4 + i;
-        tn_i[(size_t)t * 4 + i] = -(T * 4 + i) - 2;
+        TV(m, T) = verts;
+        TNI(m, T, i) = outer;
+        if (M == 3) TNI(m, T, 3) = -1;
+        if (outer >= 0) TNI(m, outer >> 2, outer & 3) = T * 4 + i;
+        TNI(m, t, i) = -(T * 4 + i) - 2;
     }
     // phase B: sibling links.  The face of T opposite slot k (k != i) contains v and the ridge R = T's vertices
     // other than slots i,k.  Pivot around R through the dead cavity until a marker is met.
@@ -384,7 +387,7 @@ template <int D> VOR_HD void retri_body(const RetriArgs<D> &A, int w) {
         const int fc = sv.f[(size_t)j * sv.stride];
         const int t = fc >> 2, i = fc & 3;
         const int T = base + j;
-        const int4 tverts = m.tv[t];
+        const int4 tverts = TV(m, t);
         for (int k = 0; k < M; k++) {
             if (k == i) continue;
             int cur = t, enter = i, exitf = k;
@@ -396,14 +399,14 @@ template <int D> VOR_HD void retri_body(const RetriArgs<D> &A, int w) {
                 if (r0 < 0) r0 = get4(cv, sidx); else r1 = get4(cv, sidx);
             }
             for (;;) {
-                const int e = tn_i[(size_t)cur * 4 + exitf];
+                const int e = TNI(m, cur, exitf);
                 if (e <= -2) {
                     const int sc = -(e + 2);
-                    tn_i[(size_t)T * 4 + k] = (sc >> 2) * 4 + enter;
+                    TNI(m, T, k) = (sc >> 2) * 4 + enter;
                     break;
                 }
                 const int nxt = e >> 2, jb = e & 3;
-                cv = m.tv[nxt];
+                cv = TV(m, nxt);
                 int y = -1;
                 for (int sidx = 0; sidx < M; sidx++) {
                     if (sidx == jb) continue;

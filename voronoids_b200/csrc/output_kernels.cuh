@@ -38,12 +38,12 @@ VOR_HD bool edge_owner3(const Mesh<3> &m, int t, const int4 &tv, int sa, int sb)
     (void)enterf;
     int cur = t;
     for (int guard = 0; guard < (1 << 20); guard++) {
-        const int code = get4(m.tn[cur], exitf);
+        const int code = get4(TN(m, cur), exitf);
         if (code < 0) return false; // cannot happen for an edge of two real vertices
         const int nxt = code >> 2, jb = code & 3;
         if (nxt == t) return true;
         if (nxt < t) return false;
-        const int4 nv = m.tv[nxt];
+        const int4 nv = TV(m, nxt);
         int y = -1;
         for (int s = 0; s < 4; s++) {
             if (s == jb) continue;
@@ -70,7 +70,7 @@ template <int D> VOR_HD void edges_body(const EdgeArgs<D> &A, int t) {
     constexpr int M = Dim<D>::M;
     const Mesh<D> &m = A.m;
     if (!simplex_live(m, t)) return;
-    const int4 tv = m.tv[t];
+    const int4 tv = TV(m, t);
     if constexpr (D == 3) {
         for (int sa = 0; sa < M; sa++)
             for (int sb = sa + 1; sb < M; sb++) {
@@ -79,7 +79,7 @@ template <int D> VOR_HD void edges_body(const EdgeArgs<D> &A, int t) {
                 if (edge_owner3(m, t, tv, sa, sb)) edge_emit(A, va, vb);
             }
     } else {
-        const int4 tn = m.tn[t];
+        const int4 tn = TN(m, t);
         for (int i = 0; i < 3; i++) { // edge opposite slot i
             const int va = get4(tv, (i + 1) % 3), vb = get4(tv, (i + 2) % 3);
             if (va < m.nsuper || vb < m.nsuper) continue;
@@ -122,8 +122,8 @@ template <int D> VOR_HD void validate_body(const ValidateArgs<D> &A, int t) {
     if (!simplex_live(m, t)) return;
     atomic_add_ull(A.nlive, 1ULL);
     PredCtx cx{m.cnt};
-    const int4 tv = m.tv[t];
-    const int4 tn = m.tn[t];
+    const int4 tv = TV(m, t);
+    const int4 tn = TN(m, t);
     const typename G::Verts vt = G::load(m, tv);
     if (G::orient(cx, vt) <= 0) atomic_add_i(&A.fail[0], 1);
     for (int i = 0; i < M; i++) {
@@ -131,9 +131,9 @@ template <int D> VOR_HD void validate_body(const ValidateArgs<D> &A, int t) {
         if (code < 0) continue;
         const int nb = code >> 2, jb = code & 3;
         if (!simplex_live(m, nb)) { atomic_add_i(&A.fail[1], 1); continue; }
-        const int back = get4(m.tn[nb], jb);
+        const int back = get4(TN(m, nb), jb);
         if (back != t * 4 + i) { atomic_add_i(&A.fail[2], 1); continue; }
-        const int4 nv = m.tv[nb];
+        const int4 nv = TV(m, nb);
         bool ok = true;
         for (int k = 0; k < M; k++) {
             if (k == jb) continue;
@@ -221,8 +221,8 @@ template <int D> VOR_HD void export_fill_body(const ExportFillArgs<D> &A, int c)
     constexpr int M = Dim<D>::M;
     const Mesh<D> &m = A.m;
     const int t = A.liveId[c];
-    const int4 tv = m.tv[t];
-    const int4 tn = m.tn[t];
+    const int4 tv = TV(m, t);
+    const int4 tn = TN(m, t);
     for (int k = 0; k < M; k++) {
         const int v = get4(tv, k);
         A.verts[(size_t)c * M + k] = v < m.nsuper ? v : A.idOffset + A.inputIdx[v];

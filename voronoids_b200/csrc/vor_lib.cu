@@ -3,6 +3,6 @@
 #include "backend_cuda.cuh"
 #include "engine.cuh"
 
-namespace vor { namespace be { unsigned long long g_launches = 0; } }
+namespace vor { namespace be { unsigned long long g_launches = 0; Pool g_pool; } }
 
 #include "capi.inl"
