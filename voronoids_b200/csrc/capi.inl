@@ -262,7 +262,7 @@ vor_status vor_tree_check_delaunay(vor_tree *t, int *ok, int32_t *fail_counts) {
         return t->visit([&](auto &e) -> vor_status {
             int f[8];
             e.validate(f);
-            if (ok) *ok = (f[0] | f[1] | f[2] | f[3] | f[4] | f[5]) == 0;
+            if (ok) *ok = (f[0] | f[1] | f[2] | f[3] | f[4]) == 0;
             if (fail_counts) for (int i = 0; i < 5; i++) fail_counts[i] = f[i];
             return VOR_OK;
         });

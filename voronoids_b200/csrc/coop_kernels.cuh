@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256, VOR_ATTEMPT_MINBLOCKS) k_attempt_coop(Att
 
     // -- visibility walk: lane k < M tests facet k
     unsigned rot = (unsigned)v * 2654435761u;
-    typename Gm::Verts tvv = Gm::loadc(m, s);
+    typename Gm::Verts tvv = Gm::load(m, TV(m, s));
     bool fail = false;
     for (;;) {
         const int ok = gl < M ? GeoCoop<D>::orient_repl(cx, tvv, p, gl) : 1;
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256, VOR_ATTEMPT_MINBLOCKS) k_attempt_coop(Att
         s = code >> 2;
         rot = rot * 1664525u + 1013904223u;
         if (++steps > (1u << 22)) { if (gl == 0) set_err(m.cnt, ERR_WALK); fail = true; break; }
-        tvv = Gm::loadc(m, s);
+        tvv = Gm::load(m, TV(m, s));
     }
 
     if (!fail) {
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256, VOR_ATTEMPT_MINBLOCKS) k_attempt_coop(Att
                             pushB = true; fcode = t * 4 + i; ocode = code;
                         } else {
                             tests++;
-                            const typename Gm::Verts nv = Gm::loadc(m, n);
+                            const typename Gm::Verts nv = Gm::load(m, TV(m, n));
                             if (Gm::conflict(cx, nv, p)) {
                                 const int old = atomicMin(&m.owner[n], key_k);
                                 if (old < key_k) lostLane = true;
@@ -257,8 +257,7 @@ __global__ void __launch_bounds__(256) k_commit_coop(CheckArgs<D> A, const int *
         return;
     }
 
-    // phase A: one lane per boundary facet: new simplex (ids + coordinate block), outer back-pointer, marker in the dead simplex
-    const typename Geo<D>::Pt pv = m.pts[v];
+    // phase A: one lane per boundary facet: new simplex, outer back-pointer, marker in the dead simplex
     for (int j = gl; j < nb; j += G) {
         const int fc = sv.f[j];
         const int t = fc >> 2, i = fc & 3;
@@ -267,9 +266,6 @@ __global__ void __launch_bounds__(256) k_commit_coop(CheckArgs<D> A, const int *
         int4 verts = TV(m, t);
         set4(verts, i, v);
         TV(m, T) = verts;
-        typename Geo<D>::Verts cc = Geo<D>::loadc(m, t);
-        Geo<D>::set_vert(cc, i, pv);
-        Geo<D>::storec(m, T, cc);
         TNI(m, T, i) = outer;
         if (M == 3) TNI(m, T, 3) = -1;
         if (outer >= 0) TNI(m, outer >> 2, outer & 3) = T * 4 + i;

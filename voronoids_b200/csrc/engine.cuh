@@ -120,7 +120,7 @@ template <int D> class Engine {
         prof.on = opt.profile != 0;
     }
     ~Engine() {
-        be::dfree(mesh.pts); be::dfree(mesh.tet); be::dfree(mesh.tc); be::dfree(mesh.owner); be::dfree(mesh.seed);
+        be::dfree(mesh.pts); be::dfree(mesh.tet); be::dfree(mesh.owner); be::dfree(mesh.seed);
         be::dfree(mesh.ptTet); be::dfree(mesh.cnt); be::dfree(inputIdx); be::dfree(vidOfInput); be::dfree(keysAll);
         be::dfree(d_boxLo); be::dfree(d_boxHi); be::dfree(act); be::dfree(act2); be::dfree(blockCnt); be::dfree(d_edges);
         free_scratch();
@@ -172,7 +172,6 @@ template <int D> class Engine {
         nc = std::min(nc, (1LL << 29) - 1);
         const int old = mesh.cap;
         grow(mesh.tet, 2 * (size_t)old, 2 * (size_t)nc);
-        grow(mesh.tc, (size_t)Geo<D>::TCS * (size_t)old, (size_t)Geo<D>::TCS * (size_t)nc);
         grow(mesh.owner, (size_t)old, (size_t)nc);
         fill_i(mesh.owner + old, OWNER_FREE, (size_t)(nc - old));
         mesh.cap = (int)nc;
@@ -334,16 +333,6 @@ template <int D> class Engine {
         }
         be::h2d(mesh.pts, sp.data(), sizeof(Pt) * (size_t)nsuper, stream);
         be::h2d(mesh.tet, rtet.data(), sizeof(int4) * 2 * (size_t)nsets, stream);
-        {
-            std::vector<double> rtc((size_t)Geo<D>::TCS * (size_t)nsets);
-            for (int s = 0; s < nsets; s++) {
-                const int ids[4] = {rtet[2 * (size_t)s].x, rtet[2 * (size_t)s].y, rtet[2 * (size_t)s].z, rtet[2 * (size_t)s].w};
-                for (int k = 0; k < M; k++)
-                    for (int d = 0; d < D; d++) rtc[((size_t)s * M + k) * D + d] = superXYZ[(size_t)ids[k] * D + d];
-            }
-            be::h2d(mesh.tc, rtc.data(), sizeof(double) * rtc.size(), stream);
-            be::sync(stream);
-        }
         be::h2d(mesh.seed, rseed.data(), sizeof(int) * (size_t)nsuper, stream);
         fill_i(mesh.ptTet, 0, (size_t)nsuper);
         fill_i(inputIdx, -1, (size_t)nsuper);

@@ -15,9 +15,6 @@
 //   tet[2t+1] int4 neighbour codes: (neighbour << 2 | slot in neighbour that    } testing a simplex also brings its
 //             points back), -1 = outside the super simplex; slot i is opposite  } adjacency into L1/L2 for the next
 //             vertex i.  The reference keeps an unordered Vec (delaunay_tree.rs:15).   BFS level / walk step
-//   tc[t]     the simplex's vertex coordinates (copy of pts[tet[2t]]), so that the in-sphere / orientation operands
-//             of simplex t come with ONE dependent gather (the chain per BFS level is neighbour code -> coordinates
-//             -> atomicMin instead of code -> ids -> coordinates -> atomicMin)
 //   owner[t]  >= 0: reservation key of the current round (OWNER_FREE when untouched)
 //             <  0: simplex is dead, ~owner = a simplex created by the insertion that killed it (forwarding)
 //   seed[v]   pending point: a simplex to start its walk from; -1 once inserted
@@ -46,8 +43,6 @@ template <> struct Dim<2> { using Pt = double2; static constexpr int M = 3; };
 template <int D> struct Mesh {
     typename Dim<D>::Pt *pts;
     int4 *tet;    // interleaved records: tet[2t] = vertex ids, tet[2t+1] = neighbour codes (one 32 B sector per simplex)
-    double *tc;   // vertex COORDINATES of simplex t, D*(D+1) doubles (96 B in 3D): a conflict test or a walk step needs
-                  // one gather of this block instead of the record followed by D+1 dependent vertex gathers
     int *owner;
     int *seed;
     int *ptTet;
@@ -110,24 +105,6 @@ template <> struct Geo<3> {
     static VOR_HD Verts load(const Mesh<3> &m, const int4 &v) {
         Verts r; r.p0 = m.pts[v.x]; r.p1 = m.pts[v.y]; r.p2 = m.pts[v.z]; r.p3 = m.pts[v.w]; return r;
     }
-    static constexpr int TCS = 12;   // doubles per simplex in tc
-    static VOR_HD Verts loadc(const Mesh<3> &m, int t) {
-        const double4 *c = reinterpret_cast<const double4 *>(m.tc + (size_t)t * TCS);
-        const double4 a = c[0], b = c[1], d = c[2];
-        Verts r;
-        r.p0 = double4{a.x, a.y, a.z, 0.0}; r.p1 = double4{a.w, b.x, b.y, 0.0};
-        r.p2 = double4{b.z, b.w, d.x, 0.0}; r.p3 = double4{d.y, d.z, d.w, 0.0};
-        return r;
-    }
-    static VOR_HD void storec(const Mesh<3> &m, int t, const Verts &r) {
-        double4 *c = reinterpret_cast<double4 *>(m.tc + (size_t)t * TCS);
-        c[0] = double4{r.p0.x, r.p0.y, r.p0.z, r.p1.x};
-        c[1] = double4{r.p1.y, r.p1.z, r.p2.x, r.p2.y};
-        c[2] = double4{r.p2.z, r.p3.x, r.p3.y, r.p3.z};
-    }
-    static VOR_HD void set_vert(Verts &r, int i, const Pt &p) {
-        if (i == 0) r.p0 = p; else if (i == 1) r.p1 = p; else if (i == 2) r.p2 = p; else r.p3 = p;
-    }
     // bit i set <=> p is strictly beyond face i (orientation with vertex i replaced by p is negative)
     static VOR_HD int beyond_mask(PredCtx &cx, const Verts &t, const Pt &p) {
         int mk = 0;
@@ -146,18 +123,6 @@ template <> struct Geo<2> {
     struct Verts { Pt p0, p1, p2; };
     static VOR_HD Verts load(const Mesh<2> &m, const int4 &v) {
         Verts r; r.p0 = m.pts[v.x]; r.p1 = m.pts[v.y]; r.p2 = m.pts[v.z]; return r;
-    }
-    static constexpr int TCS = 6;
-    static VOR_HD Verts loadc(const Mesh<2> &m, int t) {
-        const double2 *c = reinterpret_cast<const double2 *>(m.tc + (size_t)t * TCS);
-        Verts r; r.p0 = c[0]; r.p1 = c[1]; r.p2 = c[2]; return r;
-    }
-    static VOR_HD void storec(const Mesh<2> &m, int t, const Verts &r) {
-        double2 *c = reinterpret_cast<double2 *>(m.tc + (size_t)t * TCS);
-        c[0] = r.p0; c[1] = r.p1; c[2] = r.p2;
-    }
-    static VOR_HD void set_vert(Verts &r, int i, const Pt &p) {
-        if (i == 0) r.p0 = p; else if (i == 1) r.p1 = p; else r.p2 = p;
     }
     static VOR_HD int beyond_mask(PredCtx &cx, const Verts &t, const Pt &p) {
         int mk = 0;
@@ -210,7 +175,7 @@ template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
     // -- visibility walk
     unsigned rot = (unsigned)v * 2654435761u;
     unsigned steps = 0;
-    typename G::Verts tvv = G::loadc(m, s);
+    typename G::Verts tvv = G::load(m, TV(m, s));
     for (;;) {
         const int mk = G::beyond_mask(cx, tvv, p);
         if (mk == 0) break;
@@ -225,7 +190,7 @@ template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
         s = code >> 2;
         rot = rot * 1664525u + 1013904223u;
         if (++steps > (1u << 22)) { set_err(m.cnt, ERR_WALK); return; }
-        tvv = G::loadc(m, s);
+        tvv = G::load(m, TV(m, s));
     }
     m.seed[v] = s;
 
@@ -258,7 +223,7 @@ template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
                     if (ow < key_k) goto lost;               // a better point holds it
                     if (ow != key_o) {                       // not yet classified by me
                         tests++;
-                        const typename G::Verts nv = G::loadc(m, n);
+                        const typename G::Verts nv = G::load(m, TV(m, n));
                         if (G::conflict(cx, nv, p)) {
                             if (atomic_min_i(&m.owner[n], key_k) < key_k) goto lost;
                             isout = 0;
@@ -411,9 +376,6 @@ template <int D> VOR_HD void retri_body(const RetriArgs<D> &A, int w) {
         int4 verts = TV(m, t);
         set4(verts, i, v);
         TV(m, T) = verts;
-        typename Geo<D>::Verts cc = Geo<D>::loadc(m, t);
-        Geo<D>::set_vert(cc, i, m.pts[v]);
-        Geo<D>::storec(m, T, cc);
         TNI(m, T, i) = outer;
         if (M == 3) TNI(m, T, 3) = -1;
         if (outer >= 0) TNI(m, outer >> 2, outer & 3) = T * 4 + i;

@@ -112,8 +112,7 @@ VOR_HD void edge_sum_body(const EdgeSumArgs &A, int i) {
 // ---- validation
 template <int D> struct ValidateArgs {
     Mesh<D> m;
-    int *fail;   // [8] failure counters: 0 orientation, 1 dead neighbour, 2 asymmetric adjacency, 3 facet mismatch, 4 not Delaunay,
-                 //     5 coordinate block differs from the vertex array
+    int *fail;   // [8] failure counters: 0 orientation, 1 dead neighbour, 2 asymmetric adjacency, 3 facet mismatch, 4 not Delaunay
     unsigned long long *nlive;
 };
 template <int D> VOR_HD void validate_body(const ValidateArgs<D> &A, int t) {
@@ -127,16 +126,6 @@ template <int D> VOR_HD void validate_body(const ValidateArgs<D> &A, int t) {
     const int4 tn = TN(m, t);
     const typename G::Verts vt = G::load(m, tv);
     if (G::orient(cx, vt) <= 0) atomic_add_i(&A.fail[0], 1);
-    {
-        const double *cb = m.tc + (size_t)t * G::TCS;
-        bool same = true;
-        for (int k = 0; k < M; k++) {
-            const typename G::Pt pk = m.pts[get4(tv, k)];
-            same &= cb[k * D] == pk.x && cb[k * D + 1] == pk.y;
-            if constexpr (D == 3) same &= cb[k * D + 2] == pk.z;
-        }
-        if (!same) atomic_add_i(&A.fail[5], 1);
-    }
     for (int i = 0; i < M; i++) {
         const int code = get4(tn, i);
         if (code < 0) continue;
