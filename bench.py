@@ -38,7 +38,11 @@ WORKLOADS = {
     "u2_1m": (2, "uniform", 1_000_000, 0, "2D uniform random 1M points (configs[1])"),
     "c3_5m": (3, "clustered", 5_000_000, 1, "3D Gaussian mixture 5M points (configs[3])"),
     "l3_5m": (3, "lattice", 5_000_000, 2, "3D jittered lattice 5M points (configs[3])"),
+    # batch of independent sets (configs[4]): 64 sets x 100k points per GPU in ONE device store; set s of rank r uses
+    # seed 1000 + 64 r + s
+    "b3_64x100k": (3, "batch", 6_400_000, 1000, "batch of 64 independent 3D uniform sets x 100k points per GPU (configs[4] shape)"),
 }
+BATCH_SETS, BATCH_SIZE = 64, 100_000
 CPU_SAMPLE = {3: 150_000, 2: 400_000}  # points of the same workload given to the CPU baseline (about 10-30 s)
 
 
@@ -98,9 +102,20 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bench_config(desc, n, dim, world):
+    """Same dict for both arms (the driver compares them)."""
+    return {"workload": desc, "points_per_gpu": n, "dim": dim, "gpus": world,
+            "parallelism": f"{world} independent point set(s), one per GPU, no collective",
+            "timed_region": "DelaunayTree::new + insertion of every point; value: input resident in HBM, e2e: host buffers in, edge list out",
+            "l2": "inputs larger than L2 (%.0f MB of coordinates, multi-GB simplex store)" % (n * dim * 8 / 1e6)}
+
+
 def make_points(name, rank):
     from voronoids_b200 import pointgen
     dim, kind, n, seed, desc = WORKLOADS[name]
+    if kind == "batch":
+        sets = [pointgen.uniform(BATCH_SIZE, dim, seed + BATCH_SETS * rank + s) for s in range(BATCH_SETS)]
+        return np.concatenate(sets, axis=0), dim, n, desc
     return pointgen.make(kind, n, dim, seed + 7919 * rank), dim, n, desc
 
 
@@ -110,7 +125,11 @@ def cpu_reference_run(name, steps, warmup, as_arm):
     dim, kind, n, seed, desc = WORKLOADS[name]
     ns = min(n, CPU_SAMPLE[dim])
     from voronoids_b200 import pointgen
-    pts = pointgen.make(kind, n, dim, seed)[:ns] if kind != "uniform" else pointgen.uniform(ns, dim, seed)
+    if kind == "batch":
+        ns = min(BATCH_SIZE, CPU_SAMPLE[dim])   # one set of the batch (sets are independent units)
+        pts = pointgen.uniform(ns, dim, seed)
+    else:
+        pts = pointgen.make(kind, n, dim, seed)[:ns] if kind != "uniform" else pointgen.uniform(ns, dim, seed)
     cores = O.lib().vo_ref_max_threads()
     times = []
     reps = (warmup + steps) if as_arm else 1
@@ -152,7 +171,7 @@ def main():
         line = {"impl": "reference", "metric": "delaunay_points_inserted_per_sec", "value": cb["value"], "unit": "points/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": desc, "points_per_set": n, "dim": dim, "sample_points": ns},
+                "config": bench_config(desc, n, dim, args.gpus),
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line), flush=True)
@@ -163,6 +182,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: voronoids_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line (NCCL prints its version there otherwise)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import voronoids_b200 as vb
@@ -173,6 +193,7 @@ def main():
     pts_dev = torch.from_numpy(pts_host).cuda()
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
+    boff = np.arange(BATCH_SETS + 1, dtype=np.int64) * BATCH_SIZE
 
     def step_device(stats=False, profile=False):
         """create + insert with device-resident input on torch's current stream; returns (ms, stats dict)."""
@@ -182,10 +203,17 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record(stream)
-        st = lib.vor_tree_create_device(dim, C.c_void_p(pts_dev.data_ptr()), n, local_rank, sptr, C.byref(h))
+        if kind == "batch":
+            st = lib.vor_tree_create_batch_device(dim, C.c_void_p(pts_dev.data_ptr()), boff.ctypes.data_as(_capi.i64p), BATCH_SETS, local_rank, sptr,
+                                                  C.byref(h))
+        else:
+            st = lib.vor_tree_create_device(dim, C.c_void_p(pts_dev.data_ptr()), n, local_rank, sptr, C.byref(h))
         if st != 0:
             raise RuntimeError(lib.vor_last_error().decode())
-        st = lib.vor_tree_insert_device(h, C.c_void_p(pts_dev.data_ptr()), n, 1)
+        if kind == "batch":
+            st = lib.vor_tree_insert_batch_device(h, C.c_void_p(pts_dev.data_ptr()), boff.ctypes.data_as(_capi.i64p))
+        else:
+            st = lib.vor_tree_insert_device(h, C.c_void_p(pts_dev.data_ptr()), n, 1)
         if st not in (0, 3):
             raise RuntimeError(lib.vor_last_error().decode())
         e1.record(stream)
@@ -259,7 +287,10 @@ def main():
     if not args.no_e2e:
         def step_e2e():
             t0 = time.perf_counter()
-            tree = vb.delaunay(pts_host, device=local_rank)
+            if kind == "batch":
+                tree = vb.delaunay_batch([pts_host[s * BATCH_SIZE:(s + 1) * BATCH_SIZE] for s in range(BATCH_SETS)], device=local_rank)
+            else:
+                tree = vb.delaunay(pts_host, device=local_rank)
             e = tree.edges()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
@@ -277,7 +308,8 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * n / float(te.item()), "unit": "points/s", "h2d_bytes_per_step": int(n * dim * 8), "d2h_bytes_per_step": int(ne * 8),
-               "api": "voronoids_b200.delaunay(points) + tree.edges()", "edges": ne}
+               "api": ("voronoids_b200.delaunay_batch(sets) + result.edges()" if kind == "batch" else "voronoids_b200.delaunay(points) + tree.edges()"),
+               "edges": ne}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -287,9 +319,7 @@ def main():
         line = {"metric": "delaunay_points_inserted_per_sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": desc, "points_per_set": n, "dim": dim, "sets": world, "parallelism": f"{world} independent set(s), one per GPU",
-                           "timed_region": "vor_tree_create_device + vor_tree_insert_device, input resident in HBM",
-                           "l2": "inputs larger than L2 (%.0f MB of coordinates, multi-GB store)" % (n * dim * 8 / 1e6)},
+                "config": bench_config(desc, n, dim, world),
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -27,6 +27,8 @@ inline void h2d(void *d, const void *h, size_t n, Stream) { std::memcpy(d, h, n)
 inline void d2h(void *h, const void *d, size_t n, Stream) { std::memcpy(h, d, n); }
 inline void d2d(void *d, const void *s, size_t n, Stream) { std::memcpy(d, s, n); }
 inline void sync(Stream) {}
+inline void d2h_big(void *h, const void *d, size_t n, Stream) { std::memcpy(h, d, n); }
+inline void h2d_big(void *d, const void *h, size_t n, Stream) { std::memcpy(d, h, n); }
 inline void *hmalloc_pinned(size_t bytes) { return std::malloc(bytes ? bytes : 16); }
 inline void hfree_pinned(void *p) { std::free(p); }
 inline void sort_pairs(uint64_t *ki, uint64_t *ko, uint32_t *vi, uint32_t *vo, size_t n, Stream) {

@@ -71,14 +71,17 @@ class VorError(RuntimeError):
 class Tree:
     """Thin RAII wrapper over a vor_tree handle (host-buffer entry points)."""
 
-    def __init__(self, lib, points=None, device=0, dim=None, set_offsets=None, insert=True):
+    def __init__(self, lib, points=None, device=0, dim=None, set_offsets=None, insert=True, one_shot=False):
         self._lib = lib
         self._h = tree_p()
         self.duplicates = False
         p, pp = as_f64(points)
         self.dim = p.shape[1] if dim is None else dim
         self.n = p.shape[0]
-        if set_offsets is None:
+        if one_shot:
+            # vor_delaunay: one host->device copy, DelaunayTree::new + insertion of every point (lib.rs:104-125)
+            self._check(lib.vor_delaunay(self.dim, pp, self.n, device, C.byref(self._h)))
+        elif set_offsets is None:
             self._check(lib.vor_tree_create(self.dim, pp, self.n, device, C.byref(self._h)))
             if insert:
                 self.insert(p)

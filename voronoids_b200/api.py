@@ -62,7 +62,7 @@ class DelaunayTree:
         self.dim = p.shape[1]
         self._t = _tree if _tree is not None else _capi.Tree(lib(), p, device=device, insert=False)
         self._cache = None
-        self._pts = np.zeros((0, self.dim))
+        self._chunks = []   # inserted point arrays (kept by reference; concatenated only if .vertices is asked for)
 
     new = classmethod(lambda cls, points, device=0: cls(points, device))
 
@@ -72,7 +72,7 @@ class DelaunayTree:
         self._cache = None
         p = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, self.dim)
         self._t.insert(p, mode=1)
-        self._pts = np.concatenate([self._pts, p], axis=0)
+        self._chunks.append(p)
 
     insert_points_parallel = add_points_to_tree
 
@@ -81,7 +81,7 @@ class DelaunayTree:
         self._cache = None
         p = np.asarray(point, dtype=np.float64).reshape(1, self.dim)
         self._t.insert(p, mode=0)
-        self._pts = np.concatenate([self._pts, p], axis=0)
+        self._chunks.append(p)
 
     # ---- queries
     @property
@@ -172,7 +172,9 @@ class DelaunayTree:
         return out
 
     def _points(self):
-        return self._pts
+        if len(self._chunks) != 1:
+            self._chunks = [np.concatenate(self._chunks, axis=0) if self._chunks else np.zeros((0, self.dim))]
+        return self._chunks[0]
 
     def close(self):
         self._t.close()
@@ -189,8 +191,10 @@ def delaunay(points, device=0):
     the (unique) Delaunay triangulation of points + super vertices, which is what the device rounds compute.
     """
     p = np.ascontiguousarray(points, dtype=np.float64)
-    t = PyDelauanyTree(p, device=device)
-    t.add_points_to_tree(p)
+    if p.ndim != 2 or p.shape[1] not in (2, 3):
+        raise ValueError("points must be [n, 2] or [n, 3]")
+    t = PyDelauanyTree(p, device=device, _tree=_capi.Tree(lib(), p, device=device, one_shot=True))
+    t._chunks.append(p)
     return t
 
 

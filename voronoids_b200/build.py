@@ -16,7 +16,7 @@ FLAGS = [
     "-fmad=false",              # predicates' error bounds assume individually rounded operations
     "--expt-relaxed-constexpr",
     "-diag-suppress", "550",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared",
 ]
 
 

@@ -3,10 +3,13 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <cstring>
 #include <stdexcept>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 #include "vor_common.cuh"
@@ -98,6 +101,70 @@ inline void h2d(void *d, const void *h, size_t n, Stream s) { VOR_CUDA(cudaMemcp
 inline void d2h(void *h, const void *d, size_t n, Stream s) { VOR_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
 inline void d2d(void *d, const void *s_, size_t n, Stream s) { VOR_CUDA(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s)); }
 inline void sync(Stream s) { VOR_CUDA(cudaStreamSynchronize(s)); }
+
+// Large copies between pageable host memory and the device go through two pinned staging buffers so that the DMA of
+// chunk i+1 overlaps the host memcpy of chunk i (a plain cudaMemcpy on pageable memory runs at a few GB/s).
+struct Staging {
+    static constexpr size_t CHUNK = (size_t)32 << 20;
+    char *buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2];
+    std::mutex mu;
+    void init() {
+        if (buf[0]) return;
+        for (int i = 0; i < 2; i++) {
+            VOR_CUDA(cudaMallocHost((void **)&buf[i], CHUNK));
+            VOR_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+    }
+};
+extern Staging g_staging;
+// host memcpy on a few threads: the destination of a result copy is usually freshly allocated memory, so the copy is
+// dominated by first-touch page faults, which scale with threads
+inline void par_memcpy(char *dst, const char *src, size_t n) {
+    const int T = 4;
+    if (n < ((size_t)4 << 20)) { memcpy(dst, src, n); return; }
+    std::thread th[T - 1];
+    const size_t part = (n / T + 4095) & ~(size_t)4095;
+    for (int i = 1; i < T; i++) {
+        const size_t off = std::min(n, part * i), len = std::min(n - off, part);
+        th[i - 1] = std::thread([=] { if (len) memcpy(dst + off, src + off, len); });
+    }
+    memcpy(dst, src, std::min(n, part));
+    for (int i = 0; i < T - 1; i++) th[i].join();
+}
+inline void d2h_big(void *h, const void *d, size_t n, Stream s) {
+    if (n < 4 * Staging::CHUNK) { VOR_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); VOR_CUDA(cudaStreamSynchronize(s)); return; }
+    std::lock_guard<std::mutex> lk(g_staging.mu);
+    g_staging.init();
+    const size_t nch = (n + Staging::CHUNK - 1) / Staging::CHUNK;
+    auto len = [&](size_t c) { return std::min(Staging::CHUNK, n - c * Staging::CHUNK); };
+    VOR_CUDA(cudaMemcpyAsync(g_staging.buf[0], d, len(0), cudaMemcpyDeviceToHost, s));
+    VOR_CUDA(cudaEventRecord(g_staging.ev[0], s));
+    for (size_t c = 0; c < nch; c++) {
+        const int cur = (int)(c & 1), nxt = cur ^ 1;
+        if (c + 1 < nch) {
+            VOR_CUDA(cudaMemcpyAsync(g_staging.buf[nxt], (const char *)d + (c + 1) * Staging::CHUNK, len(c + 1), cudaMemcpyDeviceToHost, s));
+            VOR_CUDA(cudaEventRecord(g_staging.ev[nxt], s));
+        }
+        VOR_CUDA(cudaEventSynchronize(g_staging.ev[cur]));
+        par_memcpy((char *)h + c * Staging::CHUNK, g_staging.buf[cur], len(c));
+    }
+}
+inline void h2d_big(void *d, const void *h, size_t n, Stream s) {
+    if (n < 4 * Staging::CHUNK) { VOR_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); VOR_CUDA(cudaStreamSynchronize(s)); return; }
+    std::lock_guard<std::mutex> lk(g_staging.mu);
+    g_staging.init();
+    const size_t nch = (n + Staging::CHUNK - 1) / Staging::CHUNK;
+    auto len = [&](size_t c) { return std::min(Staging::CHUNK, n - c * Staging::CHUNK); };
+    for (size_t c = 0; c < nch; c++) {
+        const int cur = (int)(c & 1);
+        if (c >= 2) VOR_CUDA(cudaEventSynchronize(g_staging.ev[cur]));   // the DMA that used this buffer is done
+        par_memcpy(g_staging.buf[cur], (const char *)h + c * Staging::CHUNK, len(c));
+        VOR_CUDA(cudaMemcpyAsync((char *)d + c * Staging::CHUNK, g_staging.buf[cur], len(c), cudaMemcpyHostToDevice, s));
+        VOR_CUDA(cudaEventRecord(g_staging.ev[cur], s));
+    }
+    VOR_CUDA(cudaStreamSynchronize(s));
+}
 inline void *hmalloc_pinned(size_t bytes) {
     void *p = nullptr;
     VOR_CUDA(cudaMallocHost(&p, bytes ? bytes : 16));

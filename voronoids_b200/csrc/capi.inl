@@ -121,8 +121,7 @@ vor_status vor_tree_create_batch(int dim, const double *points, const int64_t *s
         vor::be::set_device(device);
         const size_t n = (size_t)set_offsets[n_sets];
         DevBuf d(sizeof(double) * n * dim);
-        vor::be::h2d(d.p, points, sizeof(double) * n * dim, vor::be::Stream{});
-        vor::be::sync(vor::be::Stream{});
+        vor::be::h2d_big(d.p, points, sizeof(double) * n * dim, vor::be::Stream{});
         return vor_tree_create_batch_device(dim, (const double *)d.p, set_offsets, n_sets, device, nullptr, out);
     });
 }
@@ -170,8 +169,7 @@ vor_status vor_tree_insert_batch(vor_tree *t, const double *points, const int64_
         vor::be::set_device(t->device);
         const size_t n = (size_t)set_offsets[t->n_sets];
         DevBuf d(sizeof(double) * n * t->dim);
-        vor::be::h2d(d.p, points, sizeof(double) * n * t->dim, t->stream);
-        vor::be::sync(t->stream);
+        vor::be::h2d_big(d.p, points, sizeof(double) * n * t->dim, t->stream);
         return vor_tree_insert_batch_device(t, (const double *)d.p, set_offsets);
     });
 }
@@ -187,8 +185,7 @@ vor_status vor_delaunay(int dim, const double *points, size_t n, int device, vor
         if (!out || (dim != 2 && dim != 3)) { g_err = "bad argument"; return VOR_ERR_ARG; }
         vor::be::set_device(device);
         DevBuf d(sizeof(double) * n * dim);
-        vor::be::h2d(d.p, points, sizeof(double) * n * dim, vor::be::Stream{});
-        vor::be::sync(vor::be::Stream{});
+        vor::be::h2d_big(d.p, points, sizeof(double) * n * dim, vor::be::Stream{});
         vor_tree *t = nullptr;
         vor_status s = vor_tree_create_device(dim, (const double *)d.p, n, device, nullptr, &t);
         if (s != VOR_OK) return s;

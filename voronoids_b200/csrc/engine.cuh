@@ -695,6 +695,12 @@ template <int D> class Engine {
     // canonical edge list on the device; returns the number of edges
     long long edges() {
         if (nedges >= 0) return nedges;
+        const auto t0 = std::chrono::steady_clock::now();
+        auto lap = [&](const char *what) {
+            if (!opt.verbose) return;
+            be::sync(stream);
+            fprintf(stderr, "[vor] edges: %s at %.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        };
         const int nt = hcnt->ntets;
         int *deg = (int *)be::dmalloc(sizeof(int) * (size_t)(ninput + 1));
         int *cursor = (int *)be::dmalloc(sizeof(int) * (size_t)(ninput + 1));
@@ -702,24 +708,27 @@ template <int D> class Engine {
         be::dmemset(cursor, 0, sizeof(int) * (size_t)(ninput + 1), stream);
         EdgeArgs<D> ea{mesh, inputIdx, deg, cursor, nullptr, 0};
         VOR_LAUNCH(EdgeArgs<D>, edges_body<D>, nt, ea, stream);
+        lap("count pass");
         const long long total = scan_exclusive(deg, ninput + 1);
+        lap("scan");
         if (total > 0x7fffffffLL) fail(ERR_OOM, "more than 2^31 edges");
         uint32_t *hi = (uint32_t *)be::dmalloc(sizeof(uint32_t) * (size_t)std::max(total, 1LL));
         d_edges = (uint32_t *)be::dmalloc(sizeof(uint32_t) * 2 * (size_t)std::max(total, 1LL));
         ea.hi = hi;
         ea.pass = 1;
         VOR_LAUNCH(EdgeArgs<D>, edges_body<D>, nt, ea, stream);
+        lap("fill pass");
         RowSortArgs ra{deg, hi, d_edges, ninput};
         VOR_LAUNCH(RowSortArgs, row_sort_body, ninput, ra, stream);
         be::sync(stream);
+        lap("row sort");
         be::dfree(deg); be::dfree(cursor); be::dfree(hi);
         nedges = total;
         return nedges;
     }
     void copy_edges(uint32_t *h_out, long long cap) {
         const long long m = edges();
-        be::d2h(h_out, d_edges, sizeof(uint32_t) * 2 * (size_t)std::min(m, cap), stream);
-        be::sync(stream);
+        be::d2h_big(h_out, d_edges, sizeof(uint32_t) * 2 * (size_t)std::min(m, cap), stream);
     }
     unsigned long long edge_checksum() {
         const long long m = edges();
