@@ -157,9 +157,10 @@ __global__ void __launch_bounds__(256, VOR_ATTEMPT_MINBLOCKS) k_attempt_coop(Att
                                 if (old < key_k) lostLane = true;
                                 else if (old != key_k) { pushK = true; newT = n; }   // first lane to claim it appends it
                             } else {
-                                const int old = atomicMin(&m.owner[n], key_o);
-                                if (old < key_k) lostLane = true;
-                                else { pushB = true; fcode = t * 4 + i; ocode = code; }
+                                // outer-ring mark: fire and forget (RED, no round trip).  A better point that holds n
+                                // was either seen by the owner read above or is caught by the ownership check of commit.
+                                atomicMin(&m.owner[n], key_o);
+                                pushB = true; fcode = t * 4 + i; ocode = code;
                             }
                         }
                     }

@@ -42,8 +42,9 @@ struct EngineOptions {
                                  // 0 = 32 for rounds up to coop_switch points, group_big above
     int coop_switch = 12288;
     int group_big = 8;
+    int bulk_locate = 1;         // locate every point of a stage at its start (thread per point) instead of in its first attempt
     int select_mode = 1;         // 1 = stratified selection along the Morton-ordered active list, 0 = random subset
-    int rounds_per_sync = 4;     // rounds launched back to back between two host read-backs of the counters
+    int rounds_per_sync = 8;     // rounds launched back to back between two host read-backs of the counters
     double tet_factor = 0.0;     // simplex slots per vertex (0 = default: 31 in 3D, 7.5 in 2D)
 };
 
@@ -61,6 +62,7 @@ inline void options_from_env(EngineOptions &o) {
     if (const char *e = getenv("VOR_COOP_SWITCH")) o.coop_switch = atoi(e);
     if (const char *e = getenv("VOR_ROUNDS_PER_SYNC")) o.rounds_per_sync = atoi(e);
     if (const char *e = getenv("VOR_SELECT_MODE")) o.select_mode = atoi(e);
+    if (const char *e = getenv("VOR_BULK_LOCATE")) o.bulk_locate = atoi(e);
     if (const char *e = getenv("VOR_CAPK")) { o.capk = atoi(e); o.capb = 2 * o.capk + 4; }
 }
 
@@ -475,8 +477,12 @@ template <int D> class Engine {
     void run_stage_pipelined(int lo, int hi) {
         const int total = hi - lo;
         int nact = total, pending = total;
-        SeedArgs sd{keysAll, mesh.ptTet, mesh.seed, nsuper, lo, refLo, refHi, D * axisBits};
-        VOR_LAUNCH(SeedArgs, init_seeds_body, nact, sd, stream);
+        SeedArgs<D> sd{keysAll, mesh.pts, mesh.ptTet, mesh.owner, mesh.seed, nsuper, lo, refLo, refHi, D * axisBits};
+        VOR_LAUNCH(SeedArgs<D>, init_seeds_body<D>, nact, sd, stream);
+        if (opt.bulk_locate) {
+            LocateArgs<D> la{mesh, lo, opt.stats};
+            VOR_LAUNCH(LocateArgs<D>, locate_body<D>, nact, la, stream);
+        }
         IotaArgs ia{act, lo};
         VOR_LAUNCH(IotaArgs, iota_body, nact, ia, stream);
         pull_counters();
@@ -554,8 +560,8 @@ template <int D> class Engine {
 #endif
         int nact = hi - lo;
         int pending = nact;
-        SeedArgs sd{keysAll, mesh.ptTet, mesh.seed, nsuper, lo, refLo, refHi, D * axisBits};
-        VOR_LAUNCH(SeedArgs, init_seeds_body, nact, sd, stream);
+        SeedArgs<D> sd{keysAll, mesh.pts, mesh.ptTet, mesh.owner, mesh.seed, nsuper, lo, refLo, refHi, D * axisBits};
+        VOR_LAUNCH(SeedArgs<D>, init_seeds_body<D>, nact, sd, stream);
         IotaArgs ia{act, lo};
         VOR_LAUNCH(IotaArgs, iota_body, nact, ia, stream);
         int stall = 0;

@@ -148,16 +148,23 @@ VOR_HD void stage_bounds_body(const StageBoundsArgs &A, int pos) {
     if (pos == 0 || st != (int)(A.keys[pos - 1] >> STAGE_SHIFT)) A.stageLo[st] = pos;
 }
 
-struct SeedArgs {
+template <int D> struct SeedArgs {
     const uint64_t *keysAll;   // Morton keys of every real vertex, indexed by v - nsuper
+    const typename Dim<D>::Pt *pts;
     const int *ptTet;
+    const int *owner;
     int *seed;
     int nsuper;
     int lo;                    // first vertex of the stage being started
     int plo, phi;              // vertex range of the reference stage (already inserted), may be empty
     int setShift;              // D * axisBits
 };
-VOR_HD void init_seeds_body(const SeedArgs &A, int j) {
+VOR_HD double dist2(const double4 &a, const double4 &b) { return (a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y) + (a.z - b.z) * (a.z - b.z); }
+VOR_HD double dist2(const double2 &a, const double2 &b) { return (a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y); }
+// Seed of a point that enters the active list: among the 4 Morton neighbours of its key in the reference stage take
+// the vertex closest in space, start from the simplex created by that vertex's insertion and resolve the forwarding
+// chain HERE (bulk, fully parallel) instead of on the critical path of the first attempt.
+template <int D> VOR_HD void init_seeds_body(const SeedArgs<D> &A, int j) {
     const int v = A.lo + j;
     const uint64_t mask = (1ULL << STAGE_SHIFT) - 1ULL;
     const uint64_t key = A.keysAll[v - A.nsuper] & mask;
@@ -169,18 +176,62 @@ VOR_HD void init_seeds_body(const SeedArgs &A, int j) {
             const int mid = (lo + hi) >> 1;
             if ((A.keysAll[mid - A.nsuper] & mask) < key) lo = mid + 1; else hi = mid;
         }
+        const typename Dim<D>::Pt p = A.pts[v];
         int best = -1;
-        uint64_t bestd = ~0ULL;
-        for (int c = lo - 1; c <= lo; c++) {
+        double bestd = INFINITY;
+        for (int c = lo - 2; c <= lo + 1; c++) {
             if (c < A.plo || c >= A.phi) continue;
             const uint64_t kc = A.keysAll[c - A.nsuper] & mask;
             if ((int)(kc >> A.setShift) != set) continue;
-            const uint64_t d = kc > key ? kc - key : key - kc;
+            if (A.ptTet[c] < 0) continue;   // dropped duplicate
+            const double d = dist2(A.pts[c], p);
             if (d < bestd) { bestd = d; best = c; }
         }
-        if (best >= 0 && A.ptTet[best] >= 0) seed = A.ptTet[best];
+        if (best >= 0) seed = A.ptTet[best];
     }
+    int o;
+    while ((o = A.owner[seed]) < 0) seed = ~o;
     A.seed[v] = seed;
+}
+
+// Bulk point location at the start of a stage: every point of the stage walks from its seed to the simplex that
+// contains it (thread per point, the mesh is static here).  The walk of a point's FIRST attempt is the longest one
+// (about 9 steps from the Morton neighbour's simplex); doing it here, with the whole stage in flight, takes it off the
+// latency-critical path of the round kernels, which then only re-walk 0-3 steps after a neighbour's insertion.
+template <int D> struct LocateArgs {
+    Mesh<D> m;
+    int lo;
+    int stats;
+};
+template <int D> VOR_HD void locate_body(const LocateArgs<D> &A, int j) {
+    constexpr int M = Dim<D>::M;
+    using G = Geo<D>;
+    const Mesh<D> &m = A.m;
+    const int v = A.lo + j;
+    int s = m.seed[v];
+    if (s < 0) return;
+    PredCtx cx{m.cnt};
+    const typename G::Pt p = m.pts[v];
+    unsigned rot = (unsigned)v * 2654435761u;
+    unsigned steps = 0;
+    for (;;) {
+        const typename G::Verts tvv = G::load(m, TV(m, s));
+        const int mk = G::beyond_mask(cx, tvv, p);
+        if (mk == 0) break;
+        int go = 0;
+        const int r0 = (int)((rot >> 16) % (unsigned)M);
+        for (int k = 0; k < M; k++) {
+            const int i = (r0 + k) % M;
+            if ((mk >> i) & 1) { go = i; break; }
+        }
+        const int code = TNI(m, s, go);
+        if (code < 0) { set_err(m.cnt, ERR_OUTSIDE); return; }
+        s = code >> 2;
+        rot = rot * 1664525u + 1013904223u;
+        if (++steps > (1u << 22)) { set_err(m.cnt, ERR_WALK); return; }
+    }
+    m.seed[v] = s;
+    if (A.stats) atomic_add_ull(&m.cnt->walk_steps, steps);
 }
 
 // generic exclusive scan over int arrays: chunk sums -> serial scan of sums -> apply
