@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256, VOR_ATTEMPT_MINBLOCKS) k_attempt_coop(Att
     if (m.seed[v] < 0) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }   // already inserted
     PredCtx cx{m.cnt};
     const typename Gm::Pt p = m.pts[v];
-    const uint32_t q = bij_hash((uint32_t)a, A.bits, A.salt);
+    const uint32_t q = bij_hash((uint32_t)slot, A.bits, A.salt);   // unique among the slots of this round
     const int key_k = A.keybase | (int)(q << 1);
     const int key_o = key_k | 1;
 
@@ -155,7 +155,21 @@ __global__ void __launch_bounds__(256, VOR_ATTEMPT_MINBLOCKS) k_attempt_coop(Att
                             if (Gm::conflict(cx, nv, p)) {
                                 const int old = atomicMin(&m.owner[n], key_k);
                                 if (old < key_k) lostLane = true;
-                                else if (old != key_k) { pushK = true; newT = n; }   // first lane to claim it appends it
+                                else if (old != key_k) {   // first lane to claim it appends it
+                                    pushK = true; newT = n;
+#ifdef VOR_PREFETCH_NEXT_LEVEL
+                                    // n joins the frontier: its neighbour codes share the sector just read; pull the
+                                    // neighbours' records and owner words towards L2 for the next BFS level
+                                    const int4 nn = TN(m, n);
+                                    for (int k2 = 0; k2 < M; k2++) {
+                                        const int c2 = get4(nn, k2);
+                                        if (c2 >= 0 && (c2 >> 2) != t) {
+                                            asm volatile("prefetch.global.L2 [%0];" ::"l"(&TV(m, c2 >> 2)));
+                                            asm volatile("prefetch.global.L2 [%0];" ::"l"(&m.owner[c2 >> 2]));
+                                        }
+                                    }
+#endif
+                                }
                             } else {
                                 // outer-ring mark: fire and forget (RED, no round trip).  A better point that holds n
                                 // was either seen by the owner read above or is caught by the ownership check of commit.
@@ -233,7 +247,7 @@ __global__ void __launch_bounds__(256) k_commit_coop(CheckArgs<D> A, const int *
     if (A.scr.slotStatus[slot] != ST_OK) return;
     const int a = slot_entry(rsel, slot);
     const int v = act[a];
-    const uint32_t q = bij_hash((uint32_t)a, A.bits, A.salt);
+    const uint32_t q = bij_hash((uint32_t)slot, A.bits, A.salt);   // unique among the slots of this round
     const int key_k = A.keybase | (int)(q << 1);
     const int key_o = key_k | 1;
     const ScrView sv = scr_view(A.scr, slot, A.scr.slotBig[slot]);
@@ -318,6 +332,48 @@ __global__ void __launch_bounds__(256) k_commit_coop(CheckArgs<D> A, const int *
             atomicAdd(&m.cnt->created, (unsigned long long)nb);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// order-preserving compaction of the active list (pending entries keep their Morton order): block counts,
+// single-block exclusive scan of the counts, scatter with ballot ranks
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_compact_count(const int *act, const int *seed, int *blockCnt, int n) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int keep = (i < n) && (seed[act[i]] >= 0);
+    const int c = __syncthreads_count(keep);
+    if (threadIdx.x == 0) blockCnt[blockIdx.x] = c;
+}
+__global__ void __launch_bounds__(1024) k_compact_scan(int *blockCnt, int nb, long long *total) {
+    __shared__ int part[1024];
+    const int per = (nb + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(lo + per, nb);
+    int s = 0;
+    for (int i = lo; i < hi; i++) s += blockCnt[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {   // Hillis-Steele inclusive scan
+        const int v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = part[threadIdx.x] - s;        // exclusive prefix of this thread's segment
+    for (int i = lo; i < hi; i++) { const int x = blockCnt[i]; blockCnt[i] = run; run += x; }
+    if (threadIdx.x == 1023) *total = part[1023];
+}
+__global__ void __launch_bounds__(256) k_compact_scatter(const int *act, const int *seed, const int *blockCnt, int *out, int n) {
+    __shared__ int warpCnt[8];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int v = i < n ? act[i] : 0;
+    const int keep = (i < n) && (seed[v] >= 0);
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) warpCnt[w] = __popc(bal);
+    __syncthreads();
+    int base = blockCnt[blockIdx.x];
+    for (int k = 0; k < w; k++) base += warpCnt[k];
+    if (keep) out[base + __popc(bal & ((1u << lane) - 1u))] = v;
 }
 
 } // namespace vor

@@ -404,7 +404,15 @@ template <int D> class Engine {
         int maxStage = 1;
         for (int st = 0; st < 64; st++) maxStage = std::max(maxStage, stageLo[st + 1] - stageLo[st]);
         bits = 1;
-        while ((1 << bits) < maxStage) bits++;
+        ensure_scratch(std::min(maxStage, opt.slot_cap));
+#if VOR_GPU
+        // cooperative path: the priority is a hash of the SLOT index (unique within a round), so the key needs
+        // log2(slots) bits and the epoch field is wide: owner[] is reset about once per 1000 rounds
+        const int prioRange = opt.coop ? std::min(maxStage, scr.nslots) : maxStage;
+#else
+        const int prioRange = maxStage;
+#endif
+        while ((1 << bits) < prioRange) bits++;
         if (bits + 1 > 28) fail(ERR_ARG, "stage too large for the priority key");
         epochMax = (1 << (30 - (bits + 1))) - 1;
         reset_owners();
@@ -658,14 +666,25 @@ template <int D> class Engine {
     }
 
     int compact_active(int nact) {
-        const int chunk = 256;
-        const int nb = (nact + chunk - 1) / chunk;
-        CompactArgs ca{act, mesh.seed, act2, blockCnt, nact, chunk};
-        VOR_LAUNCH(CompactArgs, compact_count_body, nb, ca, stream);
-        ScanArgs sa{nullptr, blockCnt, 0, 0, nb, d_misc};
-        VOR_LAUNCH(ScanArgs, scan_serial_body, 1, sa, stream);
-        VOR_LAUNCH(CompactArgs, compact_scatter_body, nb, ca, stream);
         long long total = 0;
+#if VOR_GPU
+        if (opt.coop) {
+            const int nb = (nact + 255) / 256;
+            k_compact_count<<<nb, 256, 0, stream>>>(act, mesh.seed, blockCnt, nact);
+            k_compact_scan<<<1, 1024, 0, stream>>>(blockCnt, nb, d_misc);
+            k_compact_scatter<<<nb, 256, 0, stream>>>(act, mesh.seed, blockCnt, act2, nact);
+            be::g_launches += 3;
+        } else
+#endif
+        {
+            const int chunk = 256;
+            const int nb = (nact + chunk - 1) / chunk;
+            CompactArgs ca{act, mesh.seed, act2, blockCnt, nact, chunk};
+            VOR_LAUNCH(CompactArgs, compact_count_body, nb, ca, stream);
+            ScanArgs sa{nullptr, blockCnt, 0, 0, nb, d_misc};
+            VOR_LAUNCH(ScanArgs, scan_serial_body, 1, sa, stream);
+            VOR_LAUNCH(CompactArgs, compact_scatter_body, nb, ca, stream);
+        }
         be::d2h(&total, d_misc, sizeof(long long), stream);
         be::sync(stream);
         std::swap(act, act2);
