@@ -272,14 +272,25 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     t_attempt = sd["profile_ms"]["attempt"] * 1e-3
     achieved = (n * b_attempt / t_attempt / 1e9) if t_attempt > 0 else None
+    # DRAM traffic of the kernel from the committed ncu --set full capture (bytes per attempted point), scaled to the
+    # average launch of this run
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "attempt_traffic.json")))
+        if tr.get("dim") == dim:
+            traffic = tr["dram_bytes_per_attempted_point"] * sd["attempts"] / max(sd["profile_launches"]["attempt"], 1)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "k_attempt_coop (locate + conflict + reservation)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "achieved_note": "algorithmic bytes of all launches / summed CUDA-event time of all launches (launch sizes vary by 4 orders of magnitude)",
                 "algorithmic_bytes_per_point_kernel": b_attempt, "algorithmic_bytes_per_point_path": b_total,
                 "kernel_launches": sd["profile_launches"]["attempt"], "kernel_ms_total": sd["profile_ms"]["attempt"],
                 "path_frac": (value / world) * b_total / (peak * 1e9),
                 "counters_per_point": {"W_walk_steps_all_attempts": sd["walk_steps"] / n, "E_tests_all_attempts": sd["tests"] / n,
                                        "K_killed": K, "C_created": Cn, "attempts_per_point": sd["attempts"] / n,
-                                       "rounds": sd["rounds"], "exact_calls": sd["exact_calls"], "exact_zero": sd["exact_zero"]},
+                                       "rounds": sd["rounds"], "exact_calls": sd["exact_calls"], "exact_zero": sd["exact_zero"],
+                                       "aborted_attempts": sd["aborted"] / n, "E_tests_completed_attempts": sd["tests_completed"] / n},
                 "step_ms_by_kernel": sd["profile_ms"]}
 
     # ---- end to end through the public API with host buffers (H2D + D2H inside the timed region)

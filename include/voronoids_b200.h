@@ -92,6 +92,12 @@ vor_status vor_tree_edges_device(vor_tree *t, const uint32_t **d_edges, size_t *
 vor_status vor_tree_export_simplices(vor_tree *t, int32_t *vertices, int32_t *neighbors, double *centers, double *radii, size_t cap,
                                      size_t *n_simplices);
 
+/* DelaunayTree::locate (delaunay_tree.rs:33-58) for n query points of a single-set tree: the conflict region of each
+ * point (simplices whose open circumsphere contains it) as indices into the current vor_tree_export_simplices order,
+ * `cap` slots per query (unsorted; the reference sorts by its own ids).  counts[i] = region size; 0 = the point
+ * coincides with a vertex (the reference panics, delaunay_tree.rs:47-54); -1 = more than cap simplices. */
+vor_status vor_tree_locate(vor_tree *t, const double *points, size_t n, int32_t *out_ids, size_t cap, int32_t *counts);
+
 /* check_delaunay (delaunay_tree.rs:512-541): *ok = 1 iff every live simplex is positively oriented, adjacency is
  * symmetric and every interior facet is locally Delaunay (equivalent to the brute-force empty-sphere test).
  * fail_counts (optional, 5 entries): orientation, dead neighbour, asymmetric, facet mismatch, not Delaunay. */
@@ -101,8 +107,9 @@ vor_status vor_tree_check_delaunay(vor_tree *t, int *ok, int32_t *fail_counts);
 vor_status vor_tree_super_simplex(vor_tree *t, size_t set, double *super_vertices, double *center, double *radius);
 
 /* engine statistics: [rounds, attempts, winners, owner_resets, compactions, stages,
- *                     walk_steps W, in-sphere tests E, killed K, created C, exact_calls, exact_zero, duplicates, simplex_slots] */
-#define VOR_N_STATS 14
+ *                     walk_steps W, in-sphere tests E, killed K, created C, exact_calls, exact_zero, duplicates, simplex_slots,
+ *                     attempts that lost during the flood, in-sphere tests of the attempts that completed] */
+#define VOR_N_STATS 16
 vor_status vor_tree_stats(vor_tree *t, uint64_t *stats);
 
 /* with option "profile": CUDA-event milliseconds per kernel class [attempt, check, retri, setup] followed by the

@@ -108,3 +108,26 @@ def case_tiny(lib, O, dim):
     # the reference's own 2D test points (tests/test_delaunay_tree.rs:42)
     if dim == 2:
         check_against_oracle(lib, O, np.array([[0.3, 0.1], [1.0, 0.2], [0.1, 1.0], [0.5, 0.5]]))
+
+
+def case_locate(lib, O, dim, n=3000, nq=40):
+    """DelaunayTree::locate (delaunay_tree.rs:33-58): the flooded conflict region equals the brute-force set of
+    simplices whose open circumsphere contains the query (exact predicates), for points in general position."""
+    pts = pointgen.uniform(n, dim, 0)
+    t = _capi.Tree(lib, pts)
+    try:
+        v, nb = t.simplices()
+        q = pointgen.uniform(nq, dim, 99)
+        regs = t.locate(q)
+        m = dim + 1
+        allp = np.vstack([t.super_simplex()[0], np.zeros((m, dim)), pts])   # export ids: super, ghosts, 2M + i
+        flat = allp[v].reshape(len(v), -1)
+        orient = O.orient3d(flat) if dim == 3 else O.orient2d(flat)
+        for qi in range(nq):
+            rows = np.concatenate([flat, np.tile(q[qi], (len(v), 1))], axis=1)
+            s = (O.insphere(rows) if dim == 3 else O.incircle(rows)) * orient
+            assert np.array_equal(np.nonzero(s > 0)[0], regs[qi])
+        # a query that coincides with an inserted vertex has an empty (strict) conflict region
+        assert len(t.locate(pts[:1])[0]) == 0
+    finally:
+        t.close()

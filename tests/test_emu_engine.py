@@ -35,6 +35,11 @@ def test_emu_duplicates_are_dropped_and_reported(emu_lib, oracle, dim):
     ec.case_duplicates(emu_lib, oracle, dim)
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_emu_locate(emu_lib, oracle, dim):
+    ec.case_locate(emu_lib, oracle, dim)
+
+
 def test_emu_overflow_scratch_and_compaction(emu_lib, oracle):
     # tiny regular slots force the overflow path; a small attempt budget forces many rounds + list compaction
     emu_lib.vor_set_option(b"capk", 8.0)

@@ -38,6 +38,29 @@ def test_gpu_duplicates(gpu_lib, oracle, dim):
     ec.case_duplicates(gpu_lib, oracle, dim)
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_gpu_locate(gpu_lib, oracle, dim):
+    ec.case_locate(gpu_lib, oracle, dim, n=20000, nq=60)
+
+
+def test_gpu_voronoi_dual(gpu_lib, oracle):
+    import voronoids_b200 as vb
+    pts = pointgen.uniform(5000, 3, 0)
+    tree = vb.delaunay(pts)
+    centres, ridges = tree.voronoi()
+    v, nb, c, r = tree.simplex_arrays()
+    assert centres.shape == (len(v), 3) and ridges.shape[1] == 2
+    # every interior facet gives exactly one ridge
+    assert len(ridges) == int((nb >= 0).sum()) // 2
+    # a Voronoi vertex is equidistant from the 4 vertices of its simplex (float circumsphere of the reference)
+    allp = np.vstack([tree.super_simplex()[0], np.zeros((4, 3)), pts])
+    d = np.linalg.norm(allp[v] - centres[:, None, :], axis=2)
+    real = (v >= 8).all(axis=1)
+    assert np.allclose(d[real], r[real, None], rtol=1e-6)
+    ids = tree.locate(pts[0] * 0.5 + pts[1] * 0.5)
+    assert ids == sorted(ids) and len(ids) > 0 and all(i in tree.simplices for i in ids)
+
+
 def test_gpu_overflow_scratch(gpu_lib, oracle):
     gpu_lib.vor_set_option(b"capk", 8.0)
     gpu_lib.vor_set_option(b"min_attempt", 2048.0)

@@ -30,6 +30,7 @@ SYMBOLS = {
     "vor_tree_edges": (C.c_int, [tree_p, u32p, C.c_size_t, szp]),
     "vor_tree_edges_device": (C.c_int, [tree_p, C.POINTER(C.c_void_p), szp, u64p]),
     "vor_tree_export_simplices": (C.c_int, [tree_p, i32p, i32p, dp, dp, C.c_size_t, szp]),
+    "vor_tree_locate": (C.c_int, [tree_p, dp, C.c_size_t, i32p, C.c_size_t, i32p]),
     "vor_tree_check_delaunay": (C.c_int, [tree_p, C.POINTER(C.c_int), i32p]),
     "vor_tree_super_simplex": (C.c_int, [tree_p, C.c_size_t, dp, dp, dp]),
     "vor_tree_stats": (C.c_int, [tree_p, u64p]),
@@ -44,9 +45,9 @@ SYMBOLS = {
     "vor_set_option": (C.c_int, [C.c_char_p, C.c_double]),
     "vor_tree_set_stream": (None, [tree_p, C.c_void_p]),
 }
-N_STATS = 14
+N_STATS = 16
 STAT_NAMES = ("rounds", "attempts", "winners", "owner_resets", "compactions", "stages", "walk_steps", "tests", "killed", "created",
-              "exact_calls", "exact_zero", "duplicates", "simplex_slots")
+              "exact_calls", "exact_zero", "duplicates", "simplex_slots", "aborted", "tests_completed")
 
 
 def bind(lib):
@@ -143,6 +144,17 @@ class Tree:
             self._h, v.ctypes.data_as(i32p), nb.ctypes.data_as(i32p),
             c.ctypes.data_as(dp) if circumspheres else None, r.ctypes.data_as(dp) if circumspheres else None, n.value, C.byref(n)))
         return (v, nb, c, r) if circumspheres else (v, nb)
+
+    def locate(self, points, cap=256):
+        """Conflict regions of the query points: list of arrays of export indices (order of self.simplices())."""
+        q, qp = as_f64(points)
+        q = q.reshape(-1, self.dim)
+        out = np.zeros((q.shape[0], cap), dtype=np.int32)
+        cnt = np.zeros(q.shape[0], dtype=np.int32)
+        self._check(self._lib.vor_tree_locate(self._h, qp, q.shape[0], out.ctypes.data_as(i32p), cap, cnt.ctypes.data_as(i32p)))
+        if (cnt < 0).any():
+            return self.locate(points, cap * 4)
+        return [np.sort(out[i, :cnt[i]]) for i in range(q.shape[0])]
 
     def check_delaunay(self):
         ok = C.c_int()

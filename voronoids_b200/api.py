@@ -95,6 +95,21 @@ class DelaunayTree:
     def counts(self):
         return self._t.counts()
 
+    def locate(self, vertex):
+        """DelaunayTree::locate (delaunay_tree.rs:33-58): sorted ids of the simplices in conflict with `vertex`
+        (the ids used as keys of `.simplices`)."""
+        first = self.dim + 2
+        return [int(first + i) for i in self._t.locate(np.asarray(vertex, dtype=np.float64).reshape(1, self.dim))[0]]
+
+    def voronoi(self):
+        """Voronoi dual of the current triangulation: (vertices = circumcentres [n, N], ridges = pairs of adjacent
+        simplex indices [m, 2]) over the live simplices in export order."""
+        v, nb, c, r = self.simplex_arrays()
+        i = np.repeat(np.arange(len(nb)), nb.shape[1])
+        j = nb.reshape(-1)
+        keep = (j >= 0) & (i < j)
+        return c, np.stack([i[keep], j[keep]], axis=1)
+
     def check_delaunay(self):
         """delaunay_tree.rs:512-541 (local-Delaunay formulation, see include/voronoids_b200.h)"""
         return self._t.check_delaunay()[0]

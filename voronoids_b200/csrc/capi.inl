@@ -252,6 +252,19 @@ vor_status vor_tree_export_simplices(vor_tree *t, int32_t *vertices, int32_t *ne
     });
 }
 
+vor_status vor_tree_locate(vor_tree *t, const double *points, size_t n, int32_t *out_ids, size_t cap, int32_t *counts) {
+    return guarded([&]() -> vor_status {
+        if (!t || !points || !out_ids || !counts || cap == 0 || t->n_sets != 1) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        return t->visit([&](auto &e) -> vor_status {
+            e.locate(points, (int)n, (int)cap, out_ids, counts);
+            for (size_t i = 0; i < n; i++)
+                if (counts[i] == -2) { g_err = "query point outside the super simplex"; return VOR_ERR_OUTSIDE; }
+            return VOR_OK;
+        });
+    });
+}
+
 vor_status vor_tree_check_delaunay(vor_tree *t, int *ok, int32_t *fail_counts) {
     return guarded([&]() -> vor_status {
         if (!t) { g_err = "null tree"; return VOR_ERR_ARG; }
@@ -288,7 +301,7 @@ vor_status vor_tree_stats(vor_tree *t, uint64_t *s) {
             const vor::Counters &c = *e.hcnt;
             s[0] = e.rs.rounds; s[1] = e.rs.attempts; s[2] = e.rs.winners; s[3] = e.rs.owner_resets; s[4] = e.rs.compactions; s[5] = e.rs.stages;
             s[6] = c.walk_steps; s[7] = c.tests; s[8] = c.killed; s[9] = c.created; s[10] = c.exact_calls; s[11] = c.exact_zero;
-            s[12] = (uint64_t)c.ndup; s[13] = (uint64_t)c.ntets;
+            s[12] = (uint64_t)c.ndup; s[13] = (uint64_t)c.ntets; s[14] = c.aborted; s[15] = c.tests_ok;
             return VOR_OK;
         });
     });

@@ -48,11 +48,17 @@ template <> struct GeoCoop<2> {
 // ------------------------------------------------------------------------------------------
 // attempt
 // ------------------------------------------------------------------------------------------
-#ifndef VOR_ATTEMPT_MINBLOCKS
-#define VOR_ATTEMPT_MINBLOCKS 4   // 64 registers: 4 blocks/SM; measured best of 3/4/5 on the 10M-point run
+// Small blocks: the groups of a block are independent, and a block keeps its registers until its SLOWEST group is
+// done; with 8 warps per block the achieved occupancy was 30 % of the 50 % the 64 registers allow (ncu, round 1);
+// measured attempt-kernel time on the 10M-point run: 135 ms (256 threads), 126 (128), 124 (64), 123 (32).
+#ifndef VOR_COOP_BLOCK
+#define VOR_COOP_BLOCK 64
+#endif
+#ifndef VOR_ATTEMPT_REGS
+#define VOR_ATTEMPT_REGS 64       // registers per thread of the attempt kernel (measured best of 80/64/48)
 #endif
 template <int D, int G>
-__global__ void __launch_bounds__(256, VOR_ATTEMPT_MINBLOCKS) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
+__global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_COOP_BLOCK)) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
     constexpr int M = Dim<D>::M;
     using Gm = Geo<D>;
     const Mesh<D> &m = A.m;
@@ -222,6 +228,7 @@ __global__ void __launch_bounds__(256, VOR_ATTEMPT_MINBLOCKS) k_attempt_coop(Att
             atomicAdd(&m.cnt->tests, (unsigned long long)tests);
             atomicAdd(&m.cnt->attempts, 1ULL);
             if (status != ST_OK) atomicAdd(&m.cnt->aborted, 1ULL);
+            else atomicAdd(&m.cnt->tests_ok, (unsigned long long)tests);
         }
     }
 }
@@ -234,7 +241,7 @@ __global__ void __launch_bounds__(256, VOR_ATTEMPT_MINBLOCKS) k_attempt_coop(Att
 // only reads owner[] of its own footprint, and a winner only changes owner[] on its own killed simplices, which any
 // group that shares them has lost anyway (it reads the winner's key or the dead mark, never its own key).
 template <int D, int G>
-__global__ void __launch_bounds__(256) k_commit_coop(CheckArgs<D> A, const int *act, RoundSel rsel, int stats) {
+__global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, const int *act, RoundSel rsel, int stats) {
     constexpr int M = Dim<D>::M;
     const Mesh<D> &m = A.m;
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;

@@ -473,12 +473,12 @@ template <int D> class Engine {
         return (long long)std::min(byRounds, byRemaining) + 4096;
     }
     template <int G> void launch_round(const AttemptArgs<D> &aa, const CheckArgs<D> &ca, const RoundSel &sel) {
-        const unsigned grid = (unsigned)(((long long)sel.nsel * G + 255) / 256);
+        const unsigned grid = (unsigned)(((long long)sel.nsel * G + VOR_COOP_BLOCK - 1) / VOR_COOP_BLOCK);
         prof.start(0, stream);
-        k_attempt_coop<D, G><<<grid, 256, 0, stream>>>(aa, sel);
+        k_attempt_coop<D, G><<<grid, VOR_COOP_BLOCK, 0, stream>>>(aa, sel);
         prof.stop(stream);
         prof.start(2, stream);
-        k_commit_coop<D, G><<<grid, 256, 0, stream>>>(ca, act, sel, opt.stats);
+        k_commit_coop<D, G><<<grid, VOR_COOP_BLOCK, 0, stream>>>(ca, act, sel, opt.stats);
         prof.stop(stream);
         be::g_launches += 2;
     }
@@ -785,6 +785,35 @@ template <int D> class Engine {
         pull_counters();
         return live;
     }
+
+    // locate (delaunay_tree.rs:33-58) for nq host query points: conflict regions as export indices (the index space
+    // of export_simplices), `cap` entries per query.  counts[i] = size, -1 = does not fit, -2 = outside.
+    void locate(const double *h_q, int nq, int cap, int *h_out, int *h_counts) {
+        const int nt = hcnt->ntets;
+        DevTmp<double> dq((size_t)nq * D);
+        DevTmp<int> dseed((size_t)nq), dout((size_t)nq * cap), dcount((size_t)nq), liveId((size_t)nt), compactOf((size_t)nt), dc(1);
+        be::h2d(dq.p, h_q, sizeof(double) * (size_t)nq * D, stream);
+        be::dmemset(dc.p, 0, sizeof(int), stream);
+        ExportArgs<D> xa{mesh, dc.p, liveId.p, compactOf.p};
+        VOR_LAUNCH(ExportArgs<D>, export_mark_body<D>, nt, xa, stream);
+        // seeds: root simplex of set 0 when nothing is inserted, else the simplex of the last inserted vertex (forwarded)
+        fill_i(dseed.p, nv > nsuper ? -1 : 0, (size_t)nq);
+        if (nv > nsuper) {
+            QuerySeedArgs<D> qs{keysAll, mesh.pts, mesh.ptTet, dq.p, d_boxLo, d_boxHi, dseed.p, nsuper, refLo, refHi, axisBits};
+            VOR_LAUNCH(QuerySeedArgs<D>, query_seed_body<D>, nq, qs, stream);
+        }
+        LocateQueryArgs<D> la{mesh, dq.p, dseed.p, compactOf.p, dout.p, dcount.p, cap};
+        VOR_LAUNCH(LocateQueryArgs<D>, locate_query_body<D>, nq, la, stream);
+        be::d2h(h_out, dout.p, sizeof(int) * (size_t)nq * cap, stream);
+        be::d2h(h_counts, dcount.p, sizeof(int) * (size_t)nq, stream);
+        be::sync(stream);
+    }
+    template <class T> struct DevTmp {
+        T *p;
+        explicit DevTmp(size_t n) : p((T *)be::dmalloc(sizeof(T) * (n ? n : 1))) {}
+        ~DevTmp() { be::dfree(p); }
+        DevTmp(const DevTmp &) = delete;
+    };
 
     // compact export of live simplices; vertex ids: super k -> k, input i -> idOffset + i.  Returns the count.
     // Any output pointer may be null.  Two-phase use: call with all null to get the count.

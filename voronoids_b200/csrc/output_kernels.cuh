@@ -235,6 +235,69 @@ template <int D> VOR_HD void export_fill_body(const ExportFillArgs<D> &A, int c)
     }
 }
 
+// ---- locate (reference: DelaunayTree::locate, delaunay_tree.rs:33-58): conflict region of query points, read only.
+// Thread per query: seed from the Morton neighbour (same rule as init_seeds), visibility walk, flood; the visited test
+// is a scan of the query's own result list (the owner words are not touched, so queries can run between inserts).
+template <int D> struct LocateQueryArgs {
+    Mesh<D> m;
+    const double *q;          // nq x D query points
+    const int *seedSimplex;   // per query: a live simplex to start from
+    const int *compactOf;     // simplex slot -> export index
+    int *out;                 // [nq x cap] export indices of the conflict region (unsorted)
+    int *count;               // per query: region size, or -1 if it does not fit `cap`, -2 if outside the super simplex
+    int cap;
+};
+VOR_HD double4 make_pt(const double *s, double4 *) { return double4{s[0], s[1], s[2], 0.0}; }
+VOR_HD double2 make_pt(const double *s, double2 *) { return double2{s[0], s[1]}; }
+template <int D> VOR_HD void locate_query_body(const LocateQueryArgs<D> &A, int qi) {
+    constexpr int M = Dim<D>::M;
+    using G = Geo<D>;
+    const Mesh<D> &m = A.m;
+    PredCtx cx{m.cnt};
+    const typename G::Pt p = make_pt(A.q + (size_t)qi * D, (typename G::Pt *)nullptr);
+    int s = A.seedSimplex[qi];
+    int o;
+    while ((o = m.owner[s]) < 0) s = ~o;
+    unsigned rot = (unsigned)qi * 2654435761u;
+    typename G::Verts tvv = G::load(m, TV(m, s));
+    for (unsigned steps = 0;; steps++) {
+        const int mk = G::beyond_mask(cx, tvv, p);
+        if (mk == 0) break;
+        int go = 0;
+        const int r0 = (int)((rot >> 16) % (unsigned)M);
+        for (int k = 0; k < M; k++) {
+            const int i = (r0 + k) % M;
+            if ((mk >> i) & 1) { go = i; break; }
+        }
+        const int code = TNI(m, s, go);
+        if (code < 0 || steps > (1u << 22)) { A.count[qi] = -2; return; }
+        s = code >> 2;
+        rot = rot * 1664525u + 1013904223u;
+        tvv = G::load(m, TV(m, s));
+    }
+    int *res = A.out + (size_t)qi * A.cap;
+    int nk = 0;
+    if (!G::conflict(cx, tvv, p)) { A.count[qi] = 0; return; }   // p coincides with a vertex: empty region (the reference panics)
+    res[nk++] = s;
+    for (int head = 0; head < nk; head++) {
+        const int4 nbr = TN(m, res[head]);
+        for (int i = 0; i < M; i++) {
+            const int code = get4(nbr, i);
+            if (code < 0) continue;
+            const int n = code >> 2;
+            bool seen = false;
+            for (int j = 0; j < nk; j++) seen |= res[j] == n;
+            if (seen) continue;
+            if (G::conflict(cx, G::load(m, TV(m, n)), p)) {
+                if (nk == A.cap) { A.count[qi] = -1; return; }
+                res[nk++] = n;
+            }
+        }
+    }
+    for (int j = 0; j < nk; j++) res[j] = A.compactOf[res[j]];
+    A.count[qi] = nk;
+}
+
 // ---- batched geometry entry points (reference API: geometry::{circumsphere, in_sphere})
 template <int D> struct CircumBatchArgs { const double *verts; double *center; double *radius; };
 VOR_HD void circum_batch_body(const CircumBatchArgs<3> &A, int i) {

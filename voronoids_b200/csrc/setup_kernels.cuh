@@ -194,6 +194,41 @@ template <int D> VOR_HD void init_seeds_body(const SeedArgs<D> &A, int j) {
     A.seed[v] = seed;
 }
 
+// seed of a read-only query point (vor_tree_locate): Morton neighbour of the query among the vertices of the last
+// completed stage of set 0 (queries address single-set trees)
+template <int D> struct QuerySeedArgs {
+    const uint64_t *keysAll;
+    const typename Dim<D>::Pt *pts;
+    const int *ptTet;
+    const double *q;
+    const double *boxLo, *boxHi;
+    int *seed;
+    int nsuper, plo, phi, axisBits;
+};
+template <int D> VOR_HD void query_seed_body(const QuerySeedArgs<D> &A, int qi) {
+    const uint64_t mask = (1ULL << STAGE_SHIFT) - 1ULL;
+    uint64_t code = 0;
+    const double scale = (double)((1u << A.axisBits) - 1u);
+    for (int k = 0; k < D; k++) {
+        const double lo = A.boxLo[k], ext = A.boxHi[k] - lo;
+        double u = ext > 0.0 ? (A.q[(size_t)qi * D + k] - lo) / ext : 0.0;
+        u = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
+        const uint64_t qv = (uint64_t)(u * scale);
+        code |= (D == 3 ? spread_bits3(qv) : spread_bits2(qv)) << k;
+    }
+    int lo = A.plo, hi = A.phi;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((A.keysAll[mid - A.nsuper] & mask) < code) lo = mid + 1; else hi = mid;
+    }
+    int best = -1;
+    for (int c = lo - 1; c <= lo + 1 && best < 0; c++)
+        if (c >= A.plo && c < A.phi && A.ptTet[c] >= 0) best = c;
+    for (int c = A.plo; c < A.phi && best < 0; c++)
+        if (A.ptTet[c] >= 0) best = c;
+    A.seed[qi] = best >= 0 ? A.ptTet[best] : 0;
+}
+
 // Bulk point location at the start of a stage: every point of the stage walks from its seed to the simplex that
 // contains it (thread per point, the mesh is static here).  The walk of a point's FIRST attempt is the longest one
 // (about 9 steps from the Morton neighbour's simplex); doing it here, with the whole stage in flight, takes it off the

@@ -133,6 +133,7 @@ struct Counters {
     unsigned long long aborted;      // attempts that lost during the flood
     unsigned long long win_total;    // points inserted (all rounds)
     unsigned long long sel_total;    // attempt slots claimed (all rounds)
+    unsigned long long tests_ok;     // in-sphere tests of the attempts that completed their flood
 };
 
 VOR_HD void set_err(Counters *c, int code) { atomic_cas_i(&c->err, 0, code); }
