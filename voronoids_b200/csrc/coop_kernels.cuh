@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
     // -- forwarding (all lanes follow the same chain: broadcast loads)
     int s = m.seed[v];
     int o;
-    while ((o = __ldcg(&m.owner[s])) < 0) s = ~o;
+    while ((o = __ldcg(&OWK(m, s))) < 0) s = ~o;
 
     // -- visibility walk: lane k < M tests facet k
     unsigned rot = (unsigned)v * 2654435761u;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
         int c0 = 0;
         if (gl == 0) c0 = Gm::conflict(cx, tvv, p);
         c0 = __shfl_sync(gmask, c0, gshift);
-        tests = 1;
+        tests = gl == 0 ? 1u : 0u;
         if (!c0) {
             if (gl == 0) { m.seed[v] = -1; atomicAdd(&m.cnt->ndup, 1); }
             fail = true;
@@ -122,7 +122,10 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
     }
     if (!fail) {
         int old0 = 0;
-        if (gl == 0) old0 = atomicMin(&m.owner[s], key_k);
+        if (gl == 0) {
+            old0 = atomicMin(&OWK(m, s), key_k);
+            if (__ldcg(&OWR(m, s)) < key_k) old0 = -1;     // a better point keeps s in its outer ring
+        }
         old0 = __shfl_sync(gmask, old0, gshift);
         if (old0 < key_k) fail = true;
     }
@@ -148,38 +151,29 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
                         pushB = true; fcode = t * 4 + i; ocode = code;
                     } else {
                         const int n = code >> 2;
-                        const int ow = __ldcg(&m.owner[n]);
-                        if (ow == key_k) {
+                        // the owner pair and the record of n are independent gathers: issue both before looking at either
+                        const int2 ow = __ldcg(reinterpret_cast<const int2 *>(&OWK(m, n)));   // x = kill word, y = ring word
+                        const int4 nverts = __ldcg(&TV(m, n));
+                        if (ow.x == key_k) {
                             // already in my cavity
-                        } else if (ow < key_k) {
-                            lostLane = true;
-                        } else if (ow == key_o) {
-                            pushB = true; fcode = t * 4 + i; ocode = code;
+                        } else if (ow.x < key_k) {
+                            lostLane = true;           // a better point kills n (or n is dead)
+                        } else if (ow.y == key_o) {
+                            pushB = true; fcode = t * 4 + i; ocode = code;   // already tested by me: not in conflict
                         } else {
                             tests++;
-                            const typename Gm::Verts nv = Gm::load(m, TV(m, n));
+                            const typename Gm::Verts nv = Gm::load(m, nverts);
                             if (Gm::conflict(cx, nv, p)) {
-                                const int old = atomicMin(&m.owner[n], key_k);
-                                if (old < key_k) lostLane = true;
-                                else if (old != key_k) {   // first lane to claim it appends it
-                                    pushK = true; newT = n;
-#ifdef VOR_PREFETCH_NEXT_LEVEL
-                                    // n joins the frontier: its neighbour codes share the sector just read; pull the
-                                    // neighbours' records and owner words towards L2 for the next BFS level
-                                    const int4 nn = TN(m, n);
-                                    for (int k2 = 0; k2 < M; k2++) {
-                                        const int c2 = get4(nn, k2);
-                                        if (c2 >= 0 && (c2 >> 2) != t) {
-                                            asm volatile("prefetch.global.L2 [%0];" ::"l"(&TV(m, c2 >> 2)));
-                                            asm volatile("prefetch.global.L2 [%0];" ::"l"(&m.owner[c2 >> 2]));
-                                        }
-                                    }
-#endif
+                                if (ow.y < key_k) lostLane = true;   // a better point keeps n in its outer ring
+                                else {
+                                    const int old = atomicMin(&OWK(m, n), key_k);
+                                    if (old < key_k) lostLane = true;
+                                    else if (old != key_k) { pushK = true; newT = n; }   // first lane to claim it appends it
                                 }
                             } else {
-                                // outer-ring mark: fire and forget (RED, no round trip).  A better point that holds n
-                                // was either seen by the owner read above or is caught by the ownership check of commit.
-                                atomicMin(&m.owner[n], key_o);
+                                // outer-ring mark: fire and forget (RED, no round trip).  Rings may be shared; a better
+                                // point that KILLS n was either seen above or is caught by the ownership check of commit.
+                                atomicMin(&OWR(m, n), key_o);
                                 pushB = true; fcode = t * 4 + i; ocode = code;
                             }
                         }
@@ -259,12 +253,15 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
     const int key_o = key_k | 1;
     const ScrView sv = scr_view(A.scr, slot, A.scr.slotBig[slot]);
     const int nk = A.scr.slotNk[slot], nb = A.scr.slotNb[slot];
+    (void)key_o;
     bool bad = false;
-    for (int j = gl; j < nk; j += G)
-        if (__ldcg(&m.owner[sv.k[j]]) != key_k) bad = true;
+    for (int j = gl; j < nk; j += G) {
+        const int2 ow = __ldcg(reinterpret_cast<const int2 *>(&OWK(m, sv.k[j])));
+        if (ow.x != key_k || ow.y < key_k) bad = true;     // best killer, and no better point has it in its ring
+    }
     for (int j = gl; j < nb; j += G) {
         const int code = sv.o[j];
-        if (code >= 0 && __ldcg(&m.owner[code >> 2]) != key_o) bad = true;
+        if (code >= 0 && __ldcg(&OWK(m, code >> 2)) < key_k) bad = true;   // no better point kills my outer ring
     }
     if (__any_sync(gmask, bad)) return;
     int base = 0;
@@ -274,7 +271,7 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
         // no room: leave the mesh untouched (the point stays pending), retire the part of the block that exists and
         // tell the host to grow the store
         for (int j = gl; j < nb; j += G)
-            if (base + j < m.cap) m.owner[base + j] = -1;
+            if (base + j < m.cap) OWK(m, base + j) = -1;
         if (gl == 0) m.cnt->oom_soft = 1;
         return;
     }
@@ -292,6 +289,7 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
         if (M == 3) TNI(m, T, 3) = -1;
         if (outer >= 0) TNI(m, outer >> 2, outer & 3) = T * 4 + i;
         TNI(m, t, i) = -(T * 4 + i) - 2;
+        OWK(m, t) = ~T;     // dead; forwards to a new simplex that shares a facet with it (any of them: benign race)
     }
     __syncwarp(gmask);
     // phase B: one lane per (new simplex, facet containing v): pivot around the ridge through the dead cavity
@@ -329,7 +327,10 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
         }
     }
     // phase C: the cavity dies (forwarding to the first new simplex)
-    for (int j = gl; j < nk; j += G) m.owner[sv.k[j]] = ~base;
+    for (int j = gl; j < nk; j += G) {
+        const int t = sv.k[j];
+        if (__ldcg(&OWK(m, t)) >= 0) OWK(m, t) = ~base;   // interior of the cavity (no boundary facet)
+    }
     if (gl == 0) {
         m.ptTet[v] = base;
         m.seed[v] = -1;

@@ -174,8 +174,8 @@ template <int D> class Engine {
         nc = std::min(nc, (1LL << 29) - 1);
         const int old = mesh.cap;
         grow(mesh.tet, 2 * (size_t)old, 2 * (size_t)nc);
-        grow(mesh.owner, (size_t)old, (size_t)nc);
-        fill_i(mesh.owner + old, OWNER_FREE, (size_t)(nc - old));
+        grow(mesh.owner, 2 * (size_t)old, 2 * (size_t)nc);       // kill word + ring word per simplex
+        fill_i(mesh.owner + 2 * (size_t)old, OWNER_FREE, 2 * (size_t)(nc - old));
         mesh.cap = (int)nc;
         if (opt.verbose) fprintf(stderr, "[vor] simplex capacity -> %lld\n", nc);
     }
@@ -535,7 +535,7 @@ template <int D> class Engine {
                 // some winners found no room: retire the slots handed out beyond the old capacity and grow
                 const int oldcap = mesh.cap;
                 ensure_simplices((long long)hcnt->ntets + batch_margin(R, nsel, newPerPoint));
-                if (hcnt->ntets > oldcap) fill_i(mesh.owner + oldcap, -1, (size_t)(std::min(hcnt->ntets, mesh.cap) - oldcap));
+                if (hcnt->ntets > oldcap) fill_i(mesh.owner + 2 * (size_t)oldcap, -1, 2 * (size_t)(std::min(hcnt->ntets, mesh.cap) - oldcap));
                 hcnt->oom_soft = 0;
                 be::h2d(&mesh.cnt->oom_soft, &hcnt->oom_soft, sizeof(int), stream);
             }
@@ -786,16 +786,24 @@ template <int D> class Engine {
         return live;
     }
 
+    // live simplices in slot order: liveId[c] = slot, compactOf[slot] = c (-1 when dead); returns the count
+    int compact_live(int *liveId, int *compactOf) {
+        const int nt = hcnt->ntets;
+        ExportArgs<D> xa{mesh, liveId, compactOf};
+        VOR_LAUNCH(ExportArgs<D>, export_flag_body<D>, nt, xa, stream);
+        const long long n = scan_exclusive(compactOf, nt);
+        VOR_LAUNCH(ExportArgs<D>, export_mark_body<D>, nt, xa, stream);
+        return (int)n;
+    }
+
     // locate (delaunay_tree.rs:33-58) for nq host query points: conflict regions as export indices (the index space
     // of export_simplices), `cap` entries per query.  counts[i] = size, -1 = does not fit, -2 = outside.
     void locate(const double *h_q, int nq, int cap, int *h_out, int *h_counts) {
         const int nt = hcnt->ntets;
         DevTmp<double> dq((size_t)nq * D);
-        DevTmp<int> dseed((size_t)nq), dout((size_t)nq * cap), dcount((size_t)nq), liveId((size_t)nt), compactOf((size_t)nt), dc(1);
+        DevTmp<int> dseed((size_t)nq), dout((size_t)nq * cap), dcount((size_t)nq), liveId((size_t)nt), compactOf((size_t)nt);
         be::h2d(dq.p, h_q, sizeof(double) * (size_t)nq * D, stream);
-        be::dmemset(dc.p, 0, sizeof(int), stream);
-        ExportArgs<D> xa{mesh, dc.p, liveId.p, compactOf.p};
-        VOR_LAUNCH(ExportArgs<D>, export_mark_body<D>, nt, xa, stream);
+        compact_live(liveId.p, compactOf.p);
         // seeds: root simplex of set 0 when nothing is inserted, else the simplex of the last inserted vertex (forwarded)
         fill_i(dseed.p, nv > nsuper ? -1 : 0, (size_t)nq);
         if (nv > nsuper) {
@@ -819,15 +827,9 @@ template <int D> class Engine {
     // Any output pointer may be null.  Two-phase use: call with all null to get the count.
     int export_simplices(int *h_verts, int *h_nbrs, double *h_center, double *h_radius, int idOffset) {
         const int nt = hcnt->ntets;
-        int *d_count = (int *)be::dmalloc(sizeof(int));
         int *liveId = (int *)be::dmalloc(sizeof(int) * (size_t)nt);
         int *compactOf = (int *)be::dmalloc(sizeof(int) * (size_t)nt);
-        be::dmemset(d_count, 0, sizeof(int), stream);
-        ExportArgs<D> xa{mesh, d_count, liveId, compactOf};
-        VOR_LAUNCH(ExportArgs<D>, export_mark_body<D>, nt, xa, stream);
-        int n = 0;
-        be::d2h(&n, d_count, sizeof(int), stream);
-        be::sync(stream);
+        const int n = compact_live(liveId, compactOf);
         if (h_verts || h_nbrs || h_center || h_radius) {
             int *d_verts = (int *)be::dmalloc(sizeof(int) * (size_t)n * M);
             int *d_nbrs = (int *)be::dmalloc(sizeof(int) * (size_t)n * M);
@@ -842,7 +844,7 @@ template <int D> class Engine {
             be::sync(stream);
             be::dfree(d_verts); be::dfree(d_nbrs); be::dfree(d_c); be::dfree(d_r);
         }
-        be::dfree(d_count); be::dfree(liveId); be::dfree(compactOf);
+        be::dfree(liveId); be::dfree(compactOf);
         return n;
     }
 };

@@ -15,8 +15,11 @@
 //   tet[2t+1] int4 neighbour codes: (neighbour << 2 | slot in neighbour that    } testing a simplex also brings its
 //             points back), -1 = outside the super simplex; slot i is opposite  } adjacency into L1/L2 for the next
 //             vertex i.  The reference keeps an unordered Vec (delaunay_tree.rs:15).   BFS level / walk step
-//   owner[t]  >= 0: reservation key of the current round (OWNER_FREE when untouched)
-//             <  0: simplex is dead, ~owner = a simplex created by the insertion that killed it (forwarding)
+//   owner[2t]   "kill word"  >= 0: smallest key of the points that want to KILL t this round (OWNER_FREE when untouched)
+//               <  0: simplex is dead, ~owner = a simplex created by the insertion that killed it (forwarding)
+//   owner[2t+1] "ring word"  smallest key of the points that have t in the OUTER RING of their cavity this round.
+//               Two winners may share an outer-ring simplex (they patch different neighbour slots of it); only
+//               kill/kill and kill/ring overlaps exclude each other, and exactly the point with the worse key loses.
 //   seed[v]   pending point: a simplex to start its walk from; -1 once inserted
 //   ptTet[v]  a simplex created by v's insertion (seed for later points near v)
 //
@@ -43,7 +46,7 @@ template <> struct Dim<2> { using Pt = double2; static constexpr int M = 3; };
 template <int D> struct Mesh {
     typename Dim<D>::Pt *pts;
     int4 *tet;    // interleaved records: tet[2t] = vertex ids, tet[2t+1] = neighbour codes (one 32 B sector per simplex)
-    int *owner;
+    int *owner;   // 2 words per simplex: kill word, ring word (see above)
     int *seed;
     int *ptTet;
     Counters *cnt;
@@ -51,6 +54,8 @@ template <int D> struct Mesh {
     int nsuper;   // vertices [0, nsuper) are super vertices
 };
 
+template <int D> VOR_HD int &OWK(const Mesh<D> &m, int t) { return m.owner[2 * (size_t)t]; }       // kill word / dead + forwarding
+template <int D> VOR_HD int &OWR(const Mesh<D> &m, int t) { return m.owner[2 * (size_t)t + 1]; }   // ring word
 template <int D> VOR_HD int4 &TV(const Mesh<D> &m, int t) { return m.tet[2 * (size_t)t]; }
 template <int D> VOR_HD int4 &TN(const Mesh<D> &m, int t) { return m.tet[2 * (size_t)t + 1]; }
 template <int D> VOR_HD int &TNI(const Mesh<D> &m, int t, int i) { return reinterpret_cast<int *>(m.tet)[8 * (size_t)t + 4 + i]; }
@@ -170,7 +175,7 @@ template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
 
     // -- forwarding: a dead seed points at a simplex created by its killer
     int o;
-    while ((o = m.owner[s]) < 0) s = ~o;
+    while ((o = OWK(m, s)) < 0) s = ~o;
 
     // -- visibility walk
     unsigned rot = (unsigned)v * 2654435761u;
@@ -204,7 +209,8 @@ template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
         atomic_add_i(&m.cnt->ndup, 1);
         return;
     }
-    if (atomic_min_i(&m.owner[s], key_k) < key_k) goto lost;
+    if (OWR(m, s) < key_k) goto lost;                       // a better point keeps s in its outer ring
+    if (atomic_min_i(&OWK(m, s), key_k) < key_k) goto lost;
     {
         ScrView sv = scr_view(A.scr, slot, -1);
         int big = -1;
@@ -218,14 +224,15 @@ template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
                 int isout = 1;
                 if (code >= 0) {
                     const int n = code >> 2;
-                    const int ow = m.owner[n];
+                    const int ow = OWK(m, n), orr = OWR(m, n);
                     if (ow == key_k) continue;               // already in my cavity
-                    if (ow < key_k) goto lost;               // a better point holds it
-                    if (ow != key_o) {                       // not yet classified by me
+                    if (ow < key_k) goto lost;               // a better point kills it (or it is dead)
+                    if (orr != key_o) {                      // not yet classified by me (or a better point shares the ring)
                         tests++;
                         const typename G::Verts nv = G::load(m, TV(m, n));
                         if (G::conflict(cx, nv, p)) {
-                            if (atomic_min_i(&m.owner[n], key_k) < key_k) goto lost;
+                            if (orr < key_k) goto lost;          // a better point keeps n in its outer ring
+                            if (atomic_min_i(&OWK(m, n), key_k) < key_k) goto lost;
                             isout = 0;
                             if (nk == sv.capk) {
                                 if (big >= 0) { set_err(m.cnt, ERR_CAPACITY); goto lost; }
@@ -240,7 +247,7 @@ template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
                             sv.k[(size_t)nk * sv.stride] = n;
                             nk++;
                         } else {
-                            if (atomic_min_i(&m.owner[n], key_o) < key_k) goto lost;
+                            atomic_min_i(&OWR(m, n), key_o);     // sharing the ring with a better point is fine
                         }
                     }
                 }
@@ -305,11 +312,14 @@ template <int D> VOR_HD void check_body(const CheckArgs<D> &A, int slot, bool va
         const int nk = A.scr.slotNk[slot];
         nb = A.scr.slotNb[slot];
         win = 1;
-        for (int j = 0; j < nk && win; j++)
-            if (m.owner[sv.k[(size_t)j * sv.stride]] != key_k) win = 0;
+        (void)key_o;
+        for (int j = 0; j < nk && win; j++) {
+            const int t = sv.k[(size_t)j * sv.stride];
+            if (OWK(m, t) != key_k || OWR(m, t) < key_k) win = 0;   // best killer, and no better point has t in its ring
+        }
         for (int j = 0; j < nb && win; j++) {
             const int code = sv.o[(size_t)j * sv.stride];
-            if (code >= 0 && m.owner[code >> 2] != key_o) win = 0;
+            if (code >= 0 && OWK(m, code >> 2) < key_k) win = 0;    // no better point kills my outer ring
         }
     }
 #ifdef __CUDA_ARCH__
@@ -418,7 +428,7 @@ template <int D> VOR_HD void retri_body(const RetriArgs<D> &A, int w) {
         }
     }
     // phase C: the cavity dies; dead simplices forward to a new one
-    for (int j = 0; j < nk; j++) m.owner[sv.k[(size_t)j * sv.stride]] = ~base;
+    for (int j = 0; j < nk; j++) OWK(m, sv.k[(size_t)j * sv.stride]) = ~base;
     m.ptTet[v] = base;
     m.seed[v] = -1;
     atomic_add_ull(&m.cnt->win_total, 1ULL);
@@ -434,7 +444,8 @@ template <int D> VOR_HD void retri_body(const RetriArgs<D> &A, int w) {
 struct ResetOwnerArgs { int *owner; const Counters *cnt; };
 VOR_HD void reset_owner_body(const ResetOwnerArgs &A, int t) {
     if (t >= A.cnt->ntets) return;   // the launch covers the whole store: the host's simplex count may be a batch behind
-    if (A.owner[t] >= 0) A.owner[t] = OWNER_FREE;
+    if (A.owner[2 * (size_t)t] >= 0) A.owner[2 * (size_t)t] = OWNER_FREE;
+    A.owner[2 * (size_t)t + 1] = OWNER_FREE;
 }
 
 struct FillArgs { int *p; int val; };

@@ -15,7 +15,7 @@
 
 namespace vor {
 
-template <int D> VOR_HD bool simplex_live(const Mesh<D> &m, int t) { return m.owner[t] >= 0; }
+template <int D> VOR_HD bool simplex_live(const Mesh<D> &m, int t) { return OWK(m, t) >= 0; }
 
 template <int D> struct EdgeArgs {
     Mesh<D> m;
@@ -147,18 +147,17 @@ template <int D> VOR_HD void validate_body(const ValidateArgs<D> &A, int t) {
     }
 }
 
-// ---- export of live simplices (compact, unordered)
+// ---- export of live simplices: compact index = rank of the slot among the live slots (deterministic, so the index
+// spaces of export_simplices and locate agree from call to call)
 template <int D> struct ExportArgs {
     Mesh<D> m;
-    int *count;      // number of live simplices
     int *liveId;     // compact index -> simplex slot
-    int *compactOf;  // simplex slot -> compact index (or -1)
+    int *compactOf;  // simplex slot -> compact index (or -1); pass 0 writes the live flag, the host scans it
 };
+template <int D> VOR_HD void export_flag_body(const ExportArgs<D> &A, int t) { A.compactOf[t] = simplex_live(A.m, t) ? 1 : 0; }
 template <int D> VOR_HD void export_mark_body(const ExportArgs<D> &A, int t) {
     if (!simplex_live(A.m, t)) { A.compactOf[t] = -1; return; }
-    const int c = agg_inc(A.count);
-    A.liveId[c] = t;
-    A.compactOf[t] = c;
+    A.liveId[A.compactOf[t]] = t;
 }
 template <int D> struct ExportFillArgs {
     Mesh<D> m;
@@ -257,7 +256,7 @@ template <int D> VOR_HD void locate_query_body(const LocateQueryArgs<D> &A, int 
     const typename G::Pt p = make_pt(A.q + (size_t)qi * D, (typename G::Pt *)nullptr);
     int s = A.seedSimplex[qi];
     int o;
-    while ((o = m.owner[s]) < 0) s = ~o;
+    while ((o = OWK(m, s)) < 0) s = ~o;
     unsigned rot = (unsigned)qi * 2654435761u;
     typename G::Verts tvv = G::load(m, TV(m, s));
     for (unsigned steps = 0;; steps++) {
