@@ -10,6 +10,7 @@ best = 1e9
 for it in range(4):
     lib.vor_set_option(b"verbose", 1.0 if (it == 3 and os.environ.get("T_VERBOSE")) else 0.0)
     lib.vor_set_option(b"stats", 1.0 if (it == 3 and stats) else 0.0)
+    lib.vor_set_option(b"profile", 1.0 if (it == 3 and os.environ.get("T_PROFILE")) else 0.0)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     h = _capi.tree_p()
     st = lib.vor_tree_create_device(dim, C.c_void_p(p.data_ptr()), n, 0, None, C.byref(h)); torch.cuda.synchronize(); t1 = time.perf_counter()
@@ -19,6 +20,10 @@ for it in range(4):
         s = (C.c_uint64 * 32)()
         lib.vor_tree_stats(h, s)
         print("stats", list(s)[:20])
+    if it == 3 and os.environ.get("T_PROFILE"):
+        pr = (C.c_double * 8)()
+        lib.vor_tree_profile(h, pr)
+        print("PROFILE attempt_ms=%.2f commit_ms=%.2f setup_ms=%.2f total_ms=%.2f" % (pr[0], pr[2], pr[3], (t2 - t0) * 1e3))
     lib.vor_tree_destroy(h); torch.cuda.synchronize()
-    if it and not (it == 3 and (stats or os.environ.get("T_VERBOSE"))): best = min(best, (t2 - t0) * 1e3)
+    if it and not (it == 3 and (stats or os.environ.get("T_VERBOSE") or os.environ.get("T_PROFILE"))): best = min(best, (t2 - t0) * 1e3)
 print("RESULT n=%d dim=%d env=%s best_ms=%.2f Mpts/s=%.2f" % (n, dim, {k: v for k, v in os.environ.items() if k.startswith("VOR_")}, best, n / best / 1e3), flush=True)

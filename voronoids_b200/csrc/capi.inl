@@ -84,6 +84,10 @@ int vor_set_option(const char *name, double value) {
     else if (n == "coop_switch") g_opts.coop_switch = (int)value;
     else if (n == "rounds_per_sync") g_opts.rounds_per_sync = (int)value;
     else if (n == "select_mode") g_opts.select_mode = (int)value;
+    else if (n == "prewalk") g_opts.prewalk = (int)value;
+    else if (n == "red") g_opts.red = (int)value;
+    else if (n == "commit_smem") g_opts.commit_smem = (int)value;
+    else if (n == "recycle") g_opts.recycle = (int)value;
     else if (n == "tet_factor") g_opts.tet_factor = value;
     else if (n == "capk") { g_opts.capk = (int)value; g_opts.capb = 2 * g_opts.capk + 4; }
     else if (n == "big_slots") g_opts.big_slots = (int)value;
@@ -202,7 +206,7 @@ vor_status vor_tree_counts(vor_tree *t, uint64_t *n_vertices, uint64_t *n_simpli
         vor::be::set_device(t->device);
         return t->visit([&](auto &e) -> vor_status {
             if (n_vertices) *n_vertices = (uint64_t)e.nsuper * 2 + (uint64_t)e.insertedTotal;
-            if (max_simplex_id) *max_simplex_id = (uint64_t)(e.M * e.nsets) + (uint64_t)(e.hcnt->ntets - e.nsets);
+            if (max_simplex_id) *max_simplex_id = (uint64_t)(e.M * e.nsets) + (uint64_t)e.created_all();
             if (n_simplices) *n_simplices = (uint64_t)e.export_simplices(nullptr, nullptr, nullptr, nullptr, 0);
             return VOR_OK;
         });

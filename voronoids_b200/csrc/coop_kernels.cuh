@@ -46,6 +46,62 @@ template <> struct GeoCoop<2> {
 };
 
 // ------------------------------------------------------------------------------------------
+// walk (option "prewalk"): forwarding + visibility walk of the points selected this round, G = 4 lanes per point
+// (8 independent walks per warp) or G = 1 (32 per warp).  In the warp-per-point attempt kernel a walk keeps 4 of 32
+// lanes busy and is ONE dependent chain of gathers per warp; run here it leaves the attempt kernel with the flood only
+// (its own walk loop ends at the first test, on sectors this kernel has just pulled into L2).
+// ------------------------------------------------------------------------------------------
+template <int D, int G>
+__global__ void __launch_bounds__(128) k_walk_coop(AttemptArgs<D> A, RoundSel rsel) {
+    constexpr int M = Dim<D>::M;
+    using Gm = Geo<D>;
+    const Mesh<D> &m = A.m;
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gl = threadIdx.x & (G - 1);
+    const unsigned gmask = G == 1 ? __activemask() : group_mask<G>();
+    const int gshift = (threadIdx.x & 31) & ~(G - 1);
+    if (gid >= rsel.nsel) return;
+    const int a = slot_entry(rsel, gid);
+    if (a >= rsel.nact) return;
+    const int v = A.act[a];
+    int s = m.seed[v];
+    if (s < 0) return;
+    PredCtx cx{m.cnt};
+    const typename Gm::Pt p = m.pts[v];
+    int o;
+    while ((o = __ldcg(&OWK(m, s))) < 0) s = ~o;
+    unsigned rot = (unsigned)v * 2654435761u;
+    unsigned steps = 0;
+    for (;;) {
+        int4 stv, stn;
+        load_rec(m, s, stv, stn);
+        const typename Gm::Verts tvv = Gm::load(m, stv);
+        unsigned bal;
+        if (G == 1) bal = (unsigned)Gm::beyond_mask(cx, tvv, p);
+        else {
+            const int ok = gl < M ? GeoCoop<D>::orient_repl(cx, tvv, p, gl) : 1;
+            bal = (__ballot_sync(gmask, ok < 0) >> gshift) & ((1u << M) - 1u);
+        }
+        if (bal == 0) break;
+        int go = 0;
+        const int r0 = (int)((rot >> 16) % (unsigned)M);
+        for (int k = 0; k < M; k++) {
+            const int i = (r0 + k) % M;
+            if ((bal >> i) & 1) { go = i; break; }
+        }
+        const int code = get4(stn, go);
+        if (code < 0) { if (gl == 0) set_err(m.cnt, ERR_OUTSIDE); return; }
+        s = code >> 2;
+        rot = rot * 1664525u + 1013904223u;
+        if (++steps > (1u << 22)) { if (gl == 0) set_err(m.cnt, ERR_WALK); return; }
+    }
+    if (gl == 0) {
+        m.seed[v] = s;
+        if (A.stats) atomicAdd(&m.cnt->walk_steps, (unsigned long long)steps);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // attempt
 // ------------------------------------------------------------------------------------------
 // Small blocks: the groups of a block are independent, and a block keeps its registers until its SLOWEST group is
@@ -54,10 +110,16 @@ template <> struct GeoCoop<2> {
 #ifndef VOR_COOP_BLOCK
 #define VOR_COOP_BLOCK 64
 #endif
+#ifndef VOR_SK
+#define VOR_SK 64                 // killed simplices of a cavity staged in shared memory (ids + neighbour codes: 20 B each)
+#endif
 #ifndef VOR_ATTEMPT_REGS
 #define VOR_ATTEMPT_REGS 64       // registers per thread of the attempt kernel (measured best of 80/64/48)
 #endif
-template <int D, int G>
+// RED = 1: the kill reservation is a fire-and-forget reduction too (no round trip on the critical path of a flood
+// level): lanes of one batch that reach the same simplex are deduplicated with match.any, and a better killer that
+// slips in between the owner read and the reduction is caught by the ownership check of commit.
+template <int D, int G, int RED>
 __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_COOP_BLOCK)) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
     constexpr int M = Dim<D>::M;
     using Gm = Geo<D>;
@@ -66,6 +128,13 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
     const int gl = threadIdx.x & (G - 1);                          // lane inside the group
     const unsigned gmask = group_mask<G>();
     const int gshift = (threadIdx.x & 31) & ~(G - 1);              // first lane of the group inside the warp
+    // the cavity found so far, staged in shared memory: ids and neighbour codes of the first SK killed simplices, so a
+    // flood level starts from two shared-memory reads instead of two dependent L2 round trips (scratch, then record)
+    constexpr int SK = VOR_SK;
+    __shared__ int s_kid[VOR_COOP_BLOCK / G][SK];
+    __shared__ int4 s_knb[VOR_COOP_BLOCK / G][SK];
+    int *const sk = s_kid[threadIdx.x / G];
+    int4 *const sn = s_knb[threadIdx.x / G];
     if (gid >= rsel.nsel) return;
     const int slot = gid;
     const int a = slot_entry(rsel, slot);
@@ -88,7 +157,9 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
 
     // -- visibility walk: lane k < M tests facet k
     unsigned rot = (unsigned)v * 2654435761u;
-    typename Gm::Verts tvv = Gm::load(m, TV(m, s));
+    int4 stv, stn;                     // record of the simplex the walk stands in: one 256-bit gather per step
+    load_rec(m, s, stv, stn);
+    typename Gm::Verts tvv = Gm::load(m, stv);
     bool fail = false;
     for (;;) {
         const int ok = gl < M ? GeoCoop<D>::orient_repl(cx, tvv, p, gl) : 1;
@@ -100,12 +171,13 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
             const int i = (r0 + k) % M;
             if ((bal >> i) & 1) { go = i; break; }
         }
-        const int code = TNI(m, s, go);
+        const int code = get4(stn, go);
         if (code < 0) { if (gl == 0) set_err(m.cnt, ERR_OUTSIDE); fail = true; break; }
         s = code >> 2;
         rot = rot * 1664525u + 1013904223u;
         if (++steps > (1u << 22)) { if (gl == 0) set_err(m.cnt, ERR_WALK); fail = true; break; }
-        tvv = Gm::load(m, TV(m, s));
+        load_rec(m, s, stv, stn);
+        tvv = Gm::load(m, stv);
     }
 
     if (!fail) {
@@ -131,7 +203,7 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
     }
     if (!fail) {
         ScrView sv = scr_view(A.scr, slot, -1);
-        if (gl == 0) sv.k[0] = s;
+        if (gl == 0) { sv.k[0] = s; sk[0] = s; sn[0] = stn; }
         __syncwarp(gmask);
         nk = 1;
         int head = 0;
@@ -143,17 +215,22 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
                 const int j = base + gl;
                 bool pushK = false, pushB = false, lostLane = false;
                 int newT = 0, fcode = 0, ocode = 0;
+                int claim = -1 - gl;   // RED: simplex this lane wants to kill (unique dummy otherwise)
+                int4 nnb = make_int4(-1, -1, -1, -1);
                 if (j < items) {
-                    const int t = sv.k[head + j / M];
+                    const int e = head + j / M;
                     const int i = j % M;
-                    const int code = TNI(m, t, i);
+                    int t, code;
+                    if (e < SK) { t = sk[e]; code = reinterpret_cast<const int *>(sn)[e * 4 + i]; }
+                    else { t = sv.k[e]; code = TNI(m, t, i); }
                     if (code < 0) {
                         pushB = true; fcode = t * 4 + i; ocode = code;
                     } else {
                         const int n = code >> 2;
                         // the owner pair and the record of n are independent gathers: issue both before looking at either
                         const int2 ow = __ldcg(reinterpret_cast<const int2 *>(&OWK(m, n)));   // x = kill word, y = ring word
-                        const int4 nverts = __ldcg(&TV(m, n));
+                        int4 nverts;
+                        load_rec_cg(m, n, nverts, nnb);   // vertex ids + neighbour codes: one 256-bit gather
                         if (ow.x == key_k) {
                             // already in my cavity
                         } else if (ow.x < key_k) {
@@ -165,7 +242,10 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
                             const typename Gm::Verts nv = Gm::load(m, nverts);
                             if (Gm::conflict(cx, nv, p)) {
                                 if (ow.y < key_k) lostLane = true;   // a better point keeps n in its outer ring
-                                else {
+                                else if (RED) {
+                                    atomicMin(&OWK(m, n), key_k);
+                                    claim = n;
+                                } else {
                                     const int old = atomicMin(&OWK(m, n), key_k);
                                     if (old < key_k) lostLane = true;
                                     else if (old != key_k) { pushK = true; newT = n; }   // first lane to claim it appends it
@@ -180,6 +260,10 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
                     }
                 }
                 if (__any_sync(gmask, lostLane)) { lost = true; break; }
+                if (RED) {
+                    const unsigned same = __match_any_sync(gmask, claim);
+                    if (claim >= 0 && (__ffs(same) - 1) == (threadIdx.x & 31)) { pushK = true; newT = claim; }
+                }
                 const unsigned mk = (__ballot_sync(gmask, pushK) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
                 const unsigned mb = (__ballot_sync(gmask, pushB) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
                 const int ck = __popc(mk), cb = __popc(mb);
@@ -198,7 +282,11 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
                     if (nk + ck > sv.capk || nb + cb > sv.capb) { if (gl == 0) set_err(m.cnt, ERR_CAPACITY); lost = true; break; }
                 }
                 const unsigned lt = (1u << gl) - 1u;
-                if (pushK) sv.k[nk + __popc(mk & lt)] = newT;
+                if (pushK) {
+                    const int pos = nk + __popc(mk & lt);
+                    sv.k[pos] = newT;
+                    if (pos < SK) { sk[pos] = newT; sn[pos] = nnb; }
+                }
                 if (pushB) { const int pos = nb + __popc(mb & lt); sv.f[pos] = fcode; sv.o[pos] = ocode; }
                 nk += ck;
                 nb += cb;
@@ -234,48 +322,11 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
 // allocator (one atomicAdd) and retriangulates at once.  This is safe while other groups are still checking: a check
 // only reads owner[] of its own footprint, and a winner only changes owner[] on its own killed simplices, which any
 // group that shares them has lost anyway (it reads the winner's key or the dead mark, never its own key).
+// Retriangulation of one cavity through the global store (any cavity size; used for the rare cavity that does not
+// fit the shared-memory staging of k_commit_coop): markers and pivots go through the dead simplices' records in HBM.
 template <int D, int G>
-__global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, const int *act, RoundSel rsel, int stats) {
+__device__ __noinline__ void commit_global(const Mesh<D> &m, const ScrView sv, int nk, int nb, int v, int base, int gl, unsigned gmask) {
     constexpr int M = Dim<D>::M;
-    const Mesh<D> &m = A.m;
-    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const int gl = threadIdx.x & (G - 1);
-    const unsigned gmask = group_mask<G>();
-    const int gshift = (threadIdx.x & 31) & ~(G - 1);
-    if (gid == 0 && gl == 0) m.cnt->nbig = 0;           // overflow slots are per round (attempt is over)
-    if (gid >= rsel.nsel) return;
-    const int slot = gid;
-    if (A.scr.slotStatus[slot] != ST_OK) return;
-    const int a = slot_entry(rsel, slot);
-    const int v = act[a];
-    const uint32_t q = bij_hash((uint32_t)slot, A.bits, A.salt);   // unique among the slots of this round
-    const int key_k = A.keybase | (int)(q << 1);
-    const int key_o = key_k | 1;
-    const ScrView sv = scr_view(A.scr, slot, A.scr.slotBig[slot]);
-    const int nk = A.scr.slotNk[slot], nb = A.scr.slotNb[slot];
-    (void)key_o;
-    bool bad = false;
-    for (int j = gl; j < nk; j += G) {
-        const int2 ow = __ldcg(reinterpret_cast<const int2 *>(&OWK(m, sv.k[j])));
-        if (ow.x != key_k || ow.y < key_k) bad = true;     // best killer, and no better point has it in its ring
-    }
-    for (int j = gl; j < nb; j += G) {
-        const int code = sv.o[j];
-        if (code >= 0 && __ldcg(&OWK(m, code >> 2)) < key_k) bad = true;   // no better point kills my outer ring
-    }
-    if (__any_sync(gmask, bad)) return;
-    int base = 0;
-    if (gl == 0) base = atomicAdd(&m.cnt->ntets, nb);
-    base = __shfl_sync(gmask, base, gshift);
-    if (base + nb > m.cap) {
-        // no room: leave the mesh untouched (the point stays pending), retire the part of the block that exists and
-        // tell the host to grow the store
-        for (int j = gl; j < nb; j += G)
-            if (base + j < m.cap) OWK(m, base + j) = -1;
-        if (gl == 0) m.cnt->oom_soft = 1;
-        return;
-    }
-
     // phase A: one lane per boundary facet: new simplex, outer back-pointer, marker in the dead simplex
     for (int j = gl; j < nb; j += G) {
         const int fc = sv.f[j];
@@ -331,11 +382,178 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
         const int t = sv.k[j];
         if (__ldcg(&OWK(m, t)) >= 0) OWK(m, t) = ~base;   // interior of the cavity (no boundary facet)
     }
+}
+
+#ifndef VOR_CK
+#define VOR_CK 48                 // commit: killed simplices of a cavity staged in shared memory (mean 20 in 3D, 4 in 2D)
+#endif
+#ifndef VOR_CB
+#define VOR_CB 100                // commit: boundary facets staged in shared memory (mean 27 / 6)
+#endif
+// The whole cavity (records of the killed simplices, boundary facets, a small id -> local index hash) is pulled into
+// shared memory with ONE level of independent gathers, checked, and retriangulated there: markers, the ridge pivots
+// of pair_simplices (delaunay_tree.rs:674-695) and the forwarding choice never leave the SM; HBM sees one full 32 B
+// record per new simplex, one back-pointer per outer facet and one dead mark per killed simplex.
+template <int D, int G>
+__global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, const int *act, RoundSel rsel, int stats) {
+    constexpr int M = Dim<D>::M;
+    constexpr int CK = VOR_CK, CB = VOR_CB, HS = 128, GPB = VOR_COOP_BLOCK / G;
+    static_assert(HS >= 2 * CK, "hash must stay at most half full");
+    __shared__ int4 s_tv[GPB][CK], s_tn[GPB][CK];
+    __shared__ int s_id[GPB][CK], s_fw[GPB][CK], s_hash[GPB][HS], s_f[GPB][CB], s_o[GPB][CB];
+    const Mesh<D> &m = A.m;
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gl = threadIdx.x & (G - 1);
+    const unsigned gmask = group_mask<G>();
+    const int gshift = (threadIdx.x & 31) & ~(G - 1);
+    if (gid == 0 && gl == 0) m.cnt->nbig = 0;           // overflow slots are per round (attempt is over)
+    if (gid >= rsel.nsel) return;
+    const int slot = gid;
+    if (A.scr.slotStatus[slot] != ST_OK) return;
+    const int a = slot_entry(rsel, slot);
+    const int v = act[a];
+    const uint32_t q = bij_hash((uint32_t)slot, A.bits, A.salt);   // unique among the slots of this round
+    const int key_k = A.keybase | (int)(q << 1);
+    const ScrView sv = scr_view(A.scr, slot, A.scr.slotBig[slot]);
+    const int nk = A.scr.slotNk[slot], nb = A.scr.slotNb[slot];
+    const bool fast = !(stats & 2) && nk <= CK && nb <= CB;   // stats bit 1: force the global-store path (A/B switch)
+    const int grp = threadIdx.x / G;
+    int4 *const tvs = s_tv[grp], *const tns = s_tn[grp];
+    int *const ids = s_id[grp], *const fw = s_fw[grp], *const hash = s_hash[grp], *const sf = s_f[grp], *const so = s_o[grp];
+    int *const tni = reinterpret_cast<int *>(tns);
+
+    // -- ownership check; the fast path loads the cavity in the same level of gathers
+    bool bad = false;
+    if (fast) {
+        for (int e = gl; e < nk; e += G) {
+            const int t = sv.k[e];
+            const int2 ow = __ldcg(reinterpret_cast<const int2 *>(&OWK(m, t)));
+            int4 tv, tn;
+            load_rec_cg(m, t, tv, tn);
+            if (ow.x != key_k || ow.y < key_k) bad = true;     // best killer, and no better point has it in its ring
+            ids[e] = t; tvs[e] = tv; tns[e] = tn; fw[e] = 0;
+        }
+        for (int j = gl; j < nb; j += G) {
+            const int f = sv.f[j], code = sv.o[j];
+            if (code >= 0 && __ldcg(&OWK(m, code >> 2)) < key_k) bad = true;   // no better point kills my outer ring
+            sf[j] = f; so[j] = code;
+        }
+        for (int h = gl; h < HS; h += G) hash[h] = -1;
+    } else {
+        for (int j = gl; j < nk; j += G) {
+            const int2 ow = __ldcg(reinterpret_cast<const int2 *>(&OWK(m, sv.k[j])));
+            if (ow.x != key_k || ow.y < key_k) bad = true;
+        }
+        for (int j = gl; j < nb; j += G) {
+            const int code = sv.o[j];
+            if (code >= 0 && __ldcg(&OWK(m, code >> 2)) < key_k) bad = true;
+        }
+    }
+    if (__any_sync(gmask, bad)) return;
+    // Slot recycling (fast path): new simplex j < nk takes the slot of killed simplex j, only the surplus comes from
+    // the bump allocator.  The store stays compact (no dead slots: 4x smaller footprint at 10M points), a new simplex
+    // lies where the simplices it replaces lay (spatial locality of the store is inherited, not diluted by time), and
+    // a pending point whose seed was killed finds a live simplex of the right neighbourhood in the same slot.
+    // The kill word of a recycled slot keeps this winner's key: every other contender of this round has a worse key
+    // on it and loses; from the next round on it is a stale mark (epochs count down).
+    const bool reuse = fast && !(stats & 4);
+    const int nfresh = reuse ? max(nb - nk, 0) : nb;
+    int base = 0;
+    if (gl == 0) base = atomicAdd(&m.cnt->ntets, nfresh);
+    base = __shfl_sync(gmask, base, gshift);
+    if (base + nfresh > m.cap) {
+        // no room: leave the mesh untouched (the point stays pending), retire the part of the block that exists and
+        // tell the host to grow the store
+        for (int j = gl; j < nfresh; j += G)
+            if (base + j < m.cap) OWK(m, base + j) = -1;
+        if (gl == 0) m.cnt->oom_soft = 1;
+        return;
+    }
+    int first = base;     // a simplex created by this insertion (seed for later points)
+    if (!fast) {
+        commit_global<D, G>(m, sv, nk, nb, v, base, gl, gmask);
+    } else {
+        const int nreuse = reuse ? min(nk, nb) : 0;
+        auto slot_of = [&](int j) -> int { return j < nreuse ? ids[j] : base + (j - nreuse); };
+        first = slot_of(0);
+        // id -> local index (open addressing, at most 3/8 full)
+        for (int e = gl; e < nk; e += G) {
+            unsigned h = ((unsigned)ids[e] * 2654435761u) >> 25;
+            while (atomicCAS(&hash[h], -1, e) != -1) h = (h + 1) & (HS - 1);
+        }
+        __syncwarp(gmask);
+        auto local_of = [&](int t) -> int {
+            unsigned h = ((unsigned)t * 2654435761u) >> 25;
+            for (int probe = 0; probe < HS; probe++) {
+                const int e = hash[h];
+                if (e < 0) break;
+                if (ids[e] == t) return e;
+                h = (h + 1) & (HS - 1);
+            }
+            set_err(m.cnt, ERR_CUDA);   // a pivot left the cavity: cannot happen on a consistent mesh
+            return -1;
+        };
+        // phase A: markers on the boundary facets of the staged cavity, forwarding choice per killed simplex
+        for (int j = gl; j < nb; j += G) {
+            const int f = sf[j];
+            const int e = local_of(f >> 2), i = f & 3;
+            if (e < 0) continue;
+            tni[e * 4 + i] = -j - 2;
+            fw[e] = j;                 // any of its boundary facets (benign race)
+            sf[j] = e * 4 + i;
+        }
+        __syncwarp(gmask);
+        // phase B: one lane per new simplex: vertices, outer neighbour, and the M-1 siblings found by pivoting around
+        // each ridge through the staged cavity
+        for (int j = gl; j < nb; j += G) {
+            const int f = sf[j];
+            const int e0 = f >> 2, i = f & 3;
+            const int outer = so[j];
+            const int T = slot_of(j);
+            const int4 cv0 = tvs[e0];
+            int4 verts = cv0;
+            set4(verts, i, v);
+            int4 nbr = make_int4(-1, -1, -1, -1);
+            set4(nbr, i, outer);
+#pragma unroll
+            for (int k = 0; k < M; k++) {
+                if (k == i) continue;
+                int r0 = -1, r1 = -1;
+#pragma unroll
+                for (int sidx = 0; sidx < M; sidx++) {
+                    if (sidx == i || sidx == k) continue;
+                    if (r0 < 0) r0 = get4(cv0, sidx); else r1 = get4(cv0, sidx);
+                }
+                int cur = e0, enter = i, exitf = k;
+                for (int guard = 0;; guard++) {
+                    const int code = tni[cur * 4 + exitf];
+                    if (code <= -2) { set4(nbr, k, slot_of(-code - 2) * 4 + enter); break; }
+                    if (guard >= 4 * CK) { set_err(m.cnt, ERR_CUDA); break; }
+                    const int ln = local_of(code >> 2), jb = code & 3;
+                    if (ln < 0) break;
+                    const int4 cv = tvs[ln];
+                    int y = -1;
+#pragma unroll
+                    for (int sidx = 0; sidx < M; sidx++) {
+                        if (sidx == jb) continue;
+                        const int vv = get4(cv, sidx);
+                        if (vv != r0 && vv != r1) y = sidx;
+                    }
+                    cur = ln; enter = jb; exitf = y;
+                }
+            }
+            store_rec(m, T, verts, nbr);
+            if (outer >= 0) TNI(m, outer >> 2, outer & 3) = T * 4 + i;
+        }
+        // phase C: killed simplices whose slot is not recycled die; a dead simplex forwards to a new simplex on one
+        // of its own boundary facets (interior simplices: to the first new simplex)
+        for (int e = gl + nreuse; e < nk; e += G) OWK(m, ids[e]) = ~slot_of(fw[e]);
+    }
     if (gl == 0) {
-        m.ptTet[v] = base;
+        m.ptTet[v] = first;
         m.seed[v] = -1;
-        atomicAdd(&m.cnt->win_total, 1ULL);
-        if (stats) {
+        atomicAdd(&m.cnt->part[gid & (NPART - 1)][0], (1ULL << 40) | (unsigned long long)nb);   // win_total, created_all
+        if (stats & 1) {
             atomicAdd(&m.cnt->killed, (unsigned long long)nk);
             atomicAdd(&m.cnt->created, (unsigned long long)nb);
         }

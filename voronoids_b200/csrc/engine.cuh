@@ -45,6 +45,10 @@ struct EngineOptions {
     int bulk_locate = 1;         // locate every point of a stage at its start (thread per point) instead of in its first attempt
     int select_mode = 1;         // 1 = stratified selection along the Morton-ordered active list, 0 = random subset
     int rounds_per_sync = 8;     // rounds launched back to back between two host read-backs of the counters
+    int prewalk = 0;             // walk kernel in front of the attempt kernel: 4 = 4 lanes per point, 1 = thread per point, 0 = off
+    int commit_smem = 1;         // commit retriangulates cavities staged in shared memory (0 = through the global store)
+    int recycle = 0;             // winners write new simplices into the slots of the simplices they kill (commit_smem path)
+    int red = 0;                 // kill reservation as a fire-and-forget reduction (match.any dedup), see k_attempt_coop
     double tet_factor = 0.0;     // simplex slots per vertex (0 = default: 31 in 3D, 7.5 in 2D)
 };
 
@@ -63,6 +67,10 @@ inline void options_from_env(EngineOptions &o) {
     if (const char *e = getenv("VOR_ROUNDS_PER_SYNC")) o.rounds_per_sync = atoi(e);
     if (const char *e = getenv("VOR_SELECT_MODE")) o.select_mode = atoi(e);
     if (const char *e = getenv("VOR_BULK_LOCATE")) o.bulk_locate = atoi(e);
+    if (const char *e = getenv("VOR_PREWALK")) o.prewalk = atoi(e);
+    if (const char *e = getenv("VOR_RED")) o.red = atoi(e);
+    if (const char *e = getenv("VOR_COMMIT_SMEM")) o.commit_smem = atoi(e);
+    if (const char *e = getenv("VOR_RECYCLE")) o.recycle = atoi(e);
     if (const char *e = getenv("VOR_CAPK")) { o.capk = atoi(e); o.capb = 2 * o.capk + 4; }
 }
 
@@ -211,6 +219,17 @@ template <int D> class Engine {
     void pull_counters() {
         be::d2h(hcnt, mesh.cnt, sizeof(Counters), stream);
         be::sync(stream);
+    }
+    // (win_total, created_all) = direct counters of the thread-per-point path + the privatised parts of k_commit_coop
+    unsigned long long win_total() const {
+        unsigned long long w = hcnt->win_total;
+        for (int p = 0; p < NPART; p++) w += hcnt->part[p][0] >> 40;
+        return w;
+    }
+    unsigned long long created_all() const {
+        unsigned long long c = hcnt->created_all;
+        for (int p = 0; p < NPART; p++) c += hcnt->part[p][0] & ((1ULL << 40) - 1ULL);
+        return c;
     }
     void push_counters() { be::h2d(mesh.cnt, hcnt, sizeof(Counters), stream); }
     void check_device_error(const char *where) {
@@ -475,10 +494,16 @@ template <int D> class Engine {
     template <int G> void launch_round(const AttemptArgs<D> &aa, const CheckArgs<D> &ca, const RoundSel &sel) {
         const unsigned grid = (unsigned)(((long long)sel.nsel * G + VOR_COOP_BLOCK - 1) / VOR_COOP_BLOCK);
         prof.start(0, stream);
-        k_attempt_coop<D, G><<<grid, VOR_COOP_BLOCK, 0, stream>>>(aa, sel);
+        if (opt.prewalk == 4) { k_walk_coop<D, 4><<<(unsigned)(((long long)sel.nsel * 4 + 127) / 128), 128, 0, stream>>>(aa, sel); be::g_launches++; }
+        else if (opt.prewalk == 1) { k_walk_coop<D, 1><<<(unsigned)((sel.nsel + 127) / 128), 128, 0, stream>>>(aa, sel); be::g_launches++; }
+        bool launched = false;
+        if constexpr (G == 32) {
+            if (opt.red) { k_attempt_coop<D, G, 1><<<grid, VOR_COOP_BLOCK, 0, stream>>>(aa, sel); launched = true; }
+        }
+        if (!launched) k_attempt_coop<D, G, 0><<<grid, VOR_COOP_BLOCK, 0, stream>>>(aa, sel);
         prof.stop(stream);
         prof.start(2, stream);
-        k_commit_coop<D, G><<<grid, VOR_COOP_BLOCK, 0, stream>>>(ca, act, sel, opt.stats);
+        k_commit_coop<D, G><<<grid, VOR_COOP_BLOCK, 0, stream>>>(ca, act, sel, (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2) | (opt.recycle ? 0 : 4));
         prof.stop(stream);
         be::g_launches += 2;
     }
@@ -494,7 +519,7 @@ template <int D> class Engine {
         IotaArgs ia{act, lo};
         VOR_LAUNCH(IotaArgs, iota_body, nact, ia, stream);
         pull_counters();
-        const unsigned long long win0 = hcnt->win_total;
+        const unsigned long long win0 = win_total();
         const int dup0 = hcnt->ndup;
         int stall = 0;
         uint32_t roundSalt = (uint32_t)mix64((uint64_t)lo * 0x9E37u + rs.rounds);
@@ -524,7 +549,7 @@ template <int D> class Engine {
             }
             pull_counters();
             check_device_error("round");
-            const long long done = (long long)(hcnt->win_total - win0) + (long long)(hcnt->ndup - dup0);
+            const long long done = (long long)(win_total() - win0) + (long long)(hcnt->ndup - dup0);
             const int newPending = total - (int)done;
             insertedTotal += (long long)(pending - newPending);
             remainingInCall -= (long long)(pending - newPending);
@@ -556,7 +581,7 @@ template <int D> class Engine {
             }
         }
         rs.attempts = hcnt->attempts;
-        rs.winners = hcnt->win_total;
+        rs.winners = win_total();
         if (opt.verbose)
             fprintf(stderr, "[vor] stage [%d,%d) done: rounds so far %llu, simplices %d\n", lo, hi, rs.rounds, hcnt->ntets);
     }

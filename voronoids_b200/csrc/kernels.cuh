@@ -60,6 +60,49 @@ template <int D> VOR_HD int4 &TV(const Mesh<D> &m, int t) { return m.tet[2 * (si
 template <int D> VOR_HD int4 &TN(const Mesh<D> &m, int t) { return m.tet[2 * (size_t)t + 1]; }
 template <int D> VOR_HD int &TNI(const Mesh<D> &m, int t, int i) { return reinterpret_cast<int *>(m.tet)[8 * (size_t)t + 4 + i]; }
 
+// One simplex record (vertex ids + neighbour codes, one 32 B sector) or one 3D vertex (double4, one sector) moves with
+// ONE 256-bit instruction (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256).  Measured on the B200 (tools/micro/gather_bench.cu):
+// once the gather footprint exceeds the TLB reach (~256 MB) the SMs sustain ~40 G scattered load INSTRUCTIONS per
+// second per thread-lane whatever their width, so a 32 B record fetched as 2 x 128 bit gathers at half the rate
+// (20.9 vs 38.2 G records/s over 16 GB).
+template <int D> VOR_HD void load_rec(const Mesh<D> &m, int t, int4 &tv, int4 &tn) {
+#ifdef __CUDA_ARCH__
+    asm volatile("ld.global.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(tv.x), "=r"(tv.y), "=r"(tv.z), "=r"(tv.w), "=r"(tn.x), "=r"(tn.y), "=r"(tn.z), "=r"(tn.w)
+                 : "l"(m.tet + 2 * (size_t)t));
+#else
+    tv = TV(m, t); tn = TN(m, t);
+#endif
+}
+template <int D> VOR_HD void load_rec_cg(const Mesh<D> &m, int t, int4 &tv, int4 &tn) {   // L2 only (like __ldcg)
+#ifdef __CUDA_ARCH__
+    asm volatile("ld.global.cg.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(tv.x), "=r"(tv.y), "=r"(tv.z), "=r"(tv.w), "=r"(tn.x), "=r"(tn.y), "=r"(tn.z), "=r"(tn.w)
+                 : "l"(m.tet + 2 * (size_t)t));
+#else
+    tv = TV(m, t); tn = TN(m, t);
+#endif
+}
+template <int D> VOR_HD void store_rec(const Mesh<D> &m, int t, const int4 &tv, const int4 &tn) {
+#ifdef __CUDA_ARCH__
+    asm volatile("st.global.v8.s32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+                 :: "r"(tv.x), "r"(tv.y), "r"(tv.z), "r"(tv.w), "r"(tn.x), "r"(tn.y), "r"(tn.z), "r"(tn.w), "l"(m.tet + 2 * (size_t)t)
+                 : "memory");
+#else
+    TV(m, t) = tv; TN(m, t) = tn;
+#endif
+}
+VOR_HD double4 load_pt(const double4 *p) {
+#ifdef __CUDA_ARCH__
+    double4 r;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+#else
+    return *p;
+#endif
+}
+VOR_HD double2 load_pt(const double2 *p) { return *p; }
+
 struct Scratch {
     int *killed, *bfacet, *bouter;     // contiguous per slot: entry j of slot s at [s * cap + j] (coalesced for a lane group)
     int *slotAct, *slotNk, *slotNb, *slotStatus, *slotBig;
@@ -108,7 +151,7 @@ template <> struct Geo<3> {
     using Pt = double4;
     struct Verts { Pt p0, p1, p2, p3; };
     static VOR_HD Verts load(const Mesh<3> &m, const int4 &v) {
-        Verts r; r.p0 = m.pts[v.x]; r.p1 = m.pts[v.y]; r.p2 = m.pts[v.z]; r.p3 = m.pts[v.w]; return r;
+        Verts r; r.p0 = load_pt(m.pts + v.x); r.p1 = load_pt(m.pts + v.y); r.p2 = load_pt(m.pts + v.z); r.p3 = load_pt(m.pts + v.w); return r;
     }
     // bit i set <=> p is strictly beyond face i (orientation with vertex i replaced by p is negative)
     static VOR_HD int beyond_mask(PredCtx &cx, const Verts &t, const Pt &p) {
@@ -432,6 +475,7 @@ template <int D> VOR_HD void retri_body(const RetriArgs<D> &A, int w) {
     m.ptTet[v] = base;
     m.seed[v] = -1;
     atomic_add_ull(&m.cnt->win_total, 1ULL);
+    atomic_add_ull(&m.cnt->created_all, (unsigned long long)nb);
     if (A.stats) {
         atomic_add_ull(&m.cnt->killed, (unsigned long long)nk);
         atomic_add_ull(&m.cnt->created, (unsigned long long)nb);

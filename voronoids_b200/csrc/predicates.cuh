@@ -65,7 +65,11 @@ VOR_HD int orient3d(PredCtx &cx, const double4 &a, const double4 &b, const doubl
     return finish_exact(cx, s, re);
 }
 
-VOR_HD int incircle(PredCtx &cx, const double2 &a, const double2 &b, const double2 &c, const double2 &d) {
+// (noinline slow paths take everything BY VALUE: a reference parameter would force the caller to keep the operands in
+// local memory and store them there before every test, not only in the rare branch that calls this)
+VOR_HD_NOINLINE int incircle_slow(Counters *cnt, double ax, double ay, double bx, double by, double cx_, double cy_, double dx, double dy) {
+    PredCtx cx{cnt};
+    const double2 a{ax, ay}, b{bx, by}, c{cx_, cy_}, d{dx, dy};
     const double adx = a.x - d.x, ady = a.y - d.y;
     const double bdx = b.x - d.x, bdy = b.y - d.y;
     const double cdx = c.x - d.x, cdy = c.y - d.y;
@@ -85,7 +89,30 @@ VOR_HD int incircle(PredCtx &cx, const double2 &a, const double2 &b, const doubl
     return finish_exact(cx, s, re);
 }
 
-VOR_HD int insphere(PredCtx &cx, const double4 &a, const double4 &b, const double4 &c, const double4 &d, const double4 &e) {
+// Static filter in front of the semi-static one: with X, Y = largest |x|, |y| difference, every term of the permanent
+// is bounded by the same expression in X, Y (rounding is monotone), so permanent <= 6 fl(XY) fl(X^2 + Y^2) (1+eps)^4 and
+// |det| > 61 eps fl(XY) fl(X^2+Y^2) >= (10 + 96 eps) eps permanent certifies the sign.  It keeps 2 extra values
+// live instead of the 6 products of the permanent.
+VOR_HD int incircle(PredCtx &cx, const double2 &a, const double2 &b, const double2 &c, const double2 &d) {
+    const double adx = a.x - d.x, ady = a.y - d.y;
+    const double bdx = b.x - d.x, bdy = b.y - d.y;
+    const double cdx = c.x - d.x, cdy = c.y - d.y;
+    const double mx = fmax(fmax(fabs(adx), fabs(bdx)), fabs(cdx));
+    const double my = fmax(fmax(fabs(ady), fabs(bdy)), fabs(cdy));
+    const double al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;
+    const double det = al * (bdx * cdy - cdx * bdy) + bl * (cdx * ady - adx * cdy) + cl * (adx * bdy - bdx * ady);
+    const double bound = ((61.0 * EPSH) * (mx * my)) * (mx * mx + my * my);
+    if (det > bound) return 1;
+    if (-det > bound) return -1;
+    return incircle_slow(cx.cnt, a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y);
+}
+
+VOR_HD_NOINLINE int insphere_slow(Counters *cnt, double ax, double ay, double az, double bx, double by, double bz, double cx_, double cy_, double cz_,
+                                  double dx, double dy, double dz, double ex, double ey, double ez) {
+    PredCtx cx{cnt};
+    double4 a, b, c, d, e;
+    a.x = ax; a.y = ay; a.z = az; a.w = 0.0; b.x = bx; b.y = by; b.z = bz; b.w = 0.0; c.x = cx_; c.y = cy_; c.z = cz_; c.w = 0.0;
+    d.x = dx; d.y = dy; d.z = dz; d.w = 0.0; e.x = ex; e.y = ey; e.z = ez; e.w = 0.0;
     const double aex = a.x - e.x, bex = b.x - e.x, cex = c.x - e.x, dex = d.x - e.x;
     const double aey = a.y - e.y, bey = b.y - e.y, cey = c.y - e.y, dey = d.y - e.y;
     const double aez = a.z - e.z, bez = b.z - e.z, cez = c.z - e.z, dez = d.z - e.z;
@@ -117,6 +144,40 @@ VOR_HD int insphere(PredCtx &cx, const double4 &a, const double4 &b, const doubl
     int re = 0;
     const int s = insphere_exact(A, B, C, D, E, &re);
     return finish_exact(cx, s, re);
+}
+
+// Static filter in front of the semi-static one (same determinant, same operation order).  With X, Y, Z = largest
+// |x|, |y|, |z| difference and L = fl(X^2 + Y^2 + Z^2): every |product| of the permanent is <= fl(XY), every lift <= L
+// (rounding is monotone), so permanent <= 24 fl(fl(XY) Z) L (1+eps)^5, and
+// |det| > 385 eps fl(fl(XY) Z) L >= (16 + 224 eps) eps permanent certifies the sign.  The permanent's 12 products do
+// not have to stay live next to the determinant (the semi-static form spilled ~45 registers per test at the 64
+// registers the attempt kernel runs with; ncu: 7x more local than global requests).
+VOR_HD int insphere(PredCtx &cx, const double4 &a, const double4 &b, const double4 &c, const double4 &d, const double4 &e) {
+    const double aex = a.x - e.x, bex = b.x - e.x, cex = c.x - e.x, dex = d.x - e.x;
+    const double aey = a.y - e.y, bey = b.y - e.y, cey = c.y - e.y, dey = d.y - e.y;
+    const double aez = a.z - e.z, bez = b.z - e.z, cez = c.z - e.z, dez = d.z - e.z;
+    const double mx = fmax(fmax(fabs(aex), fabs(bex)), fmax(fabs(cex), fabs(dex)));
+    const double my = fmax(fmax(fabs(aey), fabs(bey)), fmax(fabs(cey), fabs(dey)));
+    const double mz = fmax(fmax(fabs(aez), fabs(bez)), fmax(fabs(cez), fabs(dez)));
+    const double al = aex * aex + aey * aey + aez * aez;
+    const double bl = bex * bex + bey * bey + bez * bez;
+    const double cl = cex * cex + cey * cey + cez * cez;
+    const double dl = dex * dex + dey * dey + dez * dez;
+    const double ab = aex * bey - bex * aey;
+    const double bc = bex * cey - cex * bey;
+    const double cd = cex * dey - dex * cey;
+    const double da = dex * aey - aex * dey;
+    const double ac = aex * cey - cex * aey;
+    const double bd = bex * dey - dex * bey;
+    const double abc = aez * bc - bez * ac + cez * ab;
+    const double bcd = bez * cd - cez * bd + dez * bc;
+    const double cda = cez * da + dez * ac + aez * cd;
+    const double dab = dez * ab + aez * bd + bez * da;
+    const double det = (dl * abc - cl * dab) + (bl * cda - al * bcd);
+    const double bound = ((385.0 * EPSH) * ((mx * my) * mz)) * (mx * mx + my * my + mz * mz);
+    if (det > bound) return 1;
+    if (-det > bound) return -1;
+    return insphere_slow(cx.cnt, a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z, d.x, d.y, d.z, e.x, e.y, e.z);
 }
 
 } // namespace vor

@@ -250,7 +250,9 @@ template <int D> VOR_HD void locate_body(const LocateArgs<D> &A, int j) {
     unsigned rot = (unsigned)v * 2654435761u;
     unsigned steps = 0;
     for (;;) {
-        const typename G::Verts tvv = G::load(m, TV(m, s));
+        int4 stv, stn;
+        load_rec(m, s, stv, stn);
+        const typename G::Verts tvv = G::load(m, stv);
         const int mk = G::beyond_mask(cx, tvv, p);
         if (mk == 0) break;
         int go = 0;
@@ -259,7 +261,7 @@ template <int D> VOR_HD void locate_body(const LocateArgs<D> &A, int j) {
             const int i = (r0 + k) % M;
             if ((mk >> i) & 1) { go = i; break; }
         }
-        const int code = TNI(m, s, go);
+        const int code = get4(stn, go);
         if (code < 0) { set_err(m.cnt, ERR_OUTSIDE); return; }
         s = code >> 2;
         rot = rot * 1664525u + 1013904223u;

@@ -134,7 +134,13 @@ struct Counters {
     unsigned long long win_total;    // points inserted (all rounds)
     unsigned long long sel_total;    // attempt slots claimed (all rounds)
     unsigned long long tests_ok;     // in-sphere tests of the attempts that completed their flood
+    unsigned long long created_all;  // simplices created since the tree was made (slots are recycled: ntets is not this)
+    // privatised copies of (win_total, created_all) for the cooperative commit kernel: 10M same-address atomics cost
+    // ~9 ms each on the B200 (L2 serialises them); winner g adds (1 << 40 | created) to part[g % NPART][0], each part
+    // in its own 32 B sector.  The host folds them (Engine::win_total / created_all).
+    unsigned long long part[128][4];
 };
+constexpr int NPART = 128;
 
 VOR_HD void set_err(Counters *c, int code) { atomic_cas_i(&c->err, 0, code); }
 
