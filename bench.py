@@ -292,6 +292,16 @@ def main():
                                        "rounds": sd["rounds"], "exact_calls": sd["exact_calls"], "exact_zero": sd["exact_zero"],
                                        "aborted_attempts": sd["aborted"] / n, "E_tests_completed_attempts": sd["tests_completed"] / n},
                 "step_ms_by_kernel": sd["profile_ms"]}
+    # the resource that is actually saturated (profiles/r1_gather_microbench.md): scattered gather
+    # instructions per lane and second once the footprint exceeds the TLB reach.  Instructions the attempt kernel
+    # issues by construction: 4 per attempt (active entry, seed, point, owner), 5 per walk step (record + 4 vertices),
+    # 7 per in-sphere test (owner pair, record, 4 vertices, reduction); L1 hits on shared vertices are included, so the
+    # fraction can exceed 1 of the miss-only ceiling measured by tools/micro/gather_bench.cu (38.2 G/s over 16 GB).
+    if dim == 3 and t_attempt > 0:
+        g_instr = 4.0 * sd["attempts"] + 5.0 * sd["walk_steps"] + 7.0 * sd["tests"]
+        roofline["gather"] = {"bound": "scattered-load instruction rate beyond the TLB reach", "achieved": g_instr / t_attempt / 1e9,
+                              "peak": 38.2, "unit": "G gather instructions/s", "frac": g_instr / t_attempt / 1e9 / 38.2,
+                              "peak_source": "tools/micro/gather_bench.cu on this pool's B200 (profiles/r1_gather_microbench.md)"}
 
     # ---- end to end through the public API with host buffers (H2D + D2H inside the timed region)
     e2e = None

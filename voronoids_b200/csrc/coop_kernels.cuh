@@ -113,6 +113,12 @@ __global__ void __launch_bounds__(128) k_walk_coop(AttemptArgs<D> A, RoundSel rs
 #ifndef VOR_SK
 #define VOR_SK 64                 // killed simplices of a cavity staged in shared memory (ids + neighbour codes: 20 B each)
 #endif
+#ifndef VOR_ATT_STAGE
+#define VOR_ATT_STAGE 0           // 1: the flood reads the killed list and the neighbour codes from a shared-memory copy of
+                                  // the cavity instead of the global store (shorter dependent chain; measured 9 % SLOWER:
+                                  // the kernel is bound by the gather-instruction rate, not by the chain, and the
+                                  // copy costs registers)
+#endif
 #ifndef VOR_ATTEMPT_REGS
 #define VOR_ATTEMPT_REGS 64       // registers per thread of the attempt kernel (measured best of 80/64/48)
 #endif
@@ -120,21 +126,14 @@ __global__ void __launch_bounds__(128) k_walk_coop(AttemptArgs<D> A, RoundSel rs
 // level): lanes of one batch that reach the same simplex are deduplicated with match.any, and a better killer that
 // slips in between the owner read and the reduction is caught by the ownership check of commit.
 template <int D, int G, int RED>
-__global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_COOP_BLOCK)) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
+__device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const RoundSel &rsel, const int gid, int *const sk, int4 *const sn) {
     constexpr int M = Dim<D>::M;
     using Gm = Geo<D>;
+    constexpr int SK = VOR_SK;
     const Mesh<D> &m = A.m;
-    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;   // group = attempt slot
     const int gl = threadIdx.x & (G - 1);                          // lane inside the group
     const unsigned gmask = group_mask<G>();
     const int gshift = (threadIdx.x & 31) & ~(G - 1);              // first lane of the group inside the warp
-    // the cavity found so far, staged in shared memory: ids and neighbour codes of the first SK killed simplices, so a
-    // flood level starts from two shared-memory reads instead of two dependent L2 round trips (scratch, then record)
-    constexpr int SK = VOR_SK;
-    __shared__ int s_kid[VOR_COOP_BLOCK / G][SK];
-    __shared__ int4 s_knb[VOR_COOP_BLOCK / G][SK];
-    int *const sk = s_kid[threadIdx.x / G];
-    int4 *const sn = s_knb[threadIdx.x / G];
     if (gid >= rsel.nsel) return;
     const int slot = gid;
     const int a = slot_entry(rsel, slot);
@@ -203,7 +202,7 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
     }
     if (!fail) {
         ScrView sv = scr_view(A.scr, slot, -1);
-        if (gl == 0) { sv.k[0] = s; sk[0] = s; sn[0] = stn; }
+        if (gl == 0) { sv.k[0] = s; if (VOR_ATT_STAGE) { sk[0] = s; sn[0] = stn; } }
         __syncwarp(gmask);
         nk = 1;
         int head = 0;
@@ -221,7 +220,7 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
                     const int e = head + j / M;
                     const int i = j % M;
                     int t, code;
-                    if (e < SK) { t = sk[e]; code = reinterpret_cast<const int *>(sn)[e * 4 + i]; }
+                    if (VOR_ATT_STAGE && e < SK) { t = sk[e]; code = reinterpret_cast<const int *>(sn)[e * 4 + i]; }
                     else { t = sv.k[e]; code = TNI(m, t, i); }
                     if (code < 0) {
                         pushB = true; fcode = t * 4 + i; ocode = code;
@@ -230,7 +229,8 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
                         // the owner pair and the record of n are independent gathers: issue both before looking at either
                         const int2 ow = __ldcg(reinterpret_cast<const int2 *>(&OWK(m, n)));   // x = kill word, y = ring word
                         int4 nverts;
-                        load_rec_cg(m, n, nverts, nnb);   // vertex ids + neighbour codes: one 256-bit gather
+                        if (VOR_ATT_STAGE) load_rec_cg(m, n, nverts, nnb);   // vertex ids + neighbour codes: one 256-bit gather
+                        else nverts = __ldcg(&TV(m, n));
                         if (ow.x == key_k) {
                             // already in my cavity
                         } else if (ow.x < key_k) {
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
                 if (pushK) {
                     const int pos = nk + __popc(mk & lt);
                     sv.k[pos] = newT;
-                    if (pos < SK) { sk[pos] = newT; sn[pos] = nnb; }
+                    if (VOR_ATT_STAGE && pos < SK) { sk[pos] = newT; sn[pos] = nnb; }
                 }
                 if (pushB) { const int pos = nb + __popc(mb & lt); sv.f[pos] = fcode; sv.o[pos] = ocode; }
                 nk += ck;
@@ -311,6 +311,46 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
             atomicAdd(&m.cnt->attempts, 1ULL);
             if (status != ST_OK) atomicAdd(&m.cnt->aborted, 1ULL);
             else atomicAdd(&m.cnt->tests_ok, (unsigned long long)tests);
+        }
+    }
+}
+
+// One group per attempt slot (grid = slots), or -- option "persist" -- resident warps that pull slots from per-SM
+// queues: SM i works through the i-th contiguous range of the Morton-ordered slots, so the simplices and vertices it
+// gathers in one round come from one compact region of the mesh (and of the store) instead of every 148th block of
+// it; the ranges of SMs that finish early are drained by the others.
+template <int D, int G, int RED>
+__global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_COOP_BLOCK)) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
+    // the cavity found so far, staged in shared memory: ids and neighbour codes of the first SK killed simplices, so a
+    // flood level starts from two shared-memory reads instead of two dependent L2 round trips (scratch, then record)
+    __shared__ int s_kid[VOR_COOP_BLOCK / G][VOR_SK];
+    __shared__ int4 s_knb[VOR_COOP_BLOCK / G][VOR_SK];
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;   // group = attempt slot
+    if (gid >= rsel.nsel) return;
+    attempt_one<D, G, RED>(A, rsel, gid, s_kid[threadIdx.x / G], s_knb[threadIdx.x / G]);
+}
+
+constexpr int NQUEUE = 148;       // per-SM slot queues of the persistent kernels (one per SM of the B200)
+template <int D, int RED>
+__global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_COOP_BLOCK)) k_attempt_persist(AttemptArgs<D> A, RoundSel rsel, int *qctr) {
+    __shared__ int s_kid[VOR_COOP_BLOCK / 32][VOR_SK];
+    __shared__ int4 s_knb[VOR_COOP_BLOCK / 32][VOR_SK];
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    const int lane = threadIdx.x & 31;
+    const int per = (rsel.nsel + NQUEUE - 1) / NQUEUE;
+    for (int r = 0; r < NQUEUE; r++) {
+        const int qi = (int)((smid + (unsigned)r) % (unsigned)NQUEUE);
+        const int lo = qi * per, size = min(per, rsel.nsel - lo);
+        if (size <= 0) continue;
+        if (r > 0 && *(volatile int *)&qctr[qi] >= size) continue;     // drained
+        for (;;) {
+            int g = 0;
+            if (lane == 0) g = atomicAdd(&qctr[qi], 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            if (g >= size) break;
+            attempt_one<D, 32, RED>(A, rsel, lo + g, s_kid[threadIdx.x / 32], s_knb[threadIdx.x / 32]);
+            __syncwarp();
         }
     }
 }

@@ -47,8 +47,9 @@ struct EngineOptions {
     int rounds_per_sync = 8;     // rounds launched back to back between two host read-backs of the counters
     int prewalk = 0;             // walk kernel in front of the attempt kernel: 4 = 4 lanes per point, 1 = thread per point, 0 = off
     int commit_smem = 1;         // commit retriangulates cavities staged in shared memory (0 = through the global store)
+    int persist = 0;             // rounds of at least this many attempts run the persistent attempt kernel (0 = never)
     int recycle = 0;             // winners write new simplices into the slots of the simplices they kill (commit_smem path)
-    int red = 0;                 // kill reservation as a fire-and-forget reduction (match.any dedup), see k_attempt_coop
+    int red = 1;                 // kill reservation as a fire-and-forget reduction (match.any dedup), see k_attempt_coop
     double tet_factor = 0.0;     // simplex slots per vertex (0 = default: 31 in 3D, 7.5 in 2D)
 };
 
@@ -71,6 +72,7 @@ inline void options_from_env(EngineOptions &o) {
     if (const char *e = getenv("VOR_RED")) o.red = atoi(e);
     if (const char *e = getenv("VOR_COMMIT_SMEM")) o.commit_smem = atoi(e);
     if (const char *e = getenv("VOR_RECYCLE")) o.recycle = atoi(e);
+    if (const char *e = getenv("VOR_PERSIST")) o.persist = atoi(e);
     if (const char *e = getenv("VOR_CAPK")) { o.capk = atoi(e); o.capb = 2 * o.capk + 4; }
 }
 
@@ -105,7 +107,7 @@ template <int D> class Engine {
     Counters *hcnt = nullptr; // pinned host mirror
     // scratch
     Scratch scr{};
-    int *act = nullptr, *act2 = nullptr, *blockCnt = nullptr;
+    int *act = nullptr, *act2 = nullptr, *blockCnt = nullptr, *qctr = nullptr;
     long long *d_misc = nullptr;
     long long insertedTotal = 0;
     long long remainingInCall = 0;   // points of the current insert call not inserted yet
@@ -132,7 +134,7 @@ template <int D> class Engine {
     ~Engine() {
         be::dfree(mesh.pts); be::dfree(mesh.tet); be::dfree(mesh.owner); be::dfree(mesh.seed);
         be::dfree(mesh.ptTet); be::dfree(mesh.cnt); be::dfree(inputIdx); be::dfree(vidOfInput); be::dfree(keysAll);
-        be::dfree(d_boxLo); be::dfree(d_boxHi); be::dfree(act); be::dfree(act2); be::dfree(blockCnt); be::dfree(d_edges);
+        be::dfree(d_boxLo); be::dfree(d_boxHi); be::dfree(act); be::dfree(act2); be::dfree(blockCnt); be::dfree(d_edges); be::dfree(qctr);
         free_scratch();
         be::dfree(d_misc);
         be::hfree_pinned(hcnt);
@@ -498,7 +500,15 @@ template <int D> class Engine {
         else if (opt.prewalk == 1) { k_walk_coop<D, 1><<<(unsigned)((sel.nsel + 127) / 128), 128, 0, stream>>>(aa, sel); be::g_launches++; }
         bool launched = false;
         if constexpr (G == 32) {
-            if (opt.red) { k_attempt_coop<D, G, 1><<<grid, VOR_COOP_BLOCK, 0, stream>>>(aa, sel); launched = true; }
+            if (opt.persist && sel.nsel >= opt.persist) {
+                // resident warps pulling slots from per-SM queues (contiguous slot range per SM)
+                if (!qctr) qctr = (int *)be::dmalloc(sizeof(int) * 256);
+                be::dmemset(qctr, 0, sizeof(int) * 256, stream);
+                const unsigned pgrid = 148u * (unsigned)(65536 / (VOR_ATTEMPT_REGS * VOR_COOP_BLOCK));
+                if (opt.red) k_attempt_persist<D, 1><<<pgrid, VOR_COOP_BLOCK, 0, stream>>>(aa, sel, qctr);
+                else k_attempt_persist<D, 0><<<pgrid, VOR_COOP_BLOCK, 0, stream>>>(aa, sel, qctr);
+                launched = true;
+            } else if (opt.red) { k_attempt_coop<D, G, 1><<<grid, VOR_COOP_BLOCK, 0, stream>>>(aa, sel); launched = true; }
         }
         if (!launched) k_attempt_coop<D, G, 0><<<grid, VOR_COOP_BLOCK, 0, stream>>>(aa, sel);
         prof.stop(stream);

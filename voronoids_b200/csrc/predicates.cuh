@@ -146,13 +146,51 @@ VOR_HD_NOINLINE int insphere_slow(Counters *cnt, double ax, double ay, double az
     return finish_exact(cx, s, re);
 }
 
+VOR_HD int insphere_semi(PredCtx &cx, const double4 &a, const double4 &b, const double4 &c, const double4 &d, const double4 &e) {
+    const double aex = a.x - e.x, bex = b.x - e.x, cex = c.x - e.x, dex = d.x - e.x;
+    const double aey = a.y - e.y, bey = b.y - e.y, cey = c.y - e.y, dey = d.y - e.y;
+    const double aez = a.z - e.z, bez = b.z - e.z, cez = c.z - e.z, dez = d.z - e.z;
+    const double aexbey = aex * bey, bexaey = bex * aey, ab = aexbey - bexaey;
+    const double bexcey = bex * cey, cexbey = cex * bey, bc = bexcey - cexbey;
+    const double cexdey = cex * dey, dexcey = dex * cey, cd = cexdey - dexcey;
+    const double dexaey = dex * aey, aexdey = aex * dey, da = dexaey - aexdey;
+    const double aexcey = aex * cey, cexaey = cex * aey, ac = aexcey - cexaey;
+    const double bexdey = bex * dey, dexbey = dex * bey, bd = bexdey - dexbey;
+    const double abc = aez * bc - bez * ac + cez * ab;
+    const double bcd = bez * cd - cez * bd + dez * bc;
+    const double cda = cez * da + dez * ac + aez * cd;
+    const double dab = dez * ab + aez * bd + bez * da;
+    const double al = aex * aex + aey * aey + aez * aez;
+    const double bl = bex * bex + bey * bey + bez * bez;
+    const double cl = cex * cex + cey * cey + cez * cez;
+    const double dl = dex * dex + dey * dey + dez * dez;
+    const double det = (dl * abc - cl * dab) + (bl * cda - al * bcd);
+    const double aezp = fabs(aez), bezp = fabs(bez), cezp = fabs(cez), dezp = fabs(dez);
+    const double perm =
+        ((fabs(cexdey) + fabs(dexcey)) * bezp + (fabs(dexbey) + fabs(bexdey)) * cezp + (fabs(bexcey) + fabs(cexbey)) * dezp) * al +
+        ((fabs(dexaey) + fabs(aexdey)) * cezp + (fabs(aexcey) + fabs(cexaey)) * dezp + (fabs(cexdey) + fabs(dexcey)) * aezp) * bl +
+        ((fabs(aexbey) + fabs(bexaey)) * dezp + (fabs(bexdey) + fabs(dexbey)) * aezp + (fabs(dexaey) + fabs(aexdey)) * bezp) * cl +
+        ((fabs(bexcey) + fabs(cexbey)) * aezp + (fabs(cexaey) + fabs(aexcey)) * bezp + (fabs(aexbey) + fabs(bexaey)) * cezp) * dl;
+    const double bound = (16.0 + 224.0 * EPSH) * EPSH * perm;
+    if (det > bound) return 1;
+    if (-det > bound) return -1;
+    const double A[3] = {a.x, a.y, a.z}, B[3] = {b.x, b.y, b.z}, C[3] = {c.x, c.y, c.z}, D[3] = {d.x, d.y, d.z}, E[3] = {e.x, e.y, e.z};
+    int re = 0;
+    const int s = insphere_exact(A, B, C, D, E, &re);
+    return finish_exact(cx, s, re);
+}
+
 // Static filter in front of the semi-static one (same determinant, same operation order).  With X, Y, Z = largest
 // |x|, |y|, |z| difference and L = fl(X^2 + Y^2 + Z^2): every |product| of the permanent is <= fl(XY), every lift <= L
 // (rounding is monotone), so permanent <= 24 fl(fl(XY) Z) L (1+eps)^5, and
 // |det| > 385 eps fl(fl(XY) Z) L >= (16 + 224 eps) eps permanent certifies the sign.  The permanent's 12 products do
 // not have to stay live next to the determinant (the semi-static form spilled ~45 registers per test at the 64
 // registers the attempt kernel runs with; ncu: 7x more local than global requests).
+#ifndef VOR_STATIC_FILTER
+#define VOR_STATIC_FILTER 0   // measured on the 10M-point run: attempt kernel 98.7 ms with it, 96.2 ms without
+#endif
 VOR_HD int insphere(PredCtx &cx, const double4 &a, const double4 &b, const double4 &c, const double4 &d, const double4 &e) {
+    if (!VOR_STATIC_FILTER) return insphere_semi(cx, a, b, c, d, e);
     const double aex = a.x - e.x, bex = b.x - e.x, cex = c.x - e.x, dex = d.x - e.x;
     const double aey = a.y - e.y, bey = b.y - e.y, cey = c.y - e.y, dey = d.y - e.y;
     const double aez = a.z - e.z, bez = b.z - e.z, cez = c.z - e.z, dez = d.z - e.z;
