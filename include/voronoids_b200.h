@@ -83,6 +83,13 @@ vor_status vor_tree_counts(vor_tree *t, uint64_t *n_vertices, uint64_t *n_simpli
 /* Delaunay graph: sorted unique {lo,hi} input-index pairs, u32 little endian.
  * edges == NULL: only *n_edges is written. */
 vor_status vor_tree_edges(vor_tree *t, uint32_t *edges, size_t cap, size_t *n_edges);
+/* same list in a host block of the library's caching host allocator, owned by the CALLER afterwards (release it with
+ * vor_host_free): a recycled block is already resident, so the copy skips the first-touch page faults that dominate
+ * vor_tree_edges into a fresh buffer; VOR_PINNED_RESULTS=1 makes the blocks page-locked (direct DMA).  This is what
+ * voronoids_b200.delaunay(pts).edges() wraps as a numpy array without a copy; it has no counterpart in the reference,
+ * whose getters copy the maps element by element (src/lib.rs:73-101). */
+vor_status vor_tree_edges_host(vor_tree *t, uint32_t **edges, size_t *n_edges);
+vor_status vor_host_free(void *block);
 /* same list left on the device (pointer valid until the next insert/destroy) + an order-independent checksum */
 vor_status vor_tree_edges_device(vor_tree *t, const uint32_t **d_edges, size_t *n_edges, uint64_t *checksum);
 

@@ -31,6 +31,20 @@ inline void d2h_big(void *h, const void *d, size_t n, Stream) { std::memcpy(h, d
 inline void h2d_big(void *d, const void *h, size_t n, Stream) { std::memcpy(d, h, n); }
 inline void *hmalloc_pinned(size_t bytes) { return std::malloc(bytes ? bytes : 16); }
 inline void hfree_pinned(void *p) { std::free(p); }
+struct HostPool {   // stand-in for the caching pinned allocator of backend_cuda.cuh
+    std::vector<void *> live;
+    void *alloc(size_t bytes, bool *pinned) { void *p = std::malloc(bytes ? bytes : 16); live.push_back(p); *pinned = false; return p; }
+    bool free(void *p) {
+        if (!p) return true;
+        auto it = std::find(live.begin(), live.end(), p);
+        if (it == live.end()) return false;
+        live.erase(it);
+        std::free(p);
+        return true;
+    }
+    void release() {}
+};
+static HostPool g_hostpool;
 inline void sort_pairs(uint64_t *ki, uint64_t *ko, uint32_t *vi, uint32_t *vo, size_t n, Stream) {
     std::vector<size_t> idx(n);
     std::iota(idx.begin(), idx.end(), (size_t)0);

@@ -184,3 +184,35 @@ def test_gpu_python_api_matches_reference_shape(gpu_lib, oracle):
     # circumspheres follow the reference's float formulas
     co, ro = oracle.ref_circumsphere(np.array([verts[v].point for v in some.vertices]))
     assert some.center == co.tolist() and some.radius == ro
+
+
+def test_gpu_edges_pinned_block_outlives_tree(gpu_lib):
+    """vor_tree_edges_host hands the caller a pinned block (zero-copy numpy view); same bytes as vor_tree_edges."""
+    t = _capi.Tree(gpu_lib, pointgen.uniform(50_000, 3, 5))
+    a = t.edges(pinned=True)
+    b = t.edges(pinned=False)
+    t.close()
+    assert a.dtype == np.uint32 and a.shape == b.shape and np.array_equal(a, b)
+    assert isinstance(a.base, _capi._HostBlock)
+    ptr = a.base._ptr
+    del a                                   # the block goes back to the library's pool ...
+    assert gpu_lib.vor_host_free(ptr) != 0  # ... so a second free is refused loudly
+    assert gpu_lib.vor_host_free(12345) != 0
+
+
+ENGINE_DEFAULTS = {"recycle": 0, "persist": 0, "red": 1, "commit_smem": 1, "prewalk": 0}
+
+
+@pytest.mark.parametrize("opts", [{"recycle": 1}, {"persist": 1024}, {"persist": 1024, "recycle": 1}, {"red": 0}, {"commit_smem": 0}, {"prewalk": 4},
+                                  {"prewalk": 1}])
+def test_gpu_engine_options_keep_parity(gpu_lib, oracle, opts):
+    """every scheduling / layout option of the engine yields the oracle's edge set (3D and 2D)"""
+    try:
+        for k, v in opts.items():
+            gpu_lib.vor_set_option(k.encode(), float(v))
+        for dim in (3, 2):
+            st = ec.check_against_oracle(gpu_lib, oracle, pointgen.uniform(120_000, dim, 11))
+            assert st["winners"] == 120_000
+    finally:
+        for k, v in ENGINE_DEFAULTS.items():
+            gpu_lib.vor_set_option(k.encode(), float(v))

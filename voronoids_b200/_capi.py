@@ -28,6 +28,8 @@ SYMBOLS = {
     "vor_delaunay": (C.c_int, [C.c_int, dp, C.c_size_t, C.c_int, C.POINTER(tree_p)]),
     "vor_tree_counts": (C.c_int, [tree_p, u64p, u64p, u64p]),
     "vor_tree_edges": (C.c_int, [tree_p, u32p, C.c_size_t, szp]),
+    "vor_tree_edges_host": (C.c_int, [tree_p, C.POINTER(C.c_void_p), szp]),
+    "vor_host_free": (C.c_int, [C.c_void_p]),
     "vor_tree_edges_device": (C.c_int, [tree_p, C.POINTER(C.c_void_p), szp, u64p]),
     "vor_tree_export_simplices": (C.c_int, [tree_p, i32p, i32p, dp, dp, C.c_size_t, szp]),
     "vor_tree_locate": (C.c_int, [tree_p, dp, C.c_size_t, i32p, C.c_size_t, i32p]),
@@ -48,6 +50,20 @@ SYMBOLS = {
 N_STATS = 16
 STAT_NAMES = ("rounds", "attempts", "winners", "owner_resets", "compactions", "stages", "walk_steps", "tests", "killed", "created",
               "exact_calls", "exact_zero", "duplicates", "simplex_slots", "aborted", "tests_completed")
+
+
+class _HostBlock:
+    """Owner of one result block of the library's host pool; numpy arrays made from it keep it alive through their .base."""
+
+    def __init__(self, lib, ptr, shape, typestr):
+        self._lib, self._ptr = lib, ptr
+        self.__array_interface__ = {"data": (ptr, False), "shape": tuple(shape), "typestr": typestr, "version": 3}
+
+    def __del__(self):
+        try:
+            self._lib.vor_host_free(C.c_void_p(self._ptr))
+        except Exception:
+            pass
 
 
 def bind(lib):
@@ -120,10 +136,17 @@ class Tree:
         self._check(self._lib.vor_tree_counts(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"vertices": a.value, "simplices": b.value, "max_simplex_id": c.value}
 
-    def edges(self):
+    def edges(self, pinned=True):
+        """uint32 [m, 2].  pinned=True: zero-copy view of a block of the library's caching host allocator (recycled, hence
+        resident; page-locked with VOR_PINNED_RESULTS=1); it goes back to the pool when the array is garbage collected.
+        pinned=False: vor_tree_edges into a fresh numpy buffer."""
         n = C.c_size_t()
+        if pinned and hasattr(self._lib, "vor_tree_edges_host"):
+            ptr = C.c_void_p()
+            self._check(self._lib.vor_tree_edges_host(self._h, C.byref(ptr), C.byref(n)))
+            return np.asarray(_HostBlock(self._lib, ptr.value, (n.value, 2), "<u4"))
         self._check(self._lib.vor_tree_edges(self._h, None, 0, C.byref(n)))
-        out = np.zeros((n.value, 2), dtype=np.uint32)
+        out = np.empty((n.value, 2), dtype=np.uint32)
         self._check(self._lib.vor_tree_edges(self._h, out.ctypes.data_as(u32p), n.value, C.byref(n)))
         return out
 

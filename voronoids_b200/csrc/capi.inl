@@ -227,6 +227,24 @@ vor_status vor_tree_edges(vor_tree *t, uint32_t *edges, size_t cap, size_t *n_ed
     });
 }
 
+vor_status vor_tree_edges_host(vor_tree *t, uint32_t **edges, size_t *n_edges) {
+    return guarded([&]() -> vor_status {
+        if (!t || !edges || !n_edges) { g_err = "null argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        return t->visit([&](auto &e) -> vor_status {
+            long long m = 0;
+            *edges = e.edges_to_host_block(&m);
+            *n_edges = (size_t)m;
+            return VOR_OK;
+        });
+    });
+}
+
+vor_status vor_host_free(void *block) {
+    if (!vor::be::g_hostpool.free(block)) { g_err = "not a block handed out by this library"; return VOR_ERR_ARG; }
+    return VOR_OK;
+}
+
 vor_status vor_tree_edges_device(vor_tree *t, const uint32_t **d_edges, size_t *n_edges, uint64_t *checksum) {
     return guarded([&]() -> vor_status {
         if (!t) { g_err = "null tree"; return VOR_ERR_ARG; }

@@ -766,7 +766,8 @@ template <int D> class Engine {
         int *cursor = (int *)be::dmalloc(sizeof(int) * (size_t)(ninput + 1));
         be::dmemset(deg, 0, sizeof(int) * (size_t)(ninput + 1), stream);
         be::dmemset(cursor, 0, sizeof(int) * (size_t)(ninput + 1), stream);
-        EdgeArgs<D> ea{mesh, inputIdx, deg, cursor, nullptr, 0};
+        unsigned char *emask = D == 3 ? (unsigned char *)be::dmalloc((size_t)nt + 16) : nullptr;
+        EdgeArgs<D> ea{mesh, inputIdx, deg, cursor, nullptr, 0, emask};
         VOR_LAUNCH(EdgeArgs<D>, edges_body<D>, nt, ea, stream);
         lap("count pass");
         const long long total = scan_exclusive(deg, ninput + 1);
@@ -782,13 +783,23 @@ template <int D> class Engine {
         VOR_LAUNCH(RowSortArgs, row_sort_body, ninput, ra, stream);
         be::sync(stream);
         lap("row sort");
-        be::dfree(deg); be::dfree(cursor); be::dfree(hi);
+        be::dfree(deg); be::dfree(cursor); be::dfree(hi); be::dfree(emask);
         nedges = total;
         return nedges;
     }
     void copy_edges(uint32_t *h_out, long long cap) {
         const long long m = edges();
         be::d2h_big(h_out, d_edges, sizeof(uint32_t) * 2 * (size_t)std::min(m, cap), stream);
+    }
+    // edge list in a host block of the caching host allocator; the caller owns it afterwards (vor_host_free)
+    uint32_t *edges_to_host_block(long long *m_out) {
+        const long long m = edges();
+        bool pinned = false;
+        uint32_t *h = (uint32_t *)be::g_hostpool.alloc(sizeof(uint32_t) * 2 * (size_t)std::max(m, 1LL), &pinned);
+        if (pinned) { be::d2h(h, d_edges, sizeof(uint32_t) * 2 * (size_t)m, stream); be::sync(stream); }
+        else be::d2h_big(h, d_edges, sizeof(uint32_t) * 2 * (size_t)m, stream);
+        *m_out = m;
+        return h;
     }
     unsigned long long edge_checksum() {
         const long long m = edges();

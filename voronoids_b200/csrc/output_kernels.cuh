@@ -24,6 +24,8 @@ template <int D> struct EdgeArgs {
     int *cursor;           // [nInput] fill cursors
     uint32_t *hi;          // CSR column array
     int pass;              // 0 = count, 1 = fill
+    unsigned char *mask;   // 3D: per simplex slot, bit e = this simplex owns its e-th edge (written by the count pass so
+                           // that the fill pass does not repeat the pivots around every edge); may be null
 };
 
 // true if simplex t is the lowest-numbered simplex around edge (slots sa, sb) -- 3D pivot around the edge
@@ -72,12 +74,17 @@ template <int D> VOR_HD void edges_body(const EdgeArgs<D> &A, int t) {
     if (!simplex_live(m, t)) return;
     const int4 tv = TV(m, t);
     if constexpr (D == 3) {
+        const bool replay = A.pass == 1 && A.mask != nullptr;
+        const unsigned have = replay ? A.mask[t] : 0u;
+        unsigned own = 0;
+        int e = 0;
         for (int sa = 0; sa < M; sa++)
-            for (int sb = sa + 1; sb < M; sb++) {
+            for (int sb = sa + 1; sb < M; sb++, e++) {
                 const int va = get4(tv, sa), vb = get4(tv, sb);
                 if (va < m.nsuper || vb < m.nsuper) continue;
-                if (edge_owner3(m, t, tv, sa, sb)) edge_emit(A, va, vb);
+                if (replay ? ((have >> e) & 1u) != 0u : edge_owner3(m, t, tv, sa, sb)) { own |= 1u << e; edge_emit(A, va, vb); }
             }
+        if (A.pass == 0 && A.mask != nullptr) A.mask[t] = (unsigned char)own;
     } else {
         const int4 tn = TN(m, t);
         for (int i = 0; i < 3; i++) { // edge opposite slot i
