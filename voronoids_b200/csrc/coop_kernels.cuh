@@ -113,6 +113,10 @@ __global__ void __launch_bounds__(128) k_walk_coop(AttemptArgs<D> A, RoundSel rs
 #ifndef VOR_SK
 #define VOR_SK 64                 // killed simplices of a cavity staged in shared memory (ids + neighbour codes: 20 B each)
 #endif
+#ifndef VOR_ATTEMPT_BLOCK
+#define VOR_ATTEMPT_BLOCK 32      // threads per block of the attempt kernel: one warp, so that a finished attempt frees its
+                                  // registers at once (measured on the 10M-point run: 108 ms vs 116 ms with 64 threads)
+#endif
 #ifndef VOR_ATT_STAGE
 #define VOR_ATT_STAGE 0           // 1: the flood reads the killed list and the neighbour codes from a shared-memory copy of
                                   // the cavity instead of the global store (shorter dependent chain; measured 9 % SLOWER:
@@ -320,11 +324,11 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
 // gathers in one round come from one compact region of the mesh (and of the store) instead of every 148th block of
 // it; the ranges of SMs that finish early are drained by the others.
 template <int D, int G, int RED>
-__global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_COOP_BLOCK)) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
+__global__ void __launch_bounds__(VOR_ATTEMPT_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_ATTEMPT_BLOCK)) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
     // the cavity found so far, staged in shared memory: ids and neighbour codes of the first SK killed simplices, so a
     // flood level starts from two shared-memory reads instead of two dependent L2 round trips (scratch, then record)
-    __shared__ int s_kid[VOR_COOP_BLOCK / G][VOR_SK];
-    __shared__ int4 s_knb[VOR_COOP_BLOCK / G][VOR_SK];
+    __shared__ int s_kid[VOR_ATTEMPT_BLOCK / G][VOR_SK];
+    __shared__ int4 s_knb[VOR_ATTEMPT_BLOCK / G][VOR_SK];
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;   // group = attempt slot
     if (gid >= rsel.nsel) return;
     attempt_one<D, G, RED>(A, rsel, gid, s_kid[threadIdx.x / G], s_knb[threadIdx.x / G]);
@@ -332,9 +336,9 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VO
 
 constexpr int NQUEUE = 148;       // per-SM slot queues of the persistent kernels (one per SM of the B200)
 template <int D, int RED>
-__global__ void __launch_bounds__(VOR_COOP_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_COOP_BLOCK)) k_attempt_persist(AttemptArgs<D> A, RoundSel rsel, int *qctr) {
-    __shared__ int s_kid[VOR_COOP_BLOCK / 32][VOR_SK];
-    __shared__ int4 s_knb[VOR_COOP_BLOCK / 32][VOR_SK];
+__global__ void __launch_bounds__(VOR_ATTEMPT_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_ATTEMPT_BLOCK)) k_attempt_persist(AttemptArgs<D> A, RoundSel rsel, int *qctr) {
+    __shared__ int s_kid[VOR_ATTEMPT_BLOCK / 32][VOR_SK];
+    __shared__ int4 s_knb[VOR_ATTEMPT_BLOCK / 32][VOR_SK];
     unsigned smid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
     const int lane = threadIdx.x & 31;

@@ -495,6 +495,7 @@ template <int D> class Engine {
     }
     template <int G> void launch_round(const AttemptArgs<D> &aa, const CheckArgs<D> &ca, const RoundSel &sel) {
         const unsigned grid = (unsigned)(((long long)sel.nsel * G + VOR_COOP_BLOCK - 1) / VOR_COOP_BLOCK);
+        const unsigned agrid = (unsigned)(((long long)sel.nsel * G + VOR_ATTEMPT_BLOCK - 1) / VOR_ATTEMPT_BLOCK);
         prof.start(0, stream);
         if (opt.prewalk == 4) { k_walk_coop<D, 4><<<(unsigned)(((long long)sel.nsel * 4 + 127) / 128), 128, 0, stream>>>(aa, sel); be::g_launches++; }
         else if (opt.prewalk == 1) { k_walk_coop<D, 1><<<(unsigned)((sel.nsel + 127) / 128), 128, 0, stream>>>(aa, sel); be::g_launches++; }
@@ -504,13 +505,13 @@ template <int D> class Engine {
                 // resident warps pulling slots from per-SM queues (contiguous slot range per SM)
                 if (!qctr) qctr = (int *)be::dmalloc(sizeof(int) * 256);
                 be::dmemset(qctr, 0, sizeof(int) * 256, stream);
-                const unsigned pgrid = 148u * (unsigned)(65536 / (VOR_ATTEMPT_REGS * VOR_COOP_BLOCK));
-                if (opt.red) k_attempt_persist<D, 1><<<pgrid, VOR_COOP_BLOCK, 0, stream>>>(aa, sel, qctr);
-                else k_attempt_persist<D, 0><<<pgrid, VOR_COOP_BLOCK, 0, stream>>>(aa, sel, qctr);
+                const unsigned pgrid = 148u * (unsigned)std::min(32, 65536 / (VOR_ATTEMPT_REGS * VOR_ATTEMPT_BLOCK));
+                if (opt.red) k_attempt_persist<D, 1><<<pgrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel, qctr);
+                else k_attempt_persist<D, 0><<<pgrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel, qctr);
                 launched = true;
-            } else if (opt.red) { k_attempt_coop<D, G, 1><<<grid, VOR_COOP_BLOCK, 0, stream>>>(aa, sel); launched = true; }
+            } else if (opt.red) { k_attempt_coop<D, G, 1><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel); launched = true; }
         }
-        if (!launched) k_attempt_coop<D, G, 0><<<grid, VOR_COOP_BLOCK, 0, stream>>>(aa, sel);
+        if (!launched) k_attempt_coop<D, G, 0><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel);
         prof.stop(stream);
         prof.start(2, stream);
         k_commit_coop<D, G><<<grid, VOR_COOP_BLOCK, 0, stream>>>(ca, act, sel, (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2) | (opt.recycle ? 0 : 4));
