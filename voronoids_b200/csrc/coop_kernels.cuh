@@ -1,14 +1,17 @@
-// coop_kernels.cuh -- lane-group-cooperative versions of the three round kernels (CUDA only).
+// coop_kernels.cuh -- lane-group-cooperative round kernels (CUDA only): the product path on the B200.
 //
-// G lanes (G = 32: a whole warp, north_star's "one warp per point"; G = 8 when a round has many points) work on ONE
-// pending point.  The serial dependency chain of the thread-per-point bodies in kernels.cuh (one in-sphere test after
-// the other: ~60-100 tests x 3-4 dependent gathers each) becomes one chain per BFS LEVEL of the conflict region:
-//   attempt  walk: lane k evaluates the orientation of facet k (ballot -> facet to cross);
-//            flood: each lane takes one (frontier simplex, facet) item: gathers the neighbour code, its owner word, its
-//            4 vertex records (32 B sectors) and evaluates the exact in-sphere test; reservation by atomicMin; new killed
-//            simplices / boundary facets are appended with ballot + popc prefix sums into the point's contiguous scratch.
-//   commit   (check + retriangulate fused) lanes stride over the footprint and vote; a winner allocates its block of
-//            simplex slots and lanes stride over the boundary facets (new simplices), then over the pivot items.
+// G lanes (G = 32: a whole warp, north_star's "one warp per point"; G = 8 optional) work on ONE pending point.  The
+// serial dependency chain of the thread-per-point bodies in kernels.cuh (one in-sphere test after the other: ~60-100
+// tests x 3-4 dependent gathers each) becomes one chain per BFS LEVEL of the conflict region:
+//   attempt  walk: lane k evaluates the orientation of facet k (ballot -> facet to cross), one 256-bit record gather per
+//            step; flood: each lane takes one (frontier simplex, facet) item: gathers the neighbour code, its owner pair,
+//            its record and its 4 vertex sectors (256-bit loads) and evaluates the exact in-sphere test; reservation by
+//            red.min / atomicMin; new killed simplices / boundary facets are appended with ballot + popc prefix sums
+//            into the point's contiguous scratch.  One warp per block, 64 registers.
+//   commit   (check + retriangulate fused) the cavity is staged in shared memory, lanes vote on ownership; a winner
+//            allocates its block of simplex slots and retriangulates inside the SM (one lane per new simplex).
+// What bounds them on the B200 is the scattered-load-instruction rate beyond the TLB reach, hence
+// the wide loads; the compile-time switches below record the alternatives that were measured and lost.
 // Same scratch format and same semantics as kernels.cuh (reference: delaunay_tree.rs:33-123, :213-334, scheduler.rs:6-55),
 // so the two implementations are interchangeable (option "coop"); tests/emu exercises the thread-per-point bodies on
 // the CPU, tests/test_gpu_* exercise these against the oracle on the B200.
