@@ -13,7 +13,7 @@ for it in range(4):
     lib.vor_set_option(b"profile", 1.0 if (it == 3 and os.environ.get("T_PROFILE")) else 0.0)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     h = _capi.tree_p()
-    st = lib.vor_tree_create_device(dim, C.c_void_p(p.data_ptr()), n, 0, None, C.byref(h)); torch.cuda.synchronize(); t1 = time.perf_counter()
+    st = lib.vor_tree_create_device(dim, C.c_void_p(p.data_ptr()), n, 0, (C.c_void_p(torch.cuda.current_stream().cuda_stream) if os.environ.get('T_STREAM') else None), C.byref(h)); torch.cuda.synchronize(); t1 = time.perf_counter()
     st = lib.vor_tree_insert_device(h, C.c_void_p(p.data_ptr()), n, 1); torch.cuda.synchronize(); t2 = time.perf_counter()
     assert st == 0, st
     if it == 3 and stats:

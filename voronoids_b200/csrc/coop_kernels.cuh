@@ -120,6 +120,11 @@ __global__ void __launch_bounds__(128) k_walk_coop(AttemptArgs<D> A, RoundSel rs
 #define VOR_ATTEMPT_BLOCK 32      // threads per block of the attempt kernel: one warp, so that a finished attempt frees its
                                   // registers at once (measured on the 10M-point run: 108 ms vs 116 ms with 64 threads)
 #endif
+#ifndef VOR_DEDUP
+#define VOR_DEDUP 0               // 1: lanes of a batch that reach the same neighbour elect one tester (match.any + shuffle);
+                                  // saves the ~6 % duplicate tests but measured 12 % SLOWER (107 vs 95 ms): the election
+                                  // sits in front of every gather
+#endif
 #ifndef VOR_ATT_STAGE
 #define VOR_ATT_STAGE 0           // 1: the flood reads the killed list and the neighbour codes from a shared-memory copy of
                                   // the cavity instead of the global store (shorter dependent chain; measured 9 % SLOWER:
@@ -218,6 +223,66 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
             const int tail = nk;
             const int items = (tail - head) * M;
             for (int base = 0; base < items && !lost; base += G) {
+#if VOR_DEDUP
+                // Lanes of one batch that reach the same neighbour n (a ring simplex seen from two killed simplices of
+                // the same level) elect ONE of them with match.any: it gathers and tests n, the others take its verdict
+                // by shuffle.  Saves the ~6 % duplicate tests (7 gather instructions each) and makes the claim of a
+                // newly killed simplex unique without looking at the value an atomic returns.
+                const int j = base + gl;
+                bool pushK = false, pushB = false, lostLane = false;
+                int newT = 0, fcode = 0, ocode = 0;
+                int4 nnb = make_int4(-1, -1, -1, -1);
+                const bool active = j < items;
+                int t = 0, i = 0, code = -1;
+                int n = -1 - (int)(threadIdx.x & 31);      // unique dummy: inactive lanes and hull facets match nobody
+                if (active) {
+                    const int e = head + j / M;
+                    i = j % M;
+                    if (VOR_ATT_STAGE && e < SK) { t = sk[e]; code = reinterpret_cast<const int *>(sn)[e * 4 + i]; }
+                    else { t = sv.k[e]; code = TNI(m, t, i); }
+                    if (code >= 0) n = code >> 2;
+                    else { pushB = true; fcode = t * 4 + i; ocode = code; }
+                }
+                const unsigned same = __match_any_sync(gmask, n);
+                const int leader = __ffs(same) - 1;
+                const bool lead = n >= 0 && leader == (int)(threadIdx.x & 31);
+                enum { V_MINE = 0, V_LOST = 1, V_RING = 2, V_NEW = 3 };
+                int verdict = V_MINE;
+                if (lead) {
+                    // the owner pair and the record of n are independent gathers: issue both before looking at either
+                    const int2 ow = __ldcg(reinterpret_cast<const int2 *>(&OWK(m, n)));   // x = kill word, y = ring word
+                    int4 nverts;
+                    if (VOR_ATT_STAGE) load_rec_cg(m, n, nverts, nnb);   // vertex ids + neighbour codes: one 256-bit gather
+                    else nverts = __ldcg(&TV(m, n));
+                    if (ow.x == key_k) verdict = V_MINE;            // already in my cavity
+                    else if (ow.x < key_k) verdict = V_LOST;        // a better point kills n (or n is dead)
+                    else if (ow.y == key_o) verdict = V_RING;       // already tested by me: not in conflict
+                    else {
+                        tests++;
+                        const typename Gm::Verts nv = Gm::load(m, nverts);
+                        if (Gm::conflict(cx, nv, p)) {
+                            if (ow.y < key_k) verdict = V_LOST;     // a better point keeps n in its outer ring
+                            else if (RED) { atomicMin(&OWK(m, n), key_k); verdict = V_NEW; }
+                            else {
+                                const int old = atomicMin(&OWK(m, n), key_k);
+                                verdict = old < key_k ? V_LOST : (old != key_k ? V_NEW : V_MINE);
+                            }
+                        } else {
+                            // outer-ring mark: fire and forget (RED, no round trip).  Rings may be shared; a better
+                            // point that KILLS n was either seen above or is caught by the ownership check of commit.
+                            atomicMin(&OWR(m, n), key_o);
+                            verdict = V_RING;
+                        }
+                    }
+                }
+                verdict = __shfl_sync(gmask, verdict, leader);
+                if (n >= 0) {
+                    if (verdict == V_LOST) lostLane = true;
+                    else if (verdict == V_RING) { pushB = true; fcode = t * 4 + i; ocode = code; }
+                    else if (verdict == V_NEW && lead) { pushK = true; newT = n; }
+                }
+                if (__any_sync(gmask, lostLane)) { lost = true; break; }
+#else
                 const int j = base + gl;
                 bool pushK = false, pushB = false, lostLane = false;
                 int newT = 0, fcode = 0, ocode = 0;
@@ -271,6 +336,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
                     const unsigned same = __match_any_sync(gmask, claim);
                     if (claim >= 0 && (__ffs(same) - 1) == (threadIdx.x & 31)) { pushK = true; newT = claim; }
                 }
+#endif
                 const unsigned mk = (__ballot_sync(gmask, pushK) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
                 const unsigned mb = (__ballot_sync(gmask, pushB) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
                 const int ck = __popc(mk), cb = __popc(mb);
