@@ -105,6 +105,15 @@ vor_status vor_tree_export_simplices(vor_tree *t, int32_t *vertices, int32_t *ne
  * coincides with a vertex (the reference panics, delaunay_tree.rs:47-54); -1 = more than cap simplices. */
 vor_status vor_tree_locate(vor_tree *t, const double *points, size_t n, int32_t *out_ids, size_t cap, int32_t *counts);
 
+/* scheduler::make_queue (src/scheduler.rs:6-28): footprint of every query point against the current tree = sorted
+ * unique neighbours-of-neighbours of its conflict region, as indices into vor_tree_export_simplices.  CSR output:
+ * offsets[n+1], ids[offsets[n]].  ids == NULL: only offsets and *total are written.  The reference's ghost simplices do
+ * not exist here: hull facets contribute nothing (footprints differ only where the 2-ring reaches the super simplex). */
+vor_status vor_make_queue(vor_tree *t, const double *points, size_t n, int64_t *offsets, int32_t *ids, size_t cap, size_t *total);
+/* scheduler::find_placement (src/scheduler.rs:30-55): 1-based greedy round of every queue entry, in queue order,
+ * computed on `device`.  An empty footprint is VOR_ERR_NO_CONFLICT (the reference's .max().unwrap() panics). */
+vor_status vor_find_placement(const int64_t *offsets, const int32_t *ids, size_t n, uint64_t *placement, int device);
+
 /* check_delaunay (delaunay_tree.rs:512-541): *ok = 1 iff every live simplex is positively oriented, adjacency is
  * symmetric and every interior facet is locally Delaunay (equivalent to the brute-force empty-sphere test).
  * fail_counts (optional, 5 entries): orientation, dead neighbour, asymmetric, facet mismatch, not Delaunay. */

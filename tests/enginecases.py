@@ -131,3 +131,32 @@ def case_locate(lib, O, dim, n=3000, nq=40):
         assert len(t.locate(pts[:1])[0]) == 0
     finally:
         t.close()
+
+
+def case_scheduler(lib, O, dim, n=3000, nq=500):
+    """scheduler::make_queue + find_placement (scheduler.rs:6-55, tests/test_scheduler.rs:6-37) against the restated
+    reference: same 1-based rounds for the same queue, footprints sorted / unique / inside the export index space."""
+    pts = pointgen.uniform(n, dim, 7)
+    t = _capi.Tree(lib, pts)
+    ref = O.RefDelaunay(pts, mode="split", n_seq=n)
+    try:
+        nlive = t.counts()["simplices"]
+        for q in (0.3 + 0.4 * pointgen.uniform(nq, dim, 8), pointgen.uniform(nq, dim, 9)):
+            off, ids = t.make_queue(q)
+            assert off[0] == 0 and len(off) == nq + 1 and off[-1] == len(ids)
+            regions = t.locate(q)
+            for i in range(0, nq, 37):
+                fp = ids[off[i]:off[i + 1]]
+                assert len(fp) > 0 and np.all(np.diff(fp) > 0) and fp[0] >= 0 and fp[-1] < nlive
+                assert set(regions[i].tolist()) <= set(fp.tolist())     # the conflict region lies inside its own 2-ring
+            rounds = _capi.find_placement(lib, off, ids)
+            assert rounds.min() == 1 and np.array_equal(rounds, ref.placement(q))
+        # one entry, and an empty footprint is the reference's panic
+        assert _capi.find_placement(lib, np.array([0, 3]), np.array([5, 6, 9]))[0] == 1
+        try:
+            _capi.find_placement(lib, np.array([0, 0]), np.zeros(0, dtype=np.int32))
+            raise AssertionError("empty footprint accepted")
+        except _capi.VorError as e:
+            assert e.status == 1
+    finally:
+        t.close()

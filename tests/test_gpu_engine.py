@@ -216,3 +216,21 @@ def test_gpu_engine_options_keep_parity(gpu_lib, oracle, opts):
     finally:
         for k, v in ENGINE_DEFAULTS.items():
             gpu_lib.vor_set_option(k.encode(), float(v))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_gpu_scheduler_matches_reference_restatement(gpu_lib, oracle, dim):
+    ec.case_scheduler(gpu_lib, oracle, dim)
+
+
+def test_gpu_python_scheduler_module(gpu_lib, oracle):
+    """voronoids_b200.scheduler mirrors scheduler::{make_queue, find_placement} (tests/test_scheduler.rs:6-37)"""
+    import voronoids_b200 as vb
+    pts = pointgen.uniform(2000, 3, 0)
+    tree = vb.delaunay(pts[:1000])
+    queue = vb.scheduler.make_queue(pts[1000:], tree)
+    assert len(queue) == 1000 and queue[5][0] == 5 and queue[5][1] == [float(x) for x in pts[1005]]
+    assert all(s in tree.simplices for s in queue[5][2])
+    placement = vb.scheduler.find_placement(queue)
+    ref = oracle.RefDelaunay(pts[:1000], mode="split", n_seq=1000).placement(pts[1000:])
+    assert placement == [int(x) for x in ref]

@@ -33,6 +33,8 @@ SYMBOLS = {
     "vor_tree_edges_device": (C.c_int, [tree_p, C.POINTER(C.c_void_p), szp, u64p]),
     "vor_tree_export_simplices": (C.c_int, [tree_p, i32p, i32p, dp, dp, C.c_size_t, szp]),
     "vor_tree_locate": (C.c_int, [tree_p, dp, C.c_size_t, i32p, C.c_size_t, i32p]),
+    "vor_make_queue": (C.c_int, [tree_p, dp, C.c_size_t, i64p, i32p, C.c_size_t, szp]),
+    "vor_find_placement": (C.c_int, [i64p, i32p, C.c_size_t, u64p, C.c_int]),
     "vor_tree_check_delaunay": (C.c_int, [tree_p, C.POINTER(C.c_int), i32p]),
     "vor_tree_super_simplex": (C.c_int, [tree_p, C.c_size_t, dp, dp, dp]),
     "vor_tree_stats": (C.c_int, [tree_p, u64p]),
@@ -50,6 +52,18 @@ SYMBOLS = {
 N_STATS = 16
 STAT_NAMES = ("rounds", "attempts", "winners", "owner_resets", "compactions", "stages", "walk_steps", "tests", "killed", "created",
               "exact_calls", "exact_zero", "duplicates", "simplex_slots", "aborted", "tests_completed")
+
+
+def find_placement(lib, offsets, ids, device=0):
+    """scheduler::find_placement on a CSR queue: uint64 rounds (1-based)."""
+    off = np.ascontiguousarray(offsets, dtype=np.int64)
+    idv = np.ascontiguousarray(ids, dtype=np.int32)
+    n = off.size - 1
+    out = np.zeros(max(n, 1), dtype=np.uint64)
+    st = lib.vor_find_placement(off.ctypes.data_as(i64p), idv.ctypes.data_as(i32p) if idv.size else None, n, out.ctypes.data_as(u64p), device)
+    if st != 0:
+        raise VorError(st, lib.vor_last_error().decode())
+    return out[:n]
 
 
 class _HostBlock:
@@ -178,6 +192,18 @@ class Tree:
         if (cnt < 0).any():
             return self.locate(points, cap * 4)
         return [np.sort(out[i, :cnt[i]]) for i in range(q.shape[0])]
+
+    def make_queue(self, points):
+        """scheduler::make_queue: CSR (offsets int64 [n+1], ids int32) of the footprints, export indices."""
+        q, qp = as_f64(points)
+        q = q.reshape(-1, self.dim)
+        n = q.shape[0]
+        off = np.zeros(n + 1, dtype=np.int64)
+        tot = C.c_size_t()
+        self._check(self._lib.vor_make_queue(self._h, qp, n, off.ctypes.data_as(i64p), None, 0, C.byref(tot)))
+        ids = np.zeros(max(tot.value, 1), dtype=np.int32)
+        self._check(self._lib.vor_make_queue(self._h, qp, n, off.ctypes.data_as(i64p), ids.ctypes.data_as(i32p), ids.size, C.byref(tot)))
+        return off, ids[:tot.value]
 
     def check_delaunay(self):
         ok = C.c_int()

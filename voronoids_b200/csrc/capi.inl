@@ -288,6 +288,69 @@ vor_status vor_tree_locate(vor_tree *t, const double *points, size_t n, int32_t 
     });
 }
 
+vor_status vor_make_queue(vor_tree *t, const double *points, size_t n, int64_t *offsets, int32_t *ids, size_t cap, size_t *total) {
+    return guarded([&]() -> vor_status {
+        if (!t || (!points && n) || !offsets) { g_err = "null argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        return t->visit([&](auto &e) -> vor_status {
+            // conflict regions and footprints grow until every query fits (uniform 3D: ~20 killed, ~150 footprint ids)
+            int kcap = 64, fcap = 512;
+            std::vector<int> fp, cnt(n);
+            for (;;) {
+                fp.assign(n * (size_t)fcap, 0);
+                e.make_queue(points, (int)n, kcap, fcap, fp.data(), cnt.data());
+                bool again = false;
+                for (size_t i = 0; i < n; i++) {
+                    if (cnt[i] == -2) { g_err = "query point outside the super simplex"; return VOR_ERR_OUTSIDE; }
+                    if (cnt[i] == -1) again = true;
+                }
+                if (!again) break;
+                if (kcap >= (1 << 14)) { g_err = "conflict region exceeds the query capacity"; return VOR_ERR_CAPACITY; }
+                kcap *= 4; fcap *= 4;
+            }
+            int64_t run = 0;
+            for (size_t i = 0; i < n; i++) { offsets[i] = run; run += cnt[i]; }
+            offsets[n] = run;
+            if (total) *total = (size_t)run;
+            if (!ids) return VOR_OK;
+            if (cap < (size_t)run) { g_err = "footprint buffer too small"; return VOR_ERR_ARG; }
+            for (size_t i = 0; i < n; i++) std::copy(fp.begin() + i * (size_t)fcap, fp.begin() + i * (size_t)fcap + cnt[i], ids + offsets[i]);
+            return VOR_OK;
+        });
+    });
+}
+
+vor_status vor_find_placement(const int64_t *offsets, const int32_t *ids, size_t n, uint64_t *placement, int device) {
+    return guarded([&]() -> vor_status {
+        if (!offsets || !placement || (!ids && n && offsets[n] > 0)) { g_err = "null argument"; return VOR_ERR_ARG; }
+        if (n == 0) return VOR_OK;
+        vor::be::set_device(device);
+        const long long total = offsets[n];
+        int maxid = -1;
+        for (long long x = 0; x < total; x++) {
+            if (ids[x] < 0) { g_err = "negative simplex id in the queue"; return VOR_ERR_ARG; }
+            maxid = std::max(maxid, ids[x]);
+        }
+        for (size_t i = 0; i < n; i++)
+            if (offsets[i + 1] <= offsets[i]) { g_err = "empty footprint (the reference panics: scheduler.rs:52)"; return VOR_ERR_NO_CONFLICT; }
+        vor::be::Stream s = 0;
+        long long *d_off = (long long *)vor::be::dmalloc(sizeof(long long) * (n + 1));
+        int *d_ids = (int *)vor::be::dmalloc(sizeof(int) * (size_t)std::max(total, 1LL));
+        int *d_last = (int *)vor::be::dmalloc(sizeof(int) * (size_t)(maxid + 2));
+        unsigned long long *d_round = (unsigned long long *)vor::be::dmalloc(sizeof(unsigned long long) * n);
+        static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
+        vor::be::h2d(d_off, offsets, sizeof(long long) * (n + 1), s);
+        vor::be::h2d(d_ids, ids, sizeof(int) * (size_t)total, s);
+        vor::be::dmemset(d_last, 0, sizeof(int) * (size_t)(maxid + 2), s);
+        vor::PlacementArgs pa{d_off, d_ids, (int)n, d_last, d_round};
+        VOR_LAUNCH(vor::PlacementArgs, vor::placement_body, 1, pa, s);
+        vor::be::d2h(placement, d_round, sizeof(unsigned long long) * n, s);
+        vor::be::sync(s);
+        vor::be::dfree(d_off); vor::be::dfree(d_ids); vor::be::dfree(d_last); vor::be::dfree(d_round);
+        return VOR_OK;
+    });
+}
+
 vor_status vor_tree_check_delaunay(vor_tree *t, int *ok, int32_t *fail_counts) {
     return guarded([&]() -> vor_status {
         if (!t) { g_err = "null tree"; return VOR_ERR_ARG; }

@@ -863,6 +863,32 @@ template <int D> class Engine {
         be::d2h(h_counts, dcount.p, sizeof(int) * (size_t)nq, stream);
         be::sync(stream);
     }
+    // make_queue (scheduler.rs:6-28): footprints of nq host query points as sorted unique export indices, padded to
+    // `fcap` per query.  counts[i] = size, -1 = conflict region or footprint does not fit, -2 = outside.
+    void make_queue(const double *h_q, int nq, int kcap, int fcap, int *h_fp, int *h_counts) {
+        const int nt = hcnt->ntets;
+        DevTmp<double> dq((size_t)nq * D);
+        DevTmp<int> dseed((size_t)nq), dk((size_t)nq * kcap), dkc((size_t)nq), dfp((size_t)nq * fcap), dfc((size_t)nq), liveId((size_t)nt),
+            compactOf((size_t)nt);
+        be::h2d(dq.p, h_q, sizeof(double) * (size_t)nq * D, stream);
+        compact_live(liveId.p, compactOf.p);
+        fill_i(dseed.p, nv > nsuper ? -1 : 0, (size_t)nq);
+        if (nv > nsuper) {
+            QuerySeedArgs<D> qs{keysAll, mesh.pts, mesh.ptTet, dq.p, d_boxLo, d_boxHi, dseed.p, nsuper, refLo, refHi, axisBits};
+            VOR_LAUNCH(QuerySeedArgs<D>, query_seed_body<D>, nq, qs, stream);
+        }
+        LocateQueryArgs<D> la{mesh, dq.p, dseed.p, nullptr, dk.p, dkc.p, kcap};
+        VOR_LAUNCH(LocateQueryArgs<D>, locate_query_body<D>, nq, la, stream);
+        FootprintArgs<D> fa{mesh, dk.p, dkc.p, compactOf.p, dfp.p, dfc.p, kcap, fcap};
+        VOR_LAUNCH(FootprintArgs<D>, footprint_body<D>, nq, fa, stream);
+        std::vector<int> kc((size_t)nq);
+        be::d2h(h_fp, dfp.p, sizeof(int) * (size_t)nq * fcap, stream);
+        be::d2h(h_counts, dfc.p, sizeof(int) * (size_t)nq, stream);
+        be::d2h(kc.data(), dkc.p, sizeof(int) * (size_t)nq, stream);
+        be::sync(stream);
+        for (int i = 0; i < nq; i++)
+            if (kc[i] == -2) h_counts[i] = -2;
+    }
     template <class T> struct DevTmp {
         T *p;
         explicit DevTmp(size_t n) : p((T *)be::dmalloc(sizeof(T) * (n ? n : 1))) {}

@@ -300,8 +300,69 @@ template <int D> VOR_HD void locate_query_body(const LocateQueryArgs<D> &A, int 
             }
         }
     }
-    for (int j = 0; j < nk; j++) res[j] = A.compactOf[res[j]];
+    if (A.compactOf)
+        for (int j = 0; j < nk; j++) res[j] = A.compactOf[res[j]];
     A.count[qi] = nk;
+}
+
+// ---- scheduler (reference API: scheduler::{make_queue, find_placement}, /root/reference/src/scheduler.rs:6-55).
+// The device path does not schedule with these (it reserves simplices with atomicMin, kernels.cuh); they exist so that
+// callers of the reference's scheduler find the same functions, computed on the device from the same store.
+// make_queue: footprint of a query = sorted unique neighbours-of-neighbours of its conflict region (scheduler.rs:14-24).
+// The reference's ghost simplices (outside the super simplex) do not exist in this store: a hull facet contributes
+// nothing, so footprints differ from the reference's only for queries whose 2-ring reaches the super simplex's hull.
+template <int D> struct FootprintArgs {
+    Mesh<D> m;
+    const int *killed;      // [nq x kcap] conflict regions as simplex slots (locate_query_body with compactOf == nullptr)
+    const int *kcount;      // per query: region size (<= 0: empty / error)
+    const int *compactOf;   // simplex slot -> export index
+    int *fp;                // [nq x fcap] out: footprint as sorted unique export indices
+    int *fcount;            // per query: footprint size, -1 if it does not fit
+    int kcap, fcap;
+};
+template <int D> VOR_HD void footprint_body(const FootprintArgs<D> &A, int qi) {
+    constexpr int M = Dim<D>::M;
+    const Mesh<D> &m = A.m;
+    const int nk = A.kcount[qi];
+    int *out = A.fp + (size_t)qi * A.fcap;
+    int n = 0;
+    if (nk <= 0) { A.fcount[qi] = nk < 0 ? -1 : 0; return; }
+    // sorted insertion with binary search (footprints hold 100-300 ids)
+    for (int j = 0; j < nk; j++) {
+        const int4 na = TN(m, A.killed[(size_t)qi * A.kcap + j]);
+        for (int ia = 0; ia < M; ia++) {
+            const int ca = get4(na, ia);
+            if (ca < 0) continue;
+            const int4 nb = TN(m, ca >> 2);
+            for (int ib = 0; ib < M; ib++) {
+                const int cb = get4(nb, ib);
+                if (cb < 0) continue;
+                const int id = A.compactOf[cb >> 2];
+                int lo = 0, hi = n;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (out[mid] < id) lo = mid + 1; else hi = mid; }
+                if (lo < n && out[lo] == id) continue;
+                if (n == A.fcap) { A.fcount[qi] = -1; return; }
+                for (int x = n; x > lo; x--) out[x] = out[x - 1];
+                out[lo] = id;
+                n++;
+            }
+        }
+    }
+    A.fcount[qi] = n;
+}
+// find_placement (scheduler.rs:30-55): greedy round of every queue entry in queue order.  round[p] = 1 + the largest
+// round among the previous occupants of p's footprint simplices (0 when p is the first occupant of all of them) --
+// the same recurrence as the reference's occupancy lists, which only ever look at the LAST previous occupant.
+// Inherently sequential in p (the reference's loop is serial too): one thread walks the queue.
+struct PlacementArgs { const long long *off; const int *ids; int nq; int *last; unsigned long long *round; };
+VOR_HD void placement_body(const PlacementArgs &A, int) {
+    for (int p = 0; p < A.nq; p++) {
+        int best = 0;
+        for (long long x = A.off[p]; x < A.off[p + 1]; x++) { const int l = A.last[A.ids[x]]; best = l > best ? l : best; }
+        best += 1;
+        for (long long x = A.off[p]; x < A.off[p + 1]; x++) A.last[A.ids[x]] = best;
+        A.round[p] = (unsigned long long)best;
+    }
 }
 
 // ---- batched geometry entry points (reference API: geometry::{circumsphere, in_sphere})
