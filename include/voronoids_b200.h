@@ -105,6 +105,14 @@ vor_status vor_tree_export_simplices(vor_tree *t, int32_t *vertices, int32_t *ne
  * coincides with a vertex (the reference panics, delaunay_tree.rs:47-54); -1 = more than cap simplices. */
 vor_status vor_tree_locate(vor_tree *t, const double *points, size_t n, int32_t *out_ids, size_t cap, int32_t *counts);
 
+/* vertices in reference id order -- 0..dim super vertices, dim+1..2dim+1 their ghost copies (delaunay_tree.rs:407-412),
+ * then input point i at 2(dim+1) + i -- coords [n_vertices x dim] and the incident live simplices of each vertex
+ * (Vertex.simplex, delaunay_tree.rs:20-24) as CSR: simp_off [n_vertices + 1], simps [n_incidences] indices into
+ * vor_tree_export_simplices, each row sorted (the reference's lists are unordered).  Any array may be NULL (two-phase
+ * size query).  Replaces the PyDelauanyTree.vertices getter (lib.rs:73-85). */
+vor_status vor_tree_export_vertices(vor_tree *t, double *coords, int64_t *simp_off, int32_t *simps, size_t cap, size_t *n_vertices,
+                                    size_t *n_incidences);
+
 /* scheduler::make_queue (src/scheduler.rs:6-28): footprint of every query point against the current tree = sorted
  * unique neighbours-of-neighbours of its conflict region, as indices into vor_tree_export_simplices.  CSR output:
  * offsets[n+1], ids[offsets[n]].  ids == NULL: only offsets and *total are written.  The reference's ghost simplices do

@@ -160,3 +160,26 @@ def case_scheduler(lib, O, dim, n=3000, nq=500):
             assert e.status == 1
     finally:
         t.close()
+
+
+def case_export_vertices(lib, dim, n=2000):
+    """vor_tree_export_vertices: reference id order, coordinates, Vertex.simplex as sorted CSR of export indices."""
+    pts = pointgen.uniform(n, dim, 7)
+    t = _capi.Tree(lib, pts)
+    try:
+        m = dim + 1
+        coords, off, simps = t.vertices()
+        v, _ = t.simplices()
+        sv = t.super_simplex()[0]
+        ghost_of = {3: [0, 0, 0, 1], 2: [0, 1, 2]}[dim]
+        assert coords.shape == (2 * m + n, dim) and np.array_equal(coords[2 * m:], pts)
+        assert np.array_equal(coords[:m], sv) and np.array_equal(coords[m:2 * m], sv[ghost_of])
+        assert off[0] == 0 and off[-1] == len(simps) == len(v) * m
+        inc = {}
+        for i, row in enumerate(v.tolist()):
+            for q in row:
+                inc.setdefault(q, []).append(i)
+        for q in range(len(coords)):
+            assert simps[off[q]:off[q + 1]].tolist() == sorted(inc.get(q, []))
+    finally:
+        t.close()

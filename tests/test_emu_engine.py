@@ -45,6 +45,11 @@ def test_emu_scheduler_matches_reference_restatement(emu_lib, oracle, dim):
     ec.case_scheduler(emu_lib, oracle, dim, n=1500, nq=300)
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_emu_export_vertices(emu_lib, dim):
+    ec.case_export_vertices(emu_lib, dim, n=1200)
+
+
 def test_emu_overflow_scratch_and_compaction(emu_lib, oracle):
     # tiny regular slots force the overflow path; a small attempt budget forces many rounds + list compaction
     emu_lib.vor_set_option(b"capk", 8.0)

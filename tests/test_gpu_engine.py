@@ -234,3 +234,8 @@ def test_gpu_python_scheduler_module(gpu_lib, oracle):
     placement = vb.scheduler.find_placement(queue)
     ref = oracle.RefDelaunay(pts[:1000], mode="split", n_seq=1000).placement(pts[1000:])
     assert placement == [int(x) for x in ref]
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_gpu_export_vertices(gpu_lib, dim):
+    ec.case_export_vertices(gpu_lib, dim, n=20_000)

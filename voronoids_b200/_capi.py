@@ -33,6 +33,7 @@ SYMBOLS = {
     "vor_tree_edges_device": (C.c_int, [tree_p, C.POINTER(C.c_void_p), szp, u64p]),
     "vor_tree_export_simplices": (C.c_int, [tree_p, i32p, i32p, dp, dp, C.c_size_t, szp]),
     "vor_tree_locate": (C.c_int, [tree_p, dp, C.c_size_t, i32p, C.c_size_t, i32p]),
+    "vor_tree_export_vertices": (C.c_int, [tree_p, dp, i64p, i32p, C.c_size_t, szp, szp]),
     "vor_make_queue": (C.c_int, [tree_p, dp, C.c_size_t, i64p, i32p, C.c_size_t, szp]),
     "vor_find_placement": (C.c_int, [i64p, i32p, C.c_size_t, u64p, C.c_int]),
     "vor_tree_check_delaunay": (C.c_int, [tree_p, C.POINTER(C.c_int), i32p]),
@@ -192,6 +193,17 @@ class Tree:
         if (cnt < 0).any():
             return self.locate(points, cap * 4)
         return [np.sort(out[i, :cnt[i]]) for i in range(q.shape[0])]
+
+    def vertices(self):
+        """(coords [n, dim], simp_off int64 [n + 1], simps int32): reference-ordered vertices and their incident simplices."""
+        nv, ni = C.c_size_t(), C.c_size_t()
+        self._check(self._lib.vor_tree_export_vertices(self._h, None, None, None, 0, C.byref(nv), C.byref(ni)))
+        coords = np.zeros((nv.value, self.dim))
+        off = np.zeros(nv.value + 1, dtype=np.int64)
+        simps = np.zeros(max(ni.value, 1), dtype=np.int32)
+        self._check(self._lib.vor_tree_export_vertices(self._h, coords.ctypes.data_as(dp), off.ctypes.data_as(i64p), simps.ctypes.data_as(i32p),
+                                                       simps.size, C.byref(nv), C.byref(ni)))
+        return coords, off, simps[:ni.value]
 
     def make_queue(self, points):
         """scheduler::make_queue: CSR (offsets int64 [n+1], ids int32) of the footprints, export indices."""

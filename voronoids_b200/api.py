@@ -163,14 +163,13 @@ class DelaunayTree:
     @property
     def vertices(self):
         m = self.dim + 1
-        v, _, _, _ = self.simplex_arrays()
         sv = self._t.super_simplex()[0]
         n_real = self._t.counts()["vertices"] - 2 * m
-        inc = {}
         first = m + 1
-        for i, row in enumerate(v.tolist()):
-            for q in row:
-                inc.setdefault(q, []).append(first + i)
+        # Vertex.simplex from the device (vor_tree_export_vertices): CSR of export indices per reference vertex id
+        _, off, simps = self._t.vertices()
+        ids = (simps.astype(np.int64) + first).tolist()
+        inc = {q: ids[off[q]:off[q + 1]] for q in range(len(off) - 1) if off[q + 1] > off[q]}
         ghosts = _GHOSTS[self.dim]
         for gid, g in ghosts.items():
             for q in g:

@@ -288,6 +288,22 @@ vor_status vor_tree_locate(vor_tree *t, const double *points, size_t n, int32_t 
     });
 }
 
+vor_status vor_tree_export_vertices(vor_tree *t, double *coords, int64_t *simp_off, int32_t *simps, size_t cap, size_t *n_vertices,
+                                    size_t *n_incidences) {
+    return guarded([&]() -> vor_status {
+        if (!t) { g_err = "null tree"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        return t->visit([&](auto &e) -> vor_status {
+            long long ninc = 0;
+            static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
+            const long long n = e.export_vertices(coords, (long long *)simp_off, simps, (long long)cap, &ninc);
+            if (n_vertices) *n_vertices = (size_t)n;
+            if (n_incidences) *n_incidences = (size_t)ninc;
+            return VOR_OK;
+        });
+    });
+}
+
 vor_status vor_make_queue(vor_tree *t, const double *points, size_t n, int64_t *offsets, int32_t *ids, size_t cap, size_t *total) {
     return guarded([&]() -> vor_status {
         if (!t || (!points && n) || !offsets) { g_err = "null argument"; return VOR_ERR_ARG; }

@@ -863,6 +863,60 @@ template <int D> class Engine {
         be::d2h(h_counts, dcount.p, sizeof(int) * (size_t)nq, stream);
         be::sync(stream);
     }
+    // vertices in reference id order (super k -> k, ghost copies, input i -> 2*M*nsets + i) with their incident live
+    // simplices as CSR of export indices.  Returns the number of vertex ids; *n_inc = number of incidences.
+    // Any output pointer may be null.
+    long long export_vertices(double *h_coords, long long *h_off, int *h_simps, long long cap, long long *n_inc) {
+        const int nt = hcnt->ntets;
+        const int idOffset = 2 * M * nsets;
+        const long long nIds = (long long)idOffset + ninput;
+        DevTmp<int> liveId((size_t)nt), compactOf((size_t)nt), deg((size_t)nIds + 1), cursor((size_t)nIds + 1);
+        const int nlive = compact_live(liveId.p, compactOf.p);
+        be::dmemset(deg.p, 0, sizeof(int) * (size_t)(nIds + 1), stream);
+        be::dmemset(cursor.p, 0, sizeof(int) * (size_t)(nIds + 1), stream);
+        IncidArgs<D> ia{mesh, liveId.p, inputIdx, deg.p, cursor.p, nullptr, idOffset, 0};
+        VOR_LAUNCH(IncidArgs<D>, incid_body<D>, nlive, ia, stream);
+        const long long total = scan_exclusive(deg.p, (int)nIds + 1);
+        if (n_inc) *n_inc = total;
+        if (h_off) {
+            std::vector<int> off((size_t)nIds + 1);
+            be::d2h(off.data(), deg.p, sizeof(int) * (size_t)(nIds + 1), stream);
+            be::sync(stream);
+            for (long long i = 0; i <= nIds; i++) h_off[i] = off[(size_t)i];
+        }
+        if (h_simps) {
+            if (cap < total) fail(ERR_ARG, "incidence buffer too small");
+            DevTmp<int> simps((size_t)std::max(total, 1LL));
+            ia.simps = simps.p;
+            ia.pass = 1;
+            VOR_LAUNCH(IncidArgs<D>, incid_body<D>, nlive, ia, stream);
+            RowSortPlainArgs ra{deg.p, simps.p};
+            VOR_LAUNCH(RowSortPlainArgs, row_sort_plain_body, (int)nIds, ra, stream);
+            be::d2h(h_simps, simps.p, sizeof(int) * (size_t)total, stream);
+            be::sync(stream);
+        }
+        if (h_coords) {
+            DevTmp<double> dc((size_t)nIds * D);
+            be::dmemset(dc.p, 0, sizeof(double) * (size_t)nIds * D, stream);
+            CoordArgs<D> ca{mesh.pts, inputIdx, dc.p, nsuper, idOffset};
+            VOR_LAUNCH(CoordArgs<D>, coord_body<D>, nv - nsuper, ca, stream);
+            be::d2h(h_coords, dc.p, sizeof(double) * (size_t)nIds * D, stream);
+            be::sync(stream);
+            // super vertices, then their ghost copies (delaunay_tree.rs:407-412 / :559-566)
+            static const int ghostOf3[4] = {0, 0, 0, 1}, ghostOf2[3] = {0, 1, 2};
+            for (int s = 0; s < nsets; s++)
+                for (int k = 0; k < M; k++) {
+                    const double *sv = &superXYZ[((size_t)s * M + k) * D];
+                    const int g = D == 3 ? ghostOf3[k] : ghostOf2[k];
+                    const double *gv = &superXYZ[((size_t)s * M + g) * D];
+                    for (int d = 0; d < D; d++) {
+                        h_coords[((size_t)s * M + k) * D + d] = sv[d];
+                        h_coords[((size_t)(nsets + s) * M + k) * D + d] = gv[d];
+                    }
+                }
+        }
+        return nIds;
+    }
     // make_queue (scheduler.rs:6-28): footprints of nq host query points as sorted unique export indices, padded to
     // `fcap` per query.  counts[i] = size, -1 = conflict region or footprint does not fit, -2 = outside.
     void make_queue(const double *h_q, int nq, int kcap, int fcap, int *h_fp, int *h_counts) {

@@ -365,6 +365,48 @@ VOR_HD void placement_body(const PlacementArgs &A, int) {
     }
 }
 
+// ---- export of vertices: coordinates in reference id order + incident live simplices (Vertex.simplex,
+// delaunay_tree.rs:20-24) as CSR of export indices.  Ids: super vertex k -> k, input point i -> idOffset + i (the
+// same ids export_fill_body writes into `verts`).  Two passes like the edge list: count, scan (host), fill; rows sorted.
+template <int D> struct IncidArgs {
+    Mesh<D> m;
+    const int *liveId;
+    const int *inputIdx;
+    int *deg;        // [nIds + 1] counts, then exclusive offsets
+    int *cursor;     // [nIds]
+    int *simps;      // CSR column array (export indices)
+    int idOffset;
+    int pass;
+};
+template <int D> VOR_HD void incid_body(const IncidArgs<D> &A, int c) {
+    constexpr int M = Dim<D>::M;
+    const int4 tv = TV(A.m, A.liveId[c]);
+    for (int k = 0; k < M; k++) {
+        const int v = get4(tv, k);
+        const int id = v < A.m.nsuper ? v : A.idOffset + A.inputIdx[v];
+        if (A.pass == 0) atomic_add_i(&A.deg[id], 1);
+        else A.simps[(size_t)A.deg[id] + atomic_add_i(&A.cursor[id], 1)] = c;
+    }
+}
+struct RowSortPlainArgs { const int *off; int *val; };
+VOR_HD void row_sort_plain_body(const RowSortPlainArgs &A, int r) {
+    const int lo = A.off[r], hi = A.off[r + 1];
+    for (int i = lo + 1; i < hi; i++) {
+        const int x = A.val[i];
+        int j = i - 1;
+        while (j >= lo && A.val[j] > x) { A.val[j + 1] = A.val[j]; j--; }
+        A.val[j + 1] = x;
+    }
+}
+template <int D> struct CoordArgs { const typename Dim<D>::Pt *pts; const int *inputIdx; double *out; int nsuper; int idOffset; };
+VOR_HD void put_coords(double *o, const double4 &p) { o[0] = p.x; o[1] = p.y; o[2] = p.z; }
+VOR_HD void put_coords(double *o, const double2 &p) { o[0] = p.x; o[1] = p.y; }
+template <int D> VOR_HD void coord_body(const CoordArgs<D> &A, int j) {   // j-th real vertex (insertion order) -> row idOffset + input index
+    const int v = A.nsuper + j;
+    const int i = A.inputIdx[v];
+    if (i >= 0) put_coords(A.out + (size_t)(A.idOffset + i) * D, A.pts[v]);
+}
+
 // ---- batched geometry entry points (reference API: geometry::{circumsphere, in_sphere})
 template <int D> struct CircumBatchArgs { const double *verts; double *center; double *radius; };
 VOR_HD void circum_batch_body(const CircumBatchArgs<3> &A, int i) {
