@@ -60,6 +60,11 @@ vor_status vor_tree_create(int dim, const double *points, size_t n, int device, 
 vor_status vor_tree_create_device(int dim, const double *d_points, size_t n, int device, void *cuda_stream, vor_tree **out);
 /* batch of independent point sets in one store (BASELINE.json config 5): set s = points[set_offsets[s] .. set_offsets[s+1]) */
 vor_status vor_tree_create_batch(int dim, const double *points, const int64_t *set_offsets, size_t n_sets, int device, vor_tree **out);
+/* the same across several devices of one node: contiguous blocks of ceil(n_sets / n_dev) sets per
+ * device, one host thread per device, no exchange; trees[d] is a batch tree holding sets [shard[d], shard[d+1]) (NULL when
+ * the block is empty); shard has n_dev + 1 entries.  A device may be listed more than once. */
+vor_status vor_delaunay_batch(int dim, const double *points, const int64_t *set_offsets, size_t n_sets, const int *devices, size_t n_dev,
+                              vor_tree **trees, int64_t *shard);
 vor_status vor_tree_create_batch_device(int dim, const double *d_points, const int64_t *set_offsets, size_t n_sets, int device,
                                         void *cuda_stream, vor_tree **out);
 void vor_tree_destroy(vor_tree *t);

@@ -183,3 +183,29 @@ def case_export_vertices(lib, dim, n=2000):
             assert simps[off[q]:off[q + 1]].tolist() == sorted(inc.get(q, []))
     finally:
         t.close()
+
+
+def case_batch_devices(lib, O, dim, devices, sizes=(1500, 300, 2000, 2, 777, 1200, 64)):
+    """vor_delaunay_batch (E1): every set's edge list equals the oracle's whichever device block it landed in."""
+    sets = [pointgen.uniform(n, dim, 1000 + s) for s, n in enumerate(sizes)]
+    off = np.concatenate([[0], np.cumsum([len(x) for x in sets])]).astype(np.int64)
+    trees, shard = _capi.delaunay_batch_devices(lib, np.concatenate(sets, axis=0), off, devices)
+    try:
+        per = -(-len(sets) // len(devices))
+        assert shard.tolist() == [min(len(sets), d * per) for d in range(len(devices) + 1)]
+        for d, t in enumerate(trees):
+            lo, hi = int(shard[d]), int(shard[d + 1])
+            if hi == lo:
+                assert t is None
+                continue
+            e = t.edges()
+            base = off[lo]
+            for s in range(lo, hi):
+                a, b = off[s] - base, off[s + 1] - base
+                i0, i1 = np.searchsorted(e[:, 0], a, side="left"), np.searchsorted(e[:, 0], b, side="left")
+                got = (e[i0:i1] - np.uint32(a)).astype(np.uint32)
+                assert np.array_equal(got, O.ExactDelaunay(sets[s]).edges()), (d, s)
+    finally:
+        for t in trees:
+            if t is not None:
+                t.close()

@@ -50,6 +50,11 @@ def test_emu_export_vertices(emu_lib, dim):
     ec.case_export_vertices(emu_lib, dim, n=1200)
 
 
+@pytest.mark.parametrize("devices", [[0], [0, 0], [0, 0, 0, 0, 0, 0, 0, 0, 0]])
+def test_emu_batch_over_devices(emu_lib, oracle, devices):
+    ec.case_batch_devices(emu_lib, oracle, 3, devices)
+
+
 def test_emu_overflow_scratch_and_compaction(emu_lib, oracle):
     # tiny regular slots force the overflow path; a small attempt budget forces many rounds + list compaction
     emu_lib.vor_set_option(b"capk", 8.0)

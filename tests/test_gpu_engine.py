@@ -239,3 +239,10 @@ def test_gpu_python_scheduler_module(gpu_lib, oracle):
 @pytest.mark.parametrize("dim", [2, 3])
 def test_gpu_export_vertices(gpu_lib, dim):
     ec.case_export_vertices(gpu_lib, dim, n=20_000)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_gpu_batch_over_devices(gpu_lib, oracle, dim):
+    """vor_delaunay_batch with every visible device (and device 0 listed twice: two host threads on one GPU)"""
+    import torch
+    ec.case_batch_devices(gpu_lib, oracle, dim, list(range(torch.cuda.device_count())) + [0])

@@ -19,6 +19,7 @@ SYMBOLS = {
     "vor_tree_create": (C.c_int, [C.c_int, dp, C.c_size_t, C.c_int, C.POINTER(tree_p)]),
     "vor_tree_create_device": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(tree_p)]),
     "vor_tree_create_batch": (C.c_int, [C.c_int, dp, i64p, C.c_size_t, C.c_int, C.POINTER(tree_p)]),
+    "vor_delaunay_batch": (C.c_int, [C.c_int, dp, i64p, C.c_size_t, C.POINTER(C.c_int), C.c_size_t, C.POINTER(tree_p), i64p]),
     "vor_tree_create_batch_device": (C.c_int, [C.c_int, C.c_void_p, i64p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(tree_p)]),
     "vor_tree_destroy": (None, [tree_p]),
     "vor_tree_insert": (C.c_int, [tree_p, dp, C.c_size_t, C.c_int]),
@@ -53,6 +54,30 @@ SYMBOLS = {
 N_STATS = 16
 STAT_NAMES = ("rounds", "attempts", "winners", "owner_resets", "compactions", "stages", "walk_steps", "tests", "killed", "created",
               "exact_calls", "exact_zero", "duplicates", "simplex_slots", "aborted", "tests_completed")
+
+
+def delaunay_batch_devices(lib, points, set_offsets, devices):
+    """vor_delaunay_batch: the sets in contiguous blocks over `devices` (one host thread each).  Returns (trees, shard):
+    trees[d] is a Tree holding sets [shard[d], shard[d+1]) or None when its block is empty."""
+    p, pp = as_f64(points)
+    off = np.ascontiguousarray(set_offsets, dtype=np.int64)
+    dev = (C.c_int * len(devices))(*devices)
+    hs = (tree_p * len(devices))()
+    shard = np.zeros(len(devices) + 1, dtype=np.int64)
+    st = lib.vor_delaunay_batch(p.shape[1], pp, off.ctypes.data_as(i64p), len(off) - 1, dev, len(devices), hs, shard.ctypes.data_as(i64p))
+    if st != 0:
+        raise VorError(st, lib.vor_last_error().decode())
+    trees = []
+    for d in range(len(devices)):
+        if not hs[d]:
+            trees.append(None)
+            continue
+        t = Tree.__new__(Tree)
+        t._lib, t._h, t.duplicates, t.dim = lib, tree_p(hs[d]), False, p.shape[1]
+        t.n = int(off[shard[d + 1]] - off[shard[d]])
+        t._off = off[shard[d]:shard[d + 1] + 1] - off[shard[d]]
+        trees.append(t)
+    return trees, shard
 
 
 def find_placement(lib, offsets, ids, device=0):

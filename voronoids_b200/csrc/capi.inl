@@ -3,6 +3,7 @@
 #include <memory>
 #include <mutex>
 #include <new>
+#include <thread>
 
 #include "../../include/voronoids_b200.h"
 
@@ -129,6 +130,42 @@ vor_status vor_tree_create_batch(int dim, const double *points, const int64_t *s
         vor::be::h2d_big(d.p, points, sizeof(double) * n * dim, vor::be::Stream{});
         return vor_tree_create_batch_device(dim, (const double *)d.p, set_offsets, n_sets, device, nullptr, out);
     });
+}
+
+// E1 of SURVEY.md §8(e): sets are independent units.  Contiguous blocks of ceil(n_sets / n_dev) sets per device, one
+// host thread per device (create + insert of that block as ONE batch tree), no exchange between devices.
+vor_status vor_delaunay_batch(int dim, const double *points, const int64_t *set_offsets, size_t n_sets, const int *devices, size_t n_dev,
+                              vor_tree **trees, int64_t *shard) {
+    if (!points || !set_offsets || !devices || !trees || !shard || n_sets < 1 || n_dev < 1 || (dim != 2 && dim != 3)) {
+        g_err = "bad argument";
+        return VOR_ERR_ARG;
+    }
+    const size_t per = (n_sets + n_dev - 1) / n_dev;
+    for (size_t d = 0; d <= n_dev; d++) shard[d] = (int64_t)std::min(n_sets, d * per);
+    std::vector<vor_status> st(n_dev, VOR_OK);
+    std::vector<std::string> msg(n_dev);
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < n_dev; d++) {
+        trees[d] = nullptr;
+        th.emplace_back([&, d]() {
+            const size_t lo = (size_t)shard[d], hi = (size_t)shard[d + 1];
+            if (hi <= lo) return;   // more devices than sets: nothing for this one
+            std::vector<int64_t> off(hi - lo + 1);
+            for (size_t s = lo; s <= hi; s++) off[s - lo] = set_offsets[s] - set_offsets[lo];
+            const double *p = points + (size_t)set_offsets[lo] * dim;
+            vor_status r = vor_tree_create_batch(dim, p, off.data(), hi - lo, devices[d], &trees[d]);
+            if (r == VOR_OK) r = vor_tree_insert_batch(trees[d], p, off.data());
+            if (r != VOR_OK && r != VOR_ERR_DUPLICATE_POINT) { st[d] = r; msg[d] = vor_last_error(); }   // g_err is thread-local
+        });
+    }
+    for (auto &t : th) t.join();
+    for (size_t d = 0; d < n_dev; d++)
+        if (st[d] != VOR_OK) {
+            g_err = "device " + std::to_string(devices[d]) + ": " + msg[d];
+            for (size_t k = 0; k < n_dev; k++) { vor_tree_destroy(trees[k]); trees[k] = nullptr; }
+            return st[d];
+        }
+    return VOR_OK;
 }
 
 vor_status vor_tree_create(int dim, const double *points, size_t n, int device, vor_tree **out) {
