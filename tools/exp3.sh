@@ -2,7 +2,7 @@
 # scratch A/B timing of library variants on the GPU box (not part of the product)
 cd "$(dirname "$0")/.."
 O=gpurun_out/exp3.log; : > $O
-run() { echo "## $*" >> $O; env T_PROFILE=1 "$@" python t_stage.py ${N:-10000000} ${DIM:-3} 2>&1 | grep -E "RESULT|PROFILE|Error|error|assert" >> $O; }
+run() { echo "## $*" >> $O; env T_PROFILE=1 "$@" python tools/t_stage.py ${N:-10000000} ${DIM:-3} 2>&1 | grep -E "RESULT|PROFILE|Error|error|assert" >> $O; }
 for v in variants/*.so; do
   run VOR_SO=$PWD/$v VOR_RED=1
 done

@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 O=gpurun_out/exp5.log; : > $O
-run() { echo "## $*" >> $O; env T_PROFILE=1 "$@" python t_stage.py ${N:-10000000} ${DIM:-3} 2>&1 | grep -E "RESULT|PROFILE|Error|error|assert|rror" >> $O; }
+run() { echo "## $*" >> $O; env T_PROFILE=1 "$@" python tools/t_stage.py ${N:-10000000} ${DIM:-3} 2>&1 | grep -E "RESULT|PROFILE|Error|error|assert|rror" >> $O; }
 run VOR_RED=1
 run VOR_RED=1 VOR_RECYCLE=1
 run VOR_RED=1 VOR_COMMIT_SMEM=0

@@ -1,6 +1,6 @@
 """Scratch timing helper (not part of the product): python t_stage.py N DIM [stats] -- insert time per iteration, engine options from VOR_* env."""
 import ctypes as C, numpy as np, time, torch, sys, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from voronoids_b200 import _capi, _lib, pointgen
 lib = _lib.lib()
 n = int(sys.argv[1]); dim = int(sys.argv[2]) if len(sys.argv) > 2 else 3
