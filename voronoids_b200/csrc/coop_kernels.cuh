@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(128) k_walk_coop(AttemptArgs<D> A, RoundSel rs
 // RED = 1: the kill reservation is a fire-and-forget reduction too (no round trip on the critical path of a flood
 // level): lanes of one batch that reach the same simplex are deduplicated with match.any, and a better killer that
 // slips in between the owner read and the reduction is caught by the ownership check of commit.
-template <int D, int G, int RED>
+template <int D, int G, int RED, int STAGE>
 __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const RoundSel &rsel, const int gid, int *const sk, int4 *const sn) {
     constexpr int M = Dim<D>::M;
     using Gm = Geo<D>;
@@ -214,7 +214,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
     }
     if (!fail) {
         ScrView sv = scr_view(A.scr, slot, -1);
-        if (gl == 0) { sv.k[0] = s; if (VOR_ATT_STAGE) { sk[0] = s; sn[0] = stn; } }
+        if (gl == 0) { sv.k[0] = s; if (STAGE) { sk[0] = s; sn[0] = stn; } }
         __syncwarp(gmask);
         nk = 1;
         int head = 0;
@@ -238,7 +238,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
                 if (active) {
                     const int e = head + j / M;
                     i = j % M;
-                    if (VOR_ATT_STAGE && e < SK) { t = sk[e]; code = reinterpret_cast<const int *>(sn)[e * 4 + i]; }
+                    if (STAGE && e < SK) { t = sk[e]; code = reinterpret_cast<const int *>(sn)[e * 4 + i]; }
                     else { t = sv.k[e]; code = TNI(m, t, i); }
                     if (code >= 0) n = code >> 2;
                     else { pushB = true; fcode = t * 4 + i; ocode = code; }
@@ -252,7 +252,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
                     // the owner pair and the record of n are independent gathers: issue both before looking at either
                     const int2 ow = __ldcg(reinterpret_cast<const int2 *>(&OWK(m, n)));   // x = kill word, y = ring word
                     int4 nverts;
-                    if (VOR_ATT_STAGE) load_rec_cg(m, n, nverts, nnb);   // vertex ids + neighbour codes: one 256-bit gather
+                    if (STAGE) load_rec_cg(m, n, nverts, nnb);   // vertex ids + neighbour codes: one 256-bit gather
                     else nverts = __ldcg(&TV(m, n));
                     if (ow.x == key_k) verdict = V_MINE;            // already in my cavity
                     else if (ow.x < key_k) verdict = V_LOST;        // a better point kills n (or n is dead)
@@ -292,7 +292,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
                     const int e = head + j / M;
                     const int i = j % M;
                     int t, code;
-                    if (VOR_ATT_STAGE && e < SK) { t = sk[e]; code = reinterpret_cast<const int *>(sn)[e * 4 + i]; }
+                    if (STAGE && e < SK) { t = sk[e]; code = reinterpret_cast<const int *>(sn)[e * 4 + i]; }
                     else { t = sv.k[e]; code = TNI(m, t, i); }
                     if (code < 0) {
                         pushB = true; fcode = t * 4 + i; ocode = code;
@@ -301,7 +301,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
                         // the owner pair and the record of n are independent gathers: issue both before looking at either
                         const int2 ow = __ldcg(reinterpret_cast<const int2 *>(&OWK(m, n)));   // x = kill word, y = ring word
                         int4 nverts;
-                        if (VOR_ATT_STAGE) load_rec_cg(m, n, nverts, nnb);   // vertex ids + neighbour codes: one 256-bit gather
+                        if (STAGE) load_rec_cg(m, n, nverts, nnb);   // vertex ids + neighbour codes: one 256-bit gather
                         else nverts = __ldcg(&TV(m, n));
                         if (ow.x == key_k) {
                             // already in my cavity
@@ -358,7 +358,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
                 if (pushK) {
                     const int pos = nk + __popc(mk & lt);
                     sv.k[pos] = newT;
-                    if (VOR_ATT_STAGE && pos < SK) { sk[pos] = newT; sn[pos] = nnb; }
+                    if (STAGE && pos < SK) { sk[pos] = newT; sn[pos] = nnb; }
                 }
                 if (pushB) { const int pos = nb + __popc(mb & lt); sv.f[pos] = fcode; sv.o[pos] = ocode; }
                 nk += ck;
@@ -392,15 +392,15 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
 // queues: SM i works through the i-th contiguous range of the Morton-ordered slots, so the simplices and vertices it
 // gathers in one round come from one compact region of the mesh (and of the store) instead of every 148th block of
 // it; the ranges of SMs that finish early are drained by the others.
-template <int D, int G, int RED>
+template <int D, int G, int RED, int STAGE>
 __global__ void __launch_bounds__(VOR_ATTEMPT_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_ATTEMPT_BLOCK)) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
     // the cavity found so far, staged in shared memory: ids and neighbour codes of the first SK killed simplices, so a
     // flood level starts from two shared-memory reads instead of two dependent L2 round trips (scratch, then record)
-    __shared__ int s_kid[VOR_ATTEMPT_BLOCK / G][VOR_SK];
-    __shared__ int4 s_knb[VOR_ATTEMPT_BLOCK / G][VOR_SK];
+    __shared__ int s_kid[VOR_ATTEMPT_BLOCK / G][STAGE ? VOR_SK : 1];
+    __shared__ int4 s_knb[VOR_ATTEMPT_BLOCK / G][STAGE ? VOR_SK : 1];
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;   // group = attempt slot
     if (gid >= rsel.nsel) return;
-    attempt_one<D, G, RED>(A, rsel, gid, s_kid[threadIdx.x / G], s_knb[threadIdx.x / G]);
+    attempt_one<D, G, RED, STAGE>(A, rsel, gid, s_kid[threadIdx.x / G], s_knb[threadIdx.x / G]);
 }
 
 constexpr int NQUEUE = 148;       // per-SM slot queues of the persistent kernels (one per SM of the B200)
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(VOR_ATTEMPT_BLOCK, 65536 / (VOR_ATTEMPT_REGS *
             if (lane == 0) g = atomicAdd(&qctr[qi], 1);
             g = __shfl_sync(0xffffffffu, g, 0);
             if (g >= size) break;
-            attempt_one<D, 32, RED>(A, rsel, lo + g, s_kid[threadIdx.x / 32], s_knb[threadIdx.x / 32]);
+            attempt_one<D, 32, RED, VOR_ATT_STAGE>(A, rsel, lo + g, s_kid[threadIdx.x / 32], s_knb[threadIdx.x / 32]);
             __syncwarp();
         }
     }

@@ -47,6 +47,7 @@ struct EngineOptions {
     int rounds_per_sync = 8;     // rounds launched back to back between two host read-backs of the counters
     int prewalk = 0;             // walk kernel in front of the attempt kernel: 4 = 4 lanes per point, 1 = thread per point, 0 = off
     int commit_smem = 1;         // commit retriangulates cavities staged in shared memory (0 = through the global store)
+    int stage_below = 0;         // rounds with fewer attempts run the attempt kernel that stages the cavity in shared memory
     int persist = 0;             // rounds of at least this many attempts run the persistent attempt kernel (0 = never)
     int recycle = 0;             // winners write new simplices into the slots of the simplices they kill (commit_smem path)
     int red = 1;                 // kill reservation as a fire-and-forget reduction (match.any dedup), see k_attempt_coop
@@ -73,6 +74,7 @@ inline void options_from_env(EngineOptions &o) {
     if (const char *e = getenv("VOR_COMMIT_SMEM")) o.commit_smem = atoi(e);
     if (const char *e = getenv("VOR_RECYCLE")) o.recycle = atoi(e);
     if (const char *e = getenv("VOR_PERSIST")) o.persist = atoi(e);
+    if (const char *e = getenv("VOR_STAGE_BELOW")) o.stage_below = atoi(e);
     if (const char *e = getenv("VOR_CAPK")) { o.capk = atoi(e); o.capb = 2 * o.capk + 4; }
 }
 
@@ -509,9 +511,15 @@ template <int D> class Engine {
                 if (opt.red) k_attempt_persist<D, 1><<<pgrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel, qctr);
                 else k_attempt_persist<D, 0><<<pgrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel, qctr);
                 launched = true;
-            } else if (opt.red) { k_attempt_coop<D, G, 1><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel); launched = true; }
+            } else if (opt.red) {
+                // small rounds are latency-shaped (L2-resident mesh, a handful of waves): the cavity staged in shared
+                // memory shortens the dependent chain; large rounds are gather-rate bound and run without it
+                if (sel.nsel < opt.stage_below) k_attempt_coop<D, G, 1, 1><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel);
+                else k_attempt_coop<D, G, 1, 0><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel);
+                launched = true;
+            }
         }
-        if (!launched) k_attempt_coop<D, G, 0><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel);
+        if (!launched) k_attempt_coop<D, G, 0, VOR_ATT_STAGE><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel);
         prof.stop(stream);
         prof.start(2, stream);
         k_commit_coop<D, G><<<grid, VOR_COOP_BLOCK, 0, stream>>>(ca, act, sel, (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2) | (opt.recycle ? 0 : 4));
