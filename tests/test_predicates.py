@@ -80,3 +80,18 @@ def test_sign_conventions(oracle, emu_lib):
     assert oracle.orient2d([[0, 0, 1, 0, 0, 1]])[0] == 1
     assert oracle.incircle([[0, 0, 1, 0, 0, 1, 0.5, 0.5]])[0] == 1
     assert oracle.incircle([[0, 0, 1, 0, 0, 1, 1.0, 1.0]])[0] == 0  # on the circle: not in conflict (strict <)
+
+
+@pytest.mark.parametrize("kind", ["orient3d", "incircle", "insphere"])
+def test_engine_double_double_stage_on_jittered_lattice(emu_lib, kind):
+    """dd_stage.cuh (compiled into the emulation build): near-degenerate lattice configurations at three coordinate
+    scales get the exact sign, whether the double-double stage or the integers settle them."""
+    dim, npts = {"orient3d": (3, 4), "incircle": (2, 4), "insphere": (3, 5)}[kind]
+    rng = np.random.default_rng(11)
+    for jit in (1e-9, 1e-13, 1e-16, 0.0):
+        for scale in (1.0, 1e-40, 1e40):
+            base = rng.integers(0, 4, size=(300, npts, dim)).astype(float) / 171.0
+            rows = ((base + jit / 171.0 * rng.uniform(-1, 1, size=base.shape)) * scale).reshape(300, -1)
+            want = np.array([pc.EXACT[kind](r) for r in rows])
+            st, got, _ = emu_pred(emu_lib, kind, rows)
+            assert st == 0 and np.array_equal(got, want), (kind, jit, scale)

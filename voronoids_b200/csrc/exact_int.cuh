@@ -18,6 +18,7 @@
 // oracle/predicates.c); tests pin both against Python fractions.Fraction.
 #pragma once
 #include "vor_common.cuh"
+#include "dd_stage.cuh"
 
 namespace vor {
 
@@ -191,6 +192,7 @@ VOR_HD_NOINLINE int orient2d_exact(const double *a, const double *b, const doubl
 }
 
 VOR_HD_NOINLINE int orient3d_exact(const double *a, const double *b, const double *c, const double *d, int *range_err) {
+    if (VOR_DD) { const int sdd = orient3d_dd(a[0], a[1], a[2], b[0], b[1], b[2], c[0], c[1], c[2], d[0], d[1], d[2]); if (sdd != 0) return sdd; }
     ExpRange rg; range_init(rg);
     for (int k = 0; k < 3; k++) { range_add(rg, a[k]); range_add(rg, b[k]); range_add(rg, c[k]); range_add(rg, d[k]); }
     if (rg.emax < rg.emin) return 0;
@@ -216,6 +218,7 @@ VOR_HD_NOINLINE int orient3d_exact(const double *a, const double *b, const doubl
 }
 
 VOR_HD_NOINLINE int incircle_exact(const double *a, const double *b, const double *c, const double *d, int *range_err) {
+    if (VOR_DD) { const int sdd = incircle_dd(a[0], a[1], b[0], b[1], c[0], c[1], d[0], d[1]); if (sdd != 0) return sdd; }
     ExpRange rg; range_init(rg);
     for (int k = 0; k < 2; k++) { range_add(rg, a[k]); range_add(rg, b[k]); range_add(rg, c[k]); range_add(rg, d[k]); }
     if (rg.emax < rg.emin) return 0;
@@ -263,6 +266,10 @@ VOR_HD void big_comb3(Big<W3> &r, const Big<BIG_CW> &x, const Big<W2> &m1, int s
 }
 
 VOR_HD_NOINLINE int insphere_exact(const double *a, const double *b, const double *c, const double *d, const double *e, int *range_err) {
+    if (VOR_DD) {
+        const int sdd = insphere_dd(a[0], a[1], a[2], b[0], b[1], b[2], c[0], c[1], c[2], d[0], d[1], d[2], e[0], e[1], e[2]);
+        if (sdd != 0) return sdd;
+    }
     ExpRange rg; range_init(rg);
     for (int k = 0; k < 3; k++) { range_add(rg, a[k]); range_add(rg, b[k]); range_add(rg, c[k]); range_add(rg, d[k]); range_add(rg, e[k]); }
     if (rg.emax < rg.emin) return 0;

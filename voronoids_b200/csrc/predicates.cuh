@@ -26,6 +26,8 @@ struct PredCtx {
     Counters *cnt;
 };
 
+// exact_calls counts the predicates that left the FP64 filter, whether the double-double stage inside *_exact
+// (dd_stage.cuh) or the integers settled them; exact_zero counts true zeros.
 VOR_HD int finish_exact(PredCtx &cx, int s, int range_err) {
     atomic_add_ull(&cx.cnt->exact_calls, 1ULL);
     if (range_err) set_err(cx.cnt, ERR_RANGE);
