@@ -36,13 +36,13 @@ __device__ __forceinline__ int slot_entry(const RoundSel &rs, int slot) { return
 template <int D> struct GeoCoop;
 template <> struct GeoCoop<3> {
     // orientation of the simplex with vertex `k` replaced by p (lane k of the group evaluates facet k)
-    static __device__ __forceinline__ int orient_repl(PredCtx &cx, const Geo<3>::Verts &t, const double4 &p, int k) {
+    template <class CX> static __device__ __forceinline__ int orient_repl(CX &cx, const Geo<3>::Verts &t, const double4 &p, int k) {
         const double4 a = k == 0 ? p : t.p0, b = k == 1 ? p : t.p1, c = k == 2 ? p : t.p2, d = k == 3 ? p : t.p3;
         return orient3d(cx, a, b, c, d);
     }
 };
 template <> struct GeoCoop<2> {
-    static __device__ __forceinline__ int orient_repl(PredCtx &cx, const Geo<2>::Verts &t, const double2 &p, int k) {
+    template <class CX> static __device__ __forceinline__ int orient_repl(CX &cx, const Geo<2>::Verts &t, const double2 &p, int k) {
         const double2 a = k == 0 ? p : t.p0, b = k == 1 ? p : t.p1, c = k == 2 ? p : t.p2;
         return orient2d(cx, a, b, c);
     }
@@ -137,7 +137,11 @@ __global__ void __launch_bounds__(128) k_walk_coop(AttemptArgs<D> A, RoundSel rs
 // RED = 1: the kill reservation is a fire-and-forget reduction too (no round trip on the critical path of a flood
 // level): lanes of one batch that reach the same simplex are deduplicated with match.any, and a better killer that
 // slips in between the owner read and the reduction is caught by the ownership check of commit.
-template <int D, int G, int RED, int STAGE>
+// EXACT = 0: the hot twin without the exact predicates in its call tree (PredCtxT<false>): an attempt whose filter fails
+// is abandoned and its point flagged (A.slowFlag[v] = key base of the round); it skips flagged points.  EXACT = 1 with
+// A.thr == 2: the slow twin, launched behind it while flagged points are pending, attempts ONLY points flagged in an
+// EARLIER round (a point flagged in this round has left marks under this round's key).  A.thr == 0: everything.
+template <int D, int G, int RED, int STAGE, int EXACT>
 __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const RoundSel &rsel, const int gid, int *const sk, int4 *const sn) {
     constexpr int M = Dim<D>::M;
     using Gm = Geo<D>;
@@ -152,7 +156,16 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
     if (a >= rsel.nact) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }
     const int v = A.act[a];
     if (m.seed[v] < 0) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }   // already inserted
-    PredCtx cx{m.cnt};
+    if (A.slowFlag) {
+        const int fl = A.slowFlag[v];
+        if (EXACT ? (A.thr == 2u && (fl == 0 || fl == A.keybase)) : fl != 0) {
+            // not this twin's point.  The hot twin runs first and owns the slot's status; the slow twin leaves the
+            // status of the points it skips alone
+            if (!EXACT && gl == 0) A.scr.slotStatus[slot] = ST_LOST;
+            return;
+        }
+    }
+    PredCtxT<(EXACT != 0)> cx{m.cnt};
     const typename Gm::Pt p = m.pts[v];
     const uint32_t q = bij_hash((uint32_t)slot, A.bits, A.salt);   // unique among the slots of this round
     const int key_k = A.keybase | (int)(q << 1);
@@ -174,6 +187,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
     bool fail = false;
     for (;;) {
         const int ok = gl < M ? GeoCoop<D>::orient_repl(cx, tvv, p, gl) : 1;
+        if (!EXACT && __any_sync(gmask, cx.failed)) break;
         const unsigned bal = (__ballot_sync(gmask, ok < 0) >> gshift) & ((1u << M) - 1u);
         if (bal == 0) break;
         int go = 0;
@@ -191,6 +205,8 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
         tvv = Gm::load(m, stv);
     }
 
+    bool needSlow = !EXACT && __any_sync(gmask, cx.failed);
+    if (needSlow) fail = true;
     if (!fail) {
         if (gl == 0) m.seed[v] = s;
         // -- containing simplex must be in conflict, otherwise p duplicates one of its vertices
@@ -198,8 +214,13 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
         if (gl == 0) c0 = Gm::conflict(cx, tvv, p);
         c0 = __shfl_sync(gmask, c0, gshift);
         tests = gl == 0 ? 1u : 0u;
-        if (!c0) {
-            if (gl == 0) { m.seed[v] = -1; atomicAdd(&m.cnt->ndup, 1); }
+        if (!EXACT && __any_sync(gmask, cx.failed)) { needSlow = true; fail = true; }
+        else if (!c0) {
+            if (gl == 0) {
+                m.seed[v] = -1;
+                atomicAdd(&m.cnt->ndup, 1);
+                if (EXACT && A.slowFlag && A.slowFlag[v] != 0) atomicAdd(&m.cnt->nflag_done, 1);   // a flagged point leaves as a duplicate
+            }
             fail = true;
         }
     }
@@ -281,7 +302,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
                     else if (verdict == V_RING) { pushB = true; fcode = t * 4 + i; ocode = code; }
                     else if (verdict == V_NEW && lead) { pushK = true; newT = n; }
                 }
-                if (__any_sync(gmask, lostLane)) { lost = true; break; }
+                if (__any_sync(gmask, lostLane || (!EXACT && cx.failed))) { lost = true; break; }
 #else
                 const int j = base + gl;
                 bool pushK = false, pushB = false, lostLane = false;
@@ -331,7 +352,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
                         }
                     }
                 }
-                if (__any_sync(gmask, lostLane)) { lost = true; break; }
+                if (__any_sync(gmask, lostLane || (!EXACT && cx.failed))) { lost = true; break; }
                 if (RED) {
                     const unsigned same = __match_any_sync(gmask, claim);
                     if (claim >= 0 && (__ffs(same) - 1) == (threadIdx.x & 31)) { pushK = true; newT = claim; }
@@ -369,6 +390,15 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
         }
         if (!lost) status = ST_OK;
     }
+    if (!EXACT) {
+        needSlow = needSlow || __any_sync(gmask, cx.failed);
+        if (needSlow && gl == 0 && A.slowFlag) {
+            // hand the point to the slow twin (from the next round on); marks left under this round's key are stale then
+            A.slowFlag[v] = A.keybase;
+            atomicAdd(&m.cnt->nflag_set, 1);
+            status = ST_LOST;
+        }
+    }
     if (gl == 0) {
         A.scr.slotStatus[slot] = status;
         A.scr.slotNk[slot] = nk;
@@ -392,7 +422,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
 // queues: SM i works through the i-th contiguous range of the Morton-ordered slots, so the simplices and vertices it
 // gathers in one round come from one compact region of the mesh (and of the store) instead of every 148th block of
 // it; the ranges of SMs that finish early are drained by the others.
-template <int D, int G, int RED, int STAGE>
+template <int D, int G, int RED, int STAGE, int EXACT>
 __global__ void __launch_bounds__(VOR_ATTEMPT_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_ATTEMPT_BLOCK)) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
     // the cavity found so far, staged in shared memory: ids and neighbour codes of the first SK killed simplices, so a
     // flood level starts from two shared-memory reads instead of two dependent L2 round trips (scratch, then record)
@@ -400,7 +430,7 @@ __global__ void __launch_bounds__(VOR_ATTEMPT_BLOCK, 65536 / (VOR_ATTEMPT_REGS *
     __shared__ int4 s_knb[VOR_ATTEMPT_BLOCK / G][STAGE ? VOR_SK : 1];
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;   // group = attempt slot
     if (gid >= rsel.nsel) return;
-    attempt_one<D, G, RED, STAGE>(A, rsel, gid, s_kid[threadIdx.x / G], s_knb[threadIdx.x / G]);
+    attempt_one<D, G, RED, STAGE, EXACT>(A, rsel, gid, s_kid[threadIdx.x / G], s_knb[threadIdx.x / G]);
 }
 
 constexpr int NQUEUE = 148;       // per-SM slot queues of the persistent kernels (one per SM of the B200)
@@ -422,7 +452,7 @@ __global__ void __launch_bounds__(VOR_ATTEMPT_BLOCK, 65536 / (VOR_ATTEMPT_REGS *
             if (lane == 0) g = atomicAdd(&qctr[qi], 1);
             g = __shfl_sync(0xffffffffu, g, 0);
             if (g >= size) break;
-            attempt_one<D, 32, RED, VOR_ATT_STAGE>(A, rsel, lo + g, s_kid[threadIdx.x / 32], s_knb[threadIdx.x / 32]);
+            attempt_one<D, 32, RED, VOR_ATT_STAGE, 1>(A, rsel, lo + g, s_kid[threadIdx.x / 32], s_knb[threadIdx.x / 32]);
             __syncwarp();
         }
     }
@@ -666,6 +696,7 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
         m.ptTet[v] = first;
         m.seed[v] = -1;
         atomicAdd(&m.cnt->part[gid & (NPART - 1)][0], (1ULL << 40) | (unsigned long long)nb);   // win_total, created_all
+        if (A.slowFlag && A.slowFlag[v] != 0) atomicAdd(&m.cnt->nflag_done, 1);
         if (stats & 1) {
             atomicAdd(&m.cnt->killed, (unsigned long long)nk);
             atomicAdd(&m.cnt->created, (unsigned long long)nb);

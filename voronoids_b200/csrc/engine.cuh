@@ -47,6 +47,7 @@ struct EngineOptions {
     int rounds_per_sync = 8;     // rounds launched back to back between two host read-backs of the counters
     int prewalk = 0;             // walk kernel in front of the attempt kernel: 4 = 4 lanes per point, 1 = thread per point, 0 = off
     int commit_smem = 1;         // commit retriangulates cavities staged in shared memory (0 = through the global store)
+    int split_exact = 1;         // attempt kernel as a hot twin without exact predicates + an exact twin for the points it flags
     int stage_below = 0;         // rounds with fewer attempts run the attempt kernel that stages the cavity in shared memory
     int persist = 0;             // rounds of at least this many attempts run the persistent attempt kernel (0 = never)
     int recycle = 0;             // winners write new simplices into the slots of the simplices they kill (commit_smem path)
@@ -75,6 +76,7 @@ inline void options_from_env(EngineOptions &o) {
     if (const char *e = getenv("VOR_RECYCLE")) o.recycle = atoi(e);
     if (const char *e = getenv("VOR_PERSIST")) o.persist = atoi(e);
     if (const char *e = getenv("VOR_STAGE_BELOW")) o.stage_below = atoi(e);
+    if (const char *e = getenv("VOR_SPLIT_EXACT")) o.split_exact = atoi(e);
     if (const char *e = getenv("VOR_CAPK")) { o.capk = atoi(e); o.capb = 2 * o.capk + 4; }
 }
 
@@ -109,7 +111,8 @@ template <int D> class Engine {
     Counters *hcnt = nullptr; // pinned host mirror
     // scratch
     Scratch scr{};
-    int *act = nullptr, *act2 = nullptr, *blockCnt = nullptr, *qctr = nullptr;
+    bool slowPending = false, splitDisabled = false;
+    int *act = nullptr, *act2 = nullptr, *blockCnt = nullptr, *qctr = nullptr, *slowFlag = nullptr;
     long long *d_misc = nullptr;
     long long insertedTotal = 0;
     long long remainingInCall = 0;   // points of the current insert call not inserted yet
@@ -136,7 +139,7 @@ template <int D> class Engine {
     ~Engine() {
         be::dfree(mesh.pts); be::dfree(mesh.tet); be::dfree(mesh.owner); be::dfree(mesh.seed);
         be::dfree(mesh.ptTet); be::dfree(mesh.cnt); be::dfree(inputIdx); be::dfree(vidOfInput); be::dfree(keysAll);
-        be::dfree(d_boxLo); be::dfree(d_boxHi); be::dfree(act); be::dfree(act2); be::dfree(blockCnt); be::dfree(d_edges); be::dfree(qctr);
+        be::dfree(d_boxLo); be::dfree(d_boxHi); be::dfree(act); be::dfree(act2); be::dfree(blockCnt); be::dfree(d_edges); be::dfree(qctr); be::dfree(slowFlag);
         free_scratch();
         be::dfree(d_misc);
         be::hfree_pinned(hcnt);
@@ -171,6 +174,14 @@ template <int D> class Engine {
         grow(mesh.ptTet, (size_t)nv, (size_t)nc);
         grow(inputIdx, (size_t)nv, (size_t)nc);
         grow(keysAll, (size_t)std::max(nv - nsuper, 0), (size_t)nc);
+        {   // flags of the exact twin: zero for every vertex that is not flagged (caching allocator: blocks come back dirty)
+            int *q = (int *)be::dmalloc(sizeof(int) * (size_t)nc);
+            be::dmemset(q, 0, sizeof(int) * (size_t)nc, stream);
+            if (slowFlag && nv) be::d2d(q, slowFlag, sizeof(int) * (size_t)nv, stream);
+            be::sync(stream);
+            be::dfree(slowFlag);
+            slowFlag = q;
+        }
         vcap = nc;
     }
     void ensure_inputs(int need) {
@@ -512,14 +523,26 @@ template <int D> class Engine {
                 else k_attempt_persist<D, 0><<<pgrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel, qctr);
                 launched = true;
             } else if (opt.red) {
-                // small rounds are latency-shaped (L2-resident mesh, a handful of waves): the cavity staged in shared
-                // memory shortens the dependent chain; large rounds are gather-rate bound and run without it
-                if (sel.nsel < opt.stage_below) k_attempt_coop<D, G, 1, 1><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel);
-                else k_attempt_coop<D, G, 1, 0><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel);
+                if (sel.nsel < opt.stage_below) k_attempt_coop<D, G, 1, 1, 1><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel);
+                else if (aa.slowFlag) {
+                    // hot twin without the exact predicates in its call tree; while flagged points are pending (host
+                    // knowledge, one read-back old) the exact twin follows and attempts only those
+                    k_attempt_coop<D, G, 1, 0, 0><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel);
+                    if (slowPending) {
+                        AttemptArgs<D> as = aa;
+                        as.thr = 2u;
+                        k_attempt_coop<D, G, 1, 0, 1><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(as, sel);
+                        be::g_launches++;
+                    }
+                } else k_attempt_coop<D, G, 1, 0, 1><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel);
                 launched = true;
             }
         }
-        if (!launched) k_attempt_coop<D, G, 0, VOR_ATT_STAGE><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel);
+        if (!launched) {
+            AttemptArgs<D> af = aa;
+            af.slowFlag = nullptr;
+            k_attempt_coop<D, G, 0, VOR_ATT_STAGE, 1><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(af, sel);
+        }
         prof.stop(stream);
         prof.start(2, stream);
         k_commit_coop<D, G><<<grid, VOR_COOP_BLOCK, 0, stream>>>(ca, act, sel, (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2) | (opt.recycle ? 0 : 4));
@@ -559,8 +582,11 @@ template <int D> class Engine {
                 roundSalt = roundSalt * 1664525u + 1013904223u;
                 const int keybase = epoch << (bits + 1);
                 const RoundSel sel{nact, stride, (int)((roundSalt >> 8) % (uint32_t)stride), nsel};
-                AttemptArgs<D> aa{mesh, scr, act, bits, roundSalt, 0u, stride, sel.offset, keybase, opt.stats};
-                CheckArgs<D> ca{mesh, scr, bits, roundSalt, keybase};
+                // hot / exact twins of the attempt kernel -- unless this input keeps leaving the FP64 filter (near-degenerate:
+                // thousands of flagged points), where one kernel with the exact path inside is the better deal
+                const bool split = opt.split_exact && !splitDisabled;
+                AttemptArgs<D> aa{mesh, scr, act, bits, roundSalt, 0u, stride, sel.offset, keybase, opt.stats, split ? slowFlag : nullptr};
+                CheckArgs<D> ca{mesh, scr, bits, roundSalt, keybase, split ? slowFlag : nullptr};
                 const int G = opt.group ? opt.group : (nsel > opt.coop_switch ? opt.group_big : 32);
                 if (G == 8) launch_round<8>(aa, ca, sel); else launch_round<32>(aa, ca, sel);
                 epoch--;
@@ -568,6 +594,8 @@ template <int D> class Engine {
             }
             pull_counters();
             check_device_error("round");
+            slowPending = hcnt->nflag_set > hcnt->nflag_done;
+            if (hcnt->nflag_set > 512) splitDisabled = true;
             const long long done = (long long)(win_total() - win0) + (long long)(hcnt->ndup - dup0);
             const int newPending = total - (int)done;
             insertedTotal += (long long)(pending - newPending);
@@ -636,8 +664,8 @@ template <int D> class Engine {
             const double fsel0 = (double)thr / (double)(1u << bits);
             const int stride = (opt.select_mode == 1 && thr < (1u << bits)) ? std::max(1, (int)std::lround(1.0 / fsel0)) : 0;
             const int offset = stride > 0 ? (int)(roundSalt % (uint32_t)stride) : 0;
-            AttemptArgs<D> aa{mesh, scr, act, bits, roundSalt, thr, stride, offset, keybase, opt.stats};
-            CheckArgs<D> ca{mesh, scr, bits, roundSalt, keybase};
+            AttemptArgs<D> aa{mesh, scr, act, bits, roundSalt, thr, stride, offset, keybase, opt.stats, nullptr};
+            CheckArgs<D> ca{mesh, scr, bits, roundSalt, keybase, nullptr};
             int nw = 0, used = 0;
             {
                 prof.start(0, stream);

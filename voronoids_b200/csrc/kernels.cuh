@@ -154,7 +154,7 @@ template <> struct Geo<3> {
         Verts r; r.p0 = load_pt(m.pts + v.x); r.p1 = load_pt(m.pts + v.y); r.p2 = load_pt(m.pts + v.z); r.p3 = load_pt(m.pts + v.w); return r;
     }
     // bit i set <=> p is strictly beyond face i (orientation with vertex i replaced by p is negative)
-    static VOR_HD int beyond_mask(PredCtx &cx, const Verts &t, const Pt &p) {
+    template <class CX> static VOR_HD int beyond_mask(CX &cx, const Verts &t, const Pt &p) {
         int mk = 0;
         if (orient3d(cx, p, t.p1, t.p2, t.p3) < 0) mk |= 1;
         if (orient3d(cx, t.p0, p, t.p2, t.p3) < 0) mk |= 2;
@@ -162,8 +162,8 @@ template <> struct Geo<3> {
         if (orient3d(cx, t.p0, t.p1, t.p2, p) < 0) mk |= 8;
         return mk;
     }
-    static VOR_HD int conflict(PredCtx &cx, const Verts &t, const Pt &p) { return insphere(cx, t.p0, t.p1, t.p2, t.p3, p) > 0; }
-    static VOR_HD int orient(PredCtx &cx, const Verts &t) { return orient3d(cx, t.p0, t.p1, t.p2, t.p3); }
+    template <class CX> static VOR_HD int conflict(CX &cx, const Verts &t, const Pt &p) { return insphere(cx, t.p0, t.p1, t.p2, t.p3, p) > 0; }
+    template <class CX> static VOR_HD int orient(CX &cx, const Verts &t) { return orient3d(cx, t.p0, t.p1, t.p2, t.p3); }
 };
 
 template <> struct Geo<2> {
@@ -172,15 +172,15 @@ template <> struct Geo<2> {
     static VOR_HD Verts load(const Mesh<2> &m, const int4 &v) {
         Verts r; r.p0 = m.pts[v.x]; r.p1 = m.pts[v.y]; r.p2 = m.pts[v.z]; return r;
     }
-    static VOR_HD int beyond_mask(PredCtx &cx, const Verts &t, const Pt &p) {
+    template <class CX> static VOR_HD int beyond_mask(CX &cx, const Verts &t, const Pt &p) {
         int mk = 0;
         if (orient2d(cx, p, t.p1, t.p2) < 0) mk |= 1;
         if (orient2d(cx, t.p0, p, t.p2) < 0) mk |= 2;
         if (orient2d(cx, t.p0, t.p1, p) < 0) mk |= 4;
         return mk;
     }
-    static VOR_HD int conflict(PredCtx &cx, const Verts &t, const Pt &p) { return incircle(cx, t.p0, t.p1, t.p2, p) > 0; }
-    static VOR_HD int orient(PredCtx &cx, const Verts &t) { return orient2d(cx, t.p0, t.p1, t.p2); }
+    template <class CX> static VOR_HD int conflict(CX &cx, const Verts &t, const Pt &p) { return incircle(cx, t.p0, t.p1, t.p2, p) > 0; }
+    template <class CX> static VOR_HD int orient(CX &cx, const Verts &t) { return orient2d(cx, t.p0, t.p1, t.p2); }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -197,6 +197,7 @@ template <int D> struct AttemptArgs {
     int offset;         //   run of `stride` consecutive (Morton-ordered) active entries, rotating every round
     int keybase;        // epoch << (bits + 1)
     int stats;          // accumulate W/E counters
+    int *slowFlag;      // cooperative kernels: per vertex, != 0 = handed to the exact ("slow") twin (see coop_kernels.cuh); may be null
 };
 
 template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
@@ -339,6 +340,7 @@ template <int D> struct CheckArgs {
     int bits;
     uint32_t salt;
     int keybase;
+    const int *slowFlag;
 };
 
 // `valid` = tid addresses a claimed slot.  No early return before the allocation so that whole warps reach it.

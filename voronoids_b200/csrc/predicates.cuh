@@ -22,33 +22,41 @@ namespace vor {
 
 constexpr double EPSH = 1.1102230246251565e-16; // 2^-53
 
-struct PredCtx {
+// EX = false: a predicate that leaves the FP64 filter does NOT call the exact path; it sets `failed` and returns 0, and
+// the caller gives the work item to a kernel instantiated with EX = true.  Measured: the exact-integer code in the
+// call tree of the attempt kernel costs its hot loop 10 % (95 vs 85 ms per 10M points) although it is never executed
+// on such inputs -- so the hot kernel is built without it and a slow twin picks up the flagged points (engine.cuh).
+template <bool EX> struct PredCtxT {
     Counters *cnt;
+    bool failed = false;
+    static constexpr bool exact = EX;
 };
+using PredCtx = PredCtxT<true>;
 
 // exact_calls counts the predicates that left the FP64 filter, whether the double-double stage inside *_exact
 // (dd_stage.cuh) or the integers settled them; exact_zero counts true zeros.
-VOR_HD int finish_exact(PredCtx &cx, int s, int range_err) {
+template <class CX> VOR_HD int finish_exact(CX &cx, int s, int range_err) {
     atomic_add_ull(&cx.cnt->exact_calls, 1ULL);
     if (range_err) set_err(cx.cnt, ERR_RANGE);
     else if (s == 0) atomic_add_ull(&cx.cnt->exact_zero, 1ULL);
     return s;
 }
 
-VOR_HD int orient2d(PredCtx &cx, const double2 &a, const double2 &b, const double2 &c) {
+template <class CX> VOR_HD int orient2d(CX &cx, const double2 &a, const double2 &b, const double2 &c) {
     const double l = (a.x - c.x) * (b.y - c.y);
     const double r = (a.y - c.y) * (b.x - c.x);
     const double det = l - r;
     const double bound = (3.0 + 16.0 * EPSH) * EPSH * (fabs(l) + fabs(r));
     if (det > bound) return 1;
     if (-det > bound) return -1;
+    if constexpr (!CX::exact) { cx.failed = true; return 0; }
     const double A[2] = {a.x, a.y}, B[2] = {b.x, b.y}, C[2] = {c.x, c.y};
     int re = 0;
     const int s = orient2d_exact(A, B, C, &re);
     return finish_exact(cx, s, re);
 }
 
-VOR_HD int orient3d(PredCtx &cx, const double4 &a, const double4 &b, const double4 &c, const double4 &d) {
+template <class CX> VOR_HD int orient3d(CX &cx, const double4 &a, const double4 &b, const double4 &c, const double4 &d) {
     const double adx = a.x - d.x, bdx = b.x - d.x, cdx = c.x - d.x;
     const double ady = a.y - d.y, bdy = b.y - d.y, cdy = c.y - d.y;
     const double adz = a.z - d.z, bdz = b.z - d.z, cdz = c.z - d.z;
@@ -61,6 +69,7 @@ VOR_HD int orient3d(PredCtx &cx, const double4 &a, const double4 &b, const doubl
     const double bound = (7.0 + 56.0 * EPSH) * EPSH * perm;
     if (det > bound) return 1;
     if (-det > bound) return -1;
+    if constexpr (!CX::exact) { cx.failed = true; return 0; }
     const double A[3] = {a.x, a.y, a.z}, B[3] = {b.x, b.y, b.z}, C[3] = {c.x, c.y, c.z}, D[3] = {d.x, d.y, d.z};
     int re = 0;
     const int s = orient3d_exact(A, B, C, D, &re);
@@ -95,7 +104,7 @@ VOR_HD_NOINLINE int incircle_slow(Counters *cnt, double ax, double ay, double bx
 // is bounded by the same expression in X, Y (rounding is monotone), so permanent <= 6 fl(XY) fl(X^2 + Y^2) (1+eps)^4 and
 // |det| > 61 eps fl(XY) fl(X^2+Y^2) >= (10 + 96 eps) eps permanent certifies the sign.  It keeps 2 extra values
 // live instead of the 6 products of the permanent.
-VOR_HD int incircle(PredCtx &cx, const double2 &a, const double2 &b, const double2 &c, const double2 &d) {
+template <class CX> VOR_HD int incircle(CX &cx, const double2 &a, const double2 &b, const double2 &c, const double2 &d) {
     const double adx = a.x - d.x, ady = a.y - d.y;
     const double bdx = b.x - d.x, bdy = b.y - d.y;
     const double cdx = c.x - d.x, cdy = c.y - d.y;
@@ -106,6 +115,7 @@ VOR_HD int incircle(PredCtx &cx, const double2 &a, const double2 &b, const doubl
     const double bound = ((61.0 * EPSH) * (mx * my)) * (mx * mx + my * my);
     if (det > bound) return 1;
     if (-det > bound) return -1;
+    if constexpr (!CX::exact) { cx.failed = true; return 0; }
     return incircle_slow(cx.cnt, a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y);
 }
 
@@ -148,7 +158,7 @@ VOR_HD_NOINLINE int insphere_slow(Counters *cnt, double ax, double ay, double az
     return finish_exact(cx, s, re);
 }
 
-VOR_HD int insphere_semi(PredCtx &cx, const double4 &a, const double4 &b, const double4 &c, const double4 &d, const double4 &e) {
+template <class CX> VOR_HD int insphere_semi(CX &cx, const double4 &a, const double4 &b, const double4 &c, const double4 &d, const double4 &e) {
     const double aex = a.x - e.x, bex = b.x - e.x, cex = c.x - e.x, dex = d.x - e.x;
     const double aey = a.y - e.y, bey = b.y - e.y, cey = c.y - e.y, dey = d.y - e.y;
     const double aez = a.z - e.z, bez = b.z - e.z, cez = c.z - e.z, dez = d.z - e.z;
@@ -176,6 +186,7 @@ VOR_HD int insphere_semi(PredCtx &cx, const double4 &a, const double4 &b, const 
     const double bound = (16.0 + 224.0 * EPSH) * EPSH * perm;
     if (det > bound) return 1;
     if (-det > bound) return -1;
+    if constexpr (!CX::exact) { cx.failed = true; return 0; }
     const double A[3] = {a.x, a.y, a.z}, B[3] = {b.x, b.y, b.z}, C[3] = {c.x, c.y, c.z}, D[3] = {d.x, d.y, d.z}, E[3] = {e.x, e.y, e.z};
     int re = 0;
     const int s = insphere_exact(A, B, C, D, E, &re);
@@ -191,7 +202,7 @@ VOR_HD int insphere_semi(PredCtx &cx, const double4 &a, const double4 &b, const 
 #ifndef VOR_STATIC_FILTER
 #define VOR_STATIC_FILTER 0   // measured on the 10M-point run: attempt kernel 98.7 ms with it, 96.2 ms without
 #endif
-VOR_HD int insphere(PredCtx &cx, const double4 &a, const double4 &b, const double4 &c, const double4 &d, const double4 &e) {
+template <class CX> VOR_HD int insphere(CX &cx, const double4 &a, const double4 &b, const double4 &c, const double4 &d, const double4 &e) {
     if (!VOR_STATIC_FILTER) return insphere_semi(cx, a, b, c, d, e);
     const double aex = a.x - e.x, bex = b.x - e.x, cex = c.x - e.x, dex = d.x - e.x;
     const double aey = a.y - e.y, bey = b.y - e.y, cey = c.y - e.y, dey = d.y - e.y;
@@ -217,6 +228,7 @@ VOR_HD int insphere(PredCtx &cx, const double4 &a, const double4 &b, const doubl
     const double bound = ((385.0 * EPSH) * ((mx * my) * mz)) * (mx * mx + my * my + mz * mz);
     if (det > bound) return 1;
     if (-det > bound) return -1;
+    if constexpr (!CX::exact) { cx.failed = true; return 0; }
     return insphere_slow(cx.cnt, a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z, d.x, d.y, d.z, e.x, e.y, e.z);
 }
 

@@ -139,6 +139,7 @@ struct Counters {
     // ~9 ms each on the B200 (L2 serialises them); winner g adds (1 << 40 | created) to part[g % NPART][0], each part
     // in its own 32 B sector.  The host folds them (Engine::win_total / created_all).
     unsigned long long part[128][4];
+    int nflag_set, nflag_done;       // points handed to / finished by the exact twin of the attempt kernel
 };
 constexpr int NPART = 128;
 
