@@ -422,12 +422,25 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
 // queues: SM i works through the i-th contiguous range of the Morton-ordered slots, so the simplices and vertices it
 // gathers in one round come from one compact region of the mesh (and of the store) instead of every 148th block of
 // it; the ranges of SMs that finish early are drained by the others.
+// The hot twin needs fewer registers than the kernel with the exact path: two-warp blocks at 56 registers (36 warps per
+// SM instead of 32) measured 88.7 vs 92.1 ms per 10M points; 48 registers spill too much (110 ms).
+#ifndef VOR_HOT_BLOCK
+#define VOR_HOT_BLOCK 64
+#endif
+#ifndef VOR_HOT_REGS
+#define VOR_HOT_REGS 56
+#endif
+template <int EXACT> struct AttemptLaunch {
+    static constexpr int block = EXACT ? VOR_ATTEMPT_BLOCK : VOR_HOT_BLOCK;
+    static constexpr int regs = EXACT ? VOR_ATTEMPT_REGS : VOR_HOT_REGS;
+    static constexpr int minBlocks = (65536 / (regs * block)) > 32 ? 32 : (65536 / (regs * block));
+};
 template <int D, int G, int RED, int STAGE, int EXACT>
-__global__ void __launch_bounds__(VOR_ATTEMPT_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_ATTEMPT_BLOCK)) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
+__global__ void __launch_bounds__(AttemptLaunch<EXACT>::block, AttemptLaunch<EXACT>::minBlocks) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
     // the cavity found so far, staged in shared memory: ids and neighbour codes of the first SK killed simplices, so a
     // flood level starts from two shared-memory reads instead of two dependent L2 round trips (scratch, then record)
-    __shared__ int s_kid[VOR_ATTEMPT_BLOCK / G][STAGE ? VOR_SK : 1];
-    __shared__ int4 s_knb[VOR_ATTEMPT_BLOCK / G][STAGE ? VOR_SK : 1];
+    __shared__ int s_kid[AttemptLaunch<EXACT>::block / G][STAGE ? VOR_SK : 1];
+    __shared__ int4 s_knb[AttemptLaunch<EXACT>::block / G][STAGE ? VOR_SK : 1];
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;   // group = attempt slot
     if (gid >= rsel.nsel) return;
     attempt_one<D, G, RED, STAGE, EXACT>(A, rsel, gid, s_kid[threadIdx.x / G], s_knb[threadIdx.x / G]);

@@ -527,7 +527,8 @@ template <int D> class Engine {
                 else if (aa.slowFlag) {
                     // hot twin without the exact predicates in its call tree; while flagged points are pending (host
                     // knowledge, one read-back old) the exact twin follows and attempts only those
-                    k_attempt_coop<D, G, 1, 0, 0><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel);
+                    const unsigned hgrid = (unsigned)(((long long)sel.nsel * G + VOR_HOT_BLOCK - 1) / VOR_HOT_BLOCK);
+                    k_attempt_coop<D, G, 1, 0, 0><<<hgrid, VOR_HOT_BLOCK, 0, stream>>>(aa, sel);
                     if (slowPending) {
                         AttemptArgs<D> as = aa;
                         as.thr = 2u;
