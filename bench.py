@@ -224,7 +224,7 @@ def main():
         sd = dict(zip(_capi.STAT_NAMES, [int(x) for x in s]))
         prof = (C.c_double * 8)()
         lib.vor_tree_profile(h, prof)
-        sd["profile_ms"] = {"attempt": prof[0], "commit": prof[2], "setup": prof[3]}
+        sd["profile_ms"] = {"attempt": prof[0], "commit": prof[2], "spheres": prof[1], "setup": prof[3]}
         sd["profile_launches"] = {"attempt": prof[4], "commit": prof[6]}
         lib.vor_tree_destroy(h)
         return ms, sd

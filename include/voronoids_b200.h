@@ -129,7 +129,9 @@ vor_status vor_find_placement(const int64_t *offsets, const int32_t *ids, size_t
 
 /* check_delaunay (delaunay_tree.rs:512-541): *ok = 1 iff every live simplex is positively oriented, adjacency is
  * symmetric and every interior facet is locally Delaunay (equivalent to the brute-force empty-sphere test).
- * fail_counts (optional, 5 entries): orientation, dead neighbour, asymmetric, facet mismatch, not Delaunay. */
+ * fail_counts (optional, 6 entries): orientation, dead neighbour, asymmetric, facet mismatch, not Delaunay, and
+ * stored circumsphere filter (the cached centre/radius of delaunay_tree.rs:11-16, here a certified filter) contradicting
+ * the exact predicate on a simplex's own vertices or on the opposite vertices of its neighbours. */
 vor_status vor_tree_check_delaunay(vor_tree *t, int *ok, int32_t *fail_counts);
 
 /* bootstrap data: super-simplex vertices [(dim+1) x dim] per set, bounding-sphere centre [dim] and 10x radius */
@@ -137,8 +139,9 @@ vor_status vor_tree_super_simplex(vor_tree *t, size_t set, double *super_vertice
 
 /* engine statistics: [rounds, attempts, winners, owner_resets, compactions, stages,
  *                     walk_steps W, in-sphere tests E, killed K, created C, exact_calls, exact_zero, duplicates, simplex_slots,
- *                     attempts that lost during the flood, in-sphere tests of the attempts that completed] */
-#define VOR_N_STATS 16
+ *                     attempts that lost during the flood, in-sphere tests of the attempts that completed,
+ *                     conflict tests the cached-sphere filter left to the determinant, points handed to the exact twin] */
+#define VOR_N_STATS 18
 vor_status vor_tree_stats(vor_tree *t, uint64_t *stats);
 
 /* with option "profile": CUDA-event milliseconds per kernel class [attempt, check, retri, setup] followed by the
@@ -157,6 +160,12 @@ vor_status vor_bounding_sphere(int dim, const double *points, size_t n, double *
  * 2 incircle [4 pts], 3 insphere [5 pts]; rows are packed points; out = sign.  n_exact (optional) = calls that
  * needed the exact path. */
 vor_status vor_predicates(int kind, const double *rows, size_t n, int32_t *out, uint64_t *n_exact, int device);
+/* The cached circumsphere of Simplex{center, radius} (delaunay_tree.rs:11-16) as this engine stores it: a CERTIFIED
+ * filter in front of the exact in-sphere predicate (float centre relative to `origin`, inner / outer squared radii).
+ * rows = dim+1 simplex vertices followed by one query point; `reach` bounds |p - origin|_1 of every query;
+ * out[i] = +1 certainly strictly inside, -1 certainly not strictly inside, 0 undecided (the engine then evaluates
+ * the determinant).  blocks (optional, 5 floats per row) = cx, cy, cz, rin2, rout2. */
+vor_status vor_sphere_filter(int dim, const double *origin, double reach, const double *rows, size_t n, int32_t *out, float *blocks, int device);
 
 /* ---- misc ------------------------------------------------------------------------------------------------------ */
 const char *vor_last_error(void);          /* thread-local text of the last failure */

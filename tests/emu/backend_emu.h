@@ -56,6 +56,7 @@ inline void sort_keys(uint64_t *ki, uint64_t *ko, size_t n, Stream) {
     std::sort(ko, ko + n);
 }
 static unsigned long long g_launches = 0;
+inline void check_launch(const char *) {}
 struct Prof {
     bool on = false;
     double ms[4] = {0, 0, 0, 0};

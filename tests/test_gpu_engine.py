@@ -124,6 +124,16 @@ def test_gpu_full_size_10m(gpu_lib, oracle, golden):
         t.close()
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_gpu_sphere_filter_is_certified(gpu_lib, oracle, dim):
+    """the cached-circumsphere filter (sphere.cuh) as compiled for the B200 never certifies what the exact predicate
+    contradicts: adversarial rows (slivers, needles, near-sphere queries) at several scales and offsets"""
+    import spherecases as sc
+    for scale, offset in [(1.0, 0.0), (1e-3, 0.0), (1.0, 1e3), (1e6, -3e6)]:
+        decided, verdict, want = sc.check_filter(gpu_lib, oracle, dim, 60_000, seed=11 + dim, scale=scale, offset=offset)
+        assert decided > 0.1
+
+
 @pytest.mark.parametrize("kind", ["orient2d", "orient3d", "incircle", "insphere"])
 def test_gpu_predicates_vs_fractions(gpu_lib, oracle, kind):
     from voronoids_b200 import geometry
@@ -200,11 +210,10 @@ def test_gpu_edges_pinned_block_outlives_tree(gpu_lib):
     assert gpu_lib.vor_host_free(12345) != 0
 
 
-ENGINE_DEFAULTS = {"recycle": 0, "persist": 0, "red": 1, "commit_smem": 1, "prewalk": 0}
+ENGINE_DEFAULTS = {"red": 1, "commit_smem": 1, "split_exact": 1}
 
 
-@pytest.mark.parametrize("opts", [{"recycle": 1}, {"persist": 1024}, {"persist": 1024, "recycle": 1}, {"red": 0}, {"commit_smem": 0}, {"prewalk": 4},
-                                  {"prewalk": 1}])
+@pytest.mark.parametrize("opts", [{"red": 0}, {"commit_smem": 0}, {"split_exact": 0}, {"split_exact": 0, "commit_smem": 0}])
 def test_gpu_engine_options_keep_parity(gpu_lib, oracle, opts):
     """every scheduling / layout option of the engine yields the oracle's edge set (3D and 2D)"""
     try:

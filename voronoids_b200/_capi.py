@@ -45,15 +45,16 @@ SYMBOLS = {
     "vor_in_sphere": (C.c_int, [C.c_int, dp, dp, dp, C.c_size_t, i32p, C.c_int]),
     "vor_bounding_sphere": (C.c_int, [C.c_int, dp, C.c_size_t, dp, dp, C.c_int]),
     "vor_predicates": (C.c_int, [C.c_int, dp, C.c_size_t, i32p, u64p, C.c_int]),
+    "vor_sphere_filter": (C.c_int, [C.c_int, dp, C.c_double, dp, C.c_size_t, i32p, C.POINTER(C.c_float), C.c_int]),
     "vor_last_error": (C.c_char_p, []),
     "vor_kernel_launches": (C.c_uint64, []),
     "vor_release_memory": (None, []),
     "vor_set_option": (C.c_int, [C.c_char_p, C.c_double]),
     "vor_tree_set_stream": (None, [tree_p, C.c_void_p]),
 }
-N_STATS = 16
+N_STATS = 18
 STAT_NAMES = ("rounds", "attempts", "winners", "owner_resets", "compactions", "stages", "walk_steps", "tests", "killed", "created",
-              "exact_calls", "exact_zero", "duplicates", "simplex_slots", "aborted", "tests_completed")
+              "exact_calls", "exact_zero", "duplicates", "simplex_slots", "aborted", "tests_completed", "sphere_undecided", "flagged")
 
 
 def delaunay_batch_devices(lib, points, set_offsets, devices):
@@ -244,7 +245,7 @@ class Tree:
 
     def check_delaunay(self):
         ok = C.c_int()
-        f = np.zeros(5, dtype=np.int32)
+        f = np.zeros(6, dtype=np.int32)
         self._check(self._lib.vor_tree_check_delaunay(self._h, C.byref(ok), f.ctypes.data_as(i32p)))
         return bool(ok.value), f
 

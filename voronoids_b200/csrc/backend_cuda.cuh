@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <stdexcept>
 #include <map>
@@ -157,6 +158,9 @@ inline void sync(Stream s) { VOR_CUDA(cudaStreamSynchronize(s)); }
 
 // Large copies between pageable host memory and the device go through two pinned staging buffers so that the DMA of
 // chunk i+1 overlaps the host memcpy of chunk i (a plain cudaMemcpy on pageable memory runs at a few GB/s).
+// One staging set per DEVICE: the events are created under the device that is current at the first large copy, and an
+// event may only be recorded on a stream of its own device; per-device mutexes also keep the copies of different
+// devices (vor_delaunay_batch: one host thread per device) from serialising each other.
 struct Staging {
     static constexpr size_t CHUNK = (size_t)32 << 20;
     char *buf[2] = {nullptr, nullptr};
@@ -170,7 +174,14 @@ struct Staging {
         }
     }
 };
-extern Staging g_staging;
+constexpr int MAX_DEVICES = 64;
+extern Staging g_staging_dev[MAX_DEVICES];
+inline Staging &staging_here() {
+    int dev = 0;
+    VOR_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES) throw CudaError("device index beyond the staging table", ERR_ARG);
+    return g_staging_dev[dev];
+}
 // host memcpy on a few threads: the destination of a result copy is usually freshly allocated memory, so the copy is
 // dominated by first-touch page faults, which scale with threads
 inline void par_memcpy(char *dst, const char *src, size_t n) {
@@ -187,6 +198,7 @@ inline void par_memcpy(char *dst, const char *src, size_t n) {
 }
 inline void d2h_big(void *h, const void *d, size_t n, Stream s) {
     if (n < 4 * Staging::CHUNK) { VOR_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); VOR_CUDA(cudaStreamSynchronize(s)); return; }
+    Staging &g_staging = staging_here();
     std::lock_guard<std::mutex> lk(g_staging.mu);
     g_staging.init();
     const size_t nch = (n + Staging::CHUNK - 1) / Staging::CHUNK;
@@ -205,6 +217,7 @@ inline void d2h_big(void *h, const void *d, size_t n, Stream s) {
 }
 inline void h2d_big(void *d, const void *h, size_t n, Stream s) {
     if (n < 4 * Staging::CHUNK) { VOR_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); VOR_CUDA(cudaStreamSynchronize(s)); return; }
+    Staging &g_staging = staging_here();
     std::lock_guard<std::mutex> lk(g_staging.mu);
     g_staging.init();
     const size_t nch = (n + Staging::CHUNK - 1) / Staging::CHUNK;
@@ -243,7 +256,9 @@ inline void sort_keys(uint64_t *keys_in, uint64_t *keys_out, size_t n, Stream s)
     dfree(d);
 }
 
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;   // kernels of this library launched so far (bench.py gpu_launches)
+// a launch-configuration failure must surface at the launch, not as "no progress" hundreds of rounds later
+inline void check_launch(const char *what) { check(cudaGetLastError(), what); }
 
 // per-kernel-class CUDA-event timing on the launching stream (bench.py roofline; off unless option "profile")
 struct Prof {
@@ -278,7 +293,7 @@ struct Prof {
         ev.clear();
         cls.clear();
     }
-}; // kernels of this library launched so far (bench.py gpu_launches)
+};
 
 } // namespace be
 
@@ -300,6 +315,7 @@ __global__ void __launch_bounds__(256) k_items_full(Args a, int n) {
         const int _n = (int)(n);                                                                         \
         if (_n > 0) {                                                                                    \
             ::vor::k_items<ArgsT, body><<<(_n + 255) / 256, 256, 0, stream>>>(args, _n);                 \
+            ::vor::be::check_launch(#body);                                                              \
             ::vor::be::g_launches++;                                                                     \
         }                                                                                                \
     } while (0)
@@ -308,6 +324,7 @@ __global__ void __launch_bounds__(256) k_items_full(Args a, int n) {
         const int _n = (int)(n);                                                                         \
         if (_n > 0) {                                                                                    \
             ::vor::k_items_full<ArgsT, body><<<(_n + 255) / 256, 256, 0, stream>>>(args, _n);            \
+            ::vor::be::check_launch(#body);                                                              \
             ::vor::be::g_launches++;                                                                     \
         }                                                                                                \
     } while (0)

@@ -81,18 +81,13 @@ int vor_set_option(const char *name, double value) {
     else if (n == "verbose") g_opts.verbose = (int)value;
     else if (n == "profile") g_opts.profile = (int)value;
     else if (n == "coop") g_opts.coop = (int)value;
-    else if (n == "group") g_opts.group = (int)value;
-    else if (n == "coop_switch") g_opts.coop_switch = (int)value;
     else if (n == "rounds_per_sync") g_opts.rounds_per_sync = (int)value;
     else if (n == "select_mode") g_opts.select_mode = (int)value;
-    else if (n == "prewalk") g_opts.prewalk = (int)value;
     else if (n == "red") g_opts.red = (int)value;
     else if (n == "commit_smem") g_opts.commit_smem = (int)value;
-    else if (n == "recycle") g_opts.recycle = (int)value;
-    else if (n == "persist") g_opts.persist = (int)value;
-    else if (n == "stage_below") g_opts.stage_below = (int)value;
     else if (n == "split_exact") g_opts.split_exact = (int)value;
     else if (n == "tet_factor") g_opts.tet_factor = value;
+    else if (n == "compact_frac") g_opts.compact_frac = value;
     else if (n == "capk") { g_opts.capk = (int)value; g_opts.capb = 2 * g_opts.capk + 4; }
     else if (n == "big_slots") g_opts.big_slots = (int)value;
     else if (n == "big_capk") g_opts.big_capk = (int)value;
@@ -413,8 +408,8 @@ vor_status vor_tree_check_delaunay(vor_tree *t, int *ok, int32_t *fail_counts) {
         return t->visit([&](auto &e) -> vor_status {
             int f[8];
             e.validate(f);
-            if (ok) *ok = (f[0] | f[1] | f[2] | f[3] | f[4]) == 0;
-            if (fail_counts) for (int i = 0; i < 5; i++) fail_counts[i] = f[i];
+            if (ok) *ok = (f[0] | f[1] | f[2] | f[3] | f[4] | f[5]) == 0;
+            if (fail_counts) for (int i = 0; i < 6; i++) fail_counts[i] = f[i];
             return VOR_OK;
         });
     });
@@ -442,7 +437,8 @@ vor_status vor_tree_stats(vor_tree *t, uint64_t *s) {
             const vor::Counters &c = *e.hcnt;
             s[0] = e.rs.rounds; s[1] = e.rs.attempts; s[2] = e.rs.winners; s[3] = e.rs.owner_resets; s[4] = e.rs.compactions; s[5] = e.rs.stages;
             s[6] = c.walk_steps; s[7] = c.tests; s[8] = c.killed; s[9] = c.created; s[10] = c.exact_calls; s[11] = c.exact_zero;
-            s[12] = (uint64_t)c.ndup; s[13] = (uint64_t)c.ntets; s[14] = c.aborted; s[15] = c.tests_ok;
+            s[12] = (uint64_t)c.ndup; s[13] = (uint64_t)c.ntets; s[14] = c.aborted; s[15] = c.tests_ok; s[16] = c.sph_undecided;
+            s[17] = (uint64_t)c.nflag_set;
             return VOR_OK;
         });
     });
@@ -525,6 +521,24 @@ vor_status vor_predicates(int kind, const double *rows, size_t n, int32_t *out, 
         vor::be::sync(st);
         if (n_exact) *n_exact = hc.exact_calls;
         if (hc.err == vor::ERR_RANGE) { g_err = "coordinate range exceeds the exact-arithmetic capacity"; return VOR_ERR_RANGE; }
+        return VOR_OK;
+    });
+}
+
+vor_status vor_sphere_filter(int dim, const double *origin, double reach, const double *rows, size_t n, int32_t *out, float *blocks, int device) {
+    return guarded([&]() -> vor_status {
+        if ((dim != 2 && dim != 3) || !origin || !rows || !out) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(device);
+        const vor::be::Stream st{};
+        const size_t w = dim == 3 ? 15 : 8;
+        DevBuf dr(sizeof(double) * n * w), dout(sizeof(int) * n), db(sizeof(float) * n * 5);
+        vor::be::h2d(dr.p, rows, sizeof(double) * n * w, st);
+        vor::SphereRef ref{origin[0], origin[1], dim == 3 ? origin[2] : 0.0, 8.0 * vor::SPH_EPS * reach};
+        vor::SphereBatchArgs a{(const double *)dr.p, (int *)dout.p, blocks ? (float *)db.p : nullptr, ref, dim};
+        VOR_LAUNCH(vor::SphereBatchArgs, vor::sphere_batch_body, n, a, st);
+        vor::be::d2h(out, dout.p, sizeof(int) * n, st);
+        if (blocks) vor::be::d2h(blocks, db.p, sizeof(float) * n * 5, st);
+        vor::be::sync(st);
         return VOR_OK;
     });
 }

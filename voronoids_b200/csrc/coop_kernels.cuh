@@ -49,62 +49,6 @@ template <> struct GeoCoop<2> {
 };
 
 // ------------------------------------------------------------------------------------------
-// walk (option "prewalk"): forwarding + visibility walk of the points selected this round, G = 4 lanes per point
-// (8 independent walks per warp) or G = 1 (32 per warp).  In the warp-per-point attempt kernel a walk keeps 4 of 32
-// lanes busy and is ONE dependent chain of gathers per warp; run here it leaves the attempt kernel with the flood only
-// (its own walk loop ends at the first test, on sectors this kernel has just pulled into L2).
-// ------------------------------------------------------------------------------------------
-template <int D, int G>
-__global__ void __launch_bounds__(128) k_walk_coop(AttemptArgs<D> A, RoundSel rsel) {
-    constexpr int M = Dim<D>::M;
-    using Gm = Geo<D>;
-    const Mesh<D> &m = A.m;
-    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const int gl = threadIdx.x & (G - 1);
-    const unsigned gmask = G == 1 ? __activemask() : group_mask<G>();
-    const int gshift = (threadIdx.x & 31) & ~(G - 1);
-    if (gid >= rsel.nsel) return;
-    const int a = slot_entry(rsel, gid);
-    if (a >= rsel.nact) return;
-    const int v = A.act[a];
-    int s = m.seed[v];
-    if (s < 0) return;
-    PredCtx cx{m.cnt};
-    const typename Gm::Pt p = m.pts[v];
-    int o;
-    while ((o = __ldcg(&OWK(m, s))) < 0) s = ~o;
-    unsigned rot = (unsigned)v * 2654435761u;
-    unsigned steps = 0;
-    for (;;) {
-        int4 stv, stn;
-        load_rec(m, s, stv, stn);
-        const typename Gm::Verts tvv = Gm::load(m, stv);
-        unsigned bal;
-        if (G == 1) bal = (unsigned)Gm::beyond_mask(cx, tvv, p);
-        else {
-            const int ok = gl < M ? GeoCoop<D>::orient_repl(cx, tvv, p, gl) : 1;
-            bal = (__ballot_sync(gmask, ok < 0) >> gshift) & ((1u << M) - 1u);
-        }
-        if (bal == 0) break;
-        int go = 0;
-        const int r0 = (int)((rot >> 16) % (unsigned)M);
-        for (int k = 0; k < M; k++) {
-            const int i = (r0 + k) % M;
-            if ((bal >> i) & 1) { go = i; break; }
-        }
-        const int code = get4(stn, go);
-        if (code < 0) { if (gl == 0) set_err(m.cnt, ERR_OUTSIDE); return; }
-        s = code >> 2;
-        rot = rot * 1664525u + 1013904223u;
-        if (++steps > (1u << 22)) { if (gl == 0) set_err(m.cnt, ERR_WALK); return; }
-    }
-    if (gl == 0) {
-        m.seed[v] = s;
-        if (A.stats) atomicAdd(&m.cnt->walk_steps, (unsigned long long)steps);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // attempt
 // ------------------------------------------------------------------------------------------
 // Small blocks: the groups of a block are independent, and a block keeps its registers until its SLOWEST group is
@@ -120,20 +64,27 @@ __global__ void __launch_bounds__(128) k_walk_coop(AttemptArgs<D> A, RoundSel rs
 #define VOR_ATTEMPT_BLOCK 32      // threads per block of the attempt kernel: one warp, so that a finished attempt frees its
                                   // registers at once (measured on the 10M-point run: 108 ms vs 116 ms with 64 threads)
 #endif
-#ifndef VOR_DEDUP
-#define VOR_DEDUP 0               // 1: lanes of a batch that reach the same neighbour elect one tester (match.any + shuffle);
-                                  // saves the ~6 % duplicate tests but measured 12 % SLOWER (107 vs 95 ms): the election
-                                  // sits in front of every gather
-#endif
-#ifndef VOR_ATT_STAGE
-#define VOR_ATT_STAGE 0           // 1: the flood reads the killed list and the neighbour codes from a shared-memory copy of
-                                  // the cavity instead of the global store (shorter dependent chain; measured 9 % SLOWER:
-                                  // the kernel is bound by the gather-instruction rate, not by the chain, and the
-                                  // copy costs registers)
-#endif
 #ifndef VOR_ATTEMPT_REGS
-#define VOR_ATTEMPT_REGS 64       // registers per thread of the attempt kernel (measured best of 80/64/48)
+#define VOR_ATTEMPT_REGS 64       // registers per thread of the attempt kernel with the exact path (measured best of 80/64/48)
 #endif
+// The determinant test of one simplex (record + 4 vertex gathers + FP64 filter [+ exact integers]) for the conflict
+// tests the stored sphere leaves undecided (~1e-5 of them on uniform input).  Out of line, operands by value: the hot loop
+// must not pay registers for it.  Returns 1 in conflict, 0 not, 2 = EX == false and the FP64 filter failed too.
+template <int D, bool EX>
+__device__ __noinline__ int conflict_slow(const typename Dim<D>::Pt *pts, const int4 *tet, Counters *cnt, int n, double px, double py, double pz) {
+    Mesh<D> mm{};
+    mm.pts = const_cast<typename Dim<D>::Pt *>(pts);
+    mm.tet = const_cast<int4 *>(tet);
+    mm.cnt = cnt;
+    PredCtxT<EX> cx{cnt};
+    typename Dim<D>::Pt p;
+    if constexpr (D == 3) { p.x = px; p.y = py; p.z = pz; p.w = 0.0; } else { p.x = px; p.y = py; }
+    const int c = Geo<D>::conflict(cx, Geo<D>::load(mm, TV(mm, n)), p);
+    if (!EX && cx.failed) return 2;
+    return c;
+}
+template <int D> __device__ __forceinline__ double pt_z(const typename Dim<D>::Pt &p) { if constexpr (D == 3) return p.z; else return 0.0; }
+
 // RED = 1: the kill reservation is a fire-and-forget reduction too (no round trip on the critical path of a flood
 // level): lanes of one batch that reach the same simplex are deduplicated with match.any, and a better killer that
 // slips in between the owner read and the reduction is caught by the ownership check of commit.
@@ -141,11 +92,25 @@ __global__ void __launch_bounds__(128) k_walk_coop(AttemptArgs<D> A, RoundSel rs
 // is abandoned and its point flagged (A.slowFlag[v] = key base of the round); it skips flagged points.  EXACT = 1 with
 // A.thr == 2: the slow twin, launched behind it while flagged points are pending, attempts ONLY points flagged in an
 // EARLIER round (a point flagged in this round has left marks under this round's key).  A.thr == 0: everything.
-template <int D, int G, int RED, int STAGE, int EXACT>
+//
+// A conflict test is ONE 256-bit gather: the 32 B block of the neighbour holds its ownership words and its certified
+// circumsphere filter (sphere.cuh).  Only killed simplices have their record read (neighbour codes, by the next level).
+#ifndef VOR_SPEC
+#define VOR_SPEC 1                // 1: the neighbour codes of a tested simplex are gathered together with its block (one round
+                                  // trip per flood level); 0: only once the sphere says "in conflict" (a dependent second trip)
+#endif
+VOR_HD int4 load_nbr(const int4 *tet, int t) {
+#ifdef __CUDA_ARCH__
+    return __ldg(tet + REC4 * (size_t)t + TVO4 + 1);
+#else
+    return tet[REC4 * (size_t)t + TVO4 + 1];
+#endif
+}
+template <int D, int G, int RED, int EXACT>
 __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const RoundSel &rsel, const int gid, int *const sk, int4 *const sn) {
     constexpr int M = Dim<D>::M;
-    using Gm = Geo<D>;
     constexpr int SK = VOR_SK;
+    using Gm = Geo<D>;
     const Mesh<D> &m = A.m;
     const int gl = threadIdx.x & (G - 1);                          // lane inside the group
     const unsigned gmask = group_mask<G>();
@@ -155,7 +120,8 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
     const int a = slot_entry(rsel, slot);
     if (a >= rsel.nact) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }
     const int v = A.act[a];
-    if (m.seed[v] < 0) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }   // already inserted
+    int s = m.seed[v];
+    if (s < 0) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }   // already inserted
     if (A.slowFlag) {
         const int fl = A.slowFlag[v];
         if (EXACT ? (A.thr == 2u && (fl == 0 || fl == A.keybase)) : fl != 0) {
@@ -167,6 +133,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
     }
     PredCtxT<(EXACT != 0)> cx{m.cnt};
     const typename Gm::Pt p = m.pts[v];
+    const RelPt rq = rel_pt(m, p);
     const uint32_t q = bij_hash((uint32_t)slot, A.bits, A.salt);   // unique among the slots of this round
     const int key_k = A.keybase | (int)(q << 1);
     const int key_o = key_k | 1;
@@ -174,68 +141,75 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
     int status = ST_LOST, nk = 0, nb = 0, big = -1;
     unsigned steps = 0, tests = 0;
 
-    // -- forwarding (all lanes follow the same chain: broadcast loads)
-    int s = m.seed[v];
-    int o;
-    while ((o = __ldcg(&OWK(m, s))) < 0) s = ~o;
-
-    // -- visibility walk: lane k < M tests facet k
-    unsigned rot = (unsigned)v * 2654435761u;
-    int4 stv, stn;                     // record of the simplex the walk stands in: one 256-bit gather per step
-    load_rec(m, s, stv, stn);
-    typename Gm::Verts tvv = Gm::load(m, stv);
+    // -- forwarding (all lanes follow the same chain: broadcast loads); the block that says "dead, go there" or "alive"
+    // also holds the sphere of the simplex: a seed whose sphere certainly contains p starts the flood at once
+    OwnBlk sb = load_blk(m, s);
+    int4 stn = load_nbr(m.tet, s);         // neighbour codes of the simplex the flood starts from (speculative for a dead seed)
+    while (sb.kill < 0) { s = ~sb.kill; sb = load_blk(m, s); stn = load_nbr(m.tet, s); }
+    bool hit = sphere_test(sb, rq) > 0;
     bool fail = false;
-    for (;;) {
-        const int ok = gl < M ? GeoCoop<D>::orient_repl(cx, tvv, p, gl) : 1;
-        if (!EXACT && __any_sync(gmask, cx.failed)) break;
-        const unsigned bal = (__ballot_sync(gmask, ok < 0) >> gshift) & ((1u << M) - 1u);
-        if (bal == 0) break;
-        int go = 0;
-        const int r0 = (int)((rot >> 16) % (unsigned)M);
-        for (int k = 0; k < M; k++) {
-            const int i = (r0 + k) % M;
-            if ((bal >> i) & 1) { go = i; break; }
-        }
-        const int code = get4(stn, go);
-        if (code < 0) { if (gl == 0) set_err(m.cnt, ERR_OUTSIDE); fail = true; break; }
-        s = code >> 2;
-        rot = rot * 1664525u + 1013904223u;
-        if (++steps > (1u << 22)) { if (gl == 0) set_err(m.cnt, ERR_WALK); fail = true; break; }
+    typename Gm::Verts tvv;
+
+    // -- visibility walk: lane k < M tests facet k; it stops at the containing simplex or at any simplex whose stored
+    // sphere certainly contains p (the conflict region is connected: the flood finds all of it from any member)
+    if (!hit) {
+        unsigned rot = (unsigned)v * 2654435761u;
+        int4 stv;                          // record of the simplex the walk stands in: one 256-bit gather per step
         load_rec(m, s, stv, stn);
         tvv = Gm::load(m, stv);
+        for (;;) {
+            const int ok = gl < M ? GeoCoop<D>::orient_repl(cx, tvv, p, gl) : 1;
+            if (!EXACT && __any_sync(gmask, cx.failed)) break;
+            const unsigned bal = (__ballot_sync(gmask, ok < 0) >> gshift) & ((1u << M) - 1u);
+            if (bal == 0) break;
+            int go = 0;
+            const int r0 = (int)((rot >> 16) % (unsigned)M);
+            for (int k = 0; k < M; k++) {
+                const int i = (r0 + k) % M;
+                if ((bal >> i) & 1) { go = i; break; }
+            }
+            const int code = get4(stn, go);
+            if (code < 0) { if (gl == 0) set_err(m.cnt, ERR_OUTSIDE); fail = true; break; }
+            s = code >> 2;
+            rot = rot * 1664525u + 1013904223u;
+            if (++steps > (1u << 22)) { if (gl == 0) set_err(m.cnt, ERR_WALK); fail = true; break; }
+            sb = load_blk(m, s);           // independent of the record gather below
+            load_rec(m, s, stv, stn);
+            if (sphere_test(sb, rq) > 0) { hit = true; break; }
+            tvv = Gm::load(m, stv);
+        }
     }
 
     bool needSlow = !EXACT && __any_sync(gmask, cx.failed);
     if (needSlow) fail = true;
     if (!fail) {
         if (gl == 0) m.seed[v] = s;
-        // -- containing simplex must be in conflict, otherwise p duplicates one of its vertices
-        int c0 = 0;
-        if (gl == 0) c0 = Gm::conflict(cx, tvv, p);
-        c0 = __shfl_sync(gmask, c0, gshift);
         tests = gl == 0 ? 1u : 0u;
-        if (!EXACT && __any_sync(gmask, cx.failed)) { needSlow = true; fail = true; }
-        else if (!c0) {
-            if (gl == 0) {
-                m.seed[v] = -1;
-                atomicAdd(&m.cnt->ndup, 1);
-                if (EXACT && A.slowFlag && A.slowFlag[v] != 0) atomicAdd(&m.cnt->nflag_done, 1);   // a flagged point leaves as a duplicate
+        if (!hit) {
+            // -- containing simplex must be in conflict, otherwise p duplicates one of its vertices
+            int c0 = 0;
+            if (gl == 0) c0 = Gm::conflict(cx, tvv, p);
+            c0 = __shfl_sync(gmask, c0, gshift);
+            if (!EXACT && __any_sync(gmask, cx.failed)) { needSlow = true; fail = true; }
+            else if (!c0) {
+                if (gl == 0) {
+                    m.seed[v] = -1;
+                    atomicAdd(&m.cnt->ndup, 1);
+                    if (EXACT && A.slowFlag && A.slowFlag[v] != 0) atomicAdd(&m.cnt->nflag_done, 1);   // a flagged point leaves as a duplicate
+                }
+                fail = true;
             }
-            fail = true;
         }
     }
     if (!fail) {
-        int old0 = 0;
-        if (gl == 0) {
-            old0 = atomicMin(&OWK(m, s), key_k);
-            if (__ldcg(&OWR(m, s)) < key_k) old0 = -1;     // a better point keeps s in its outer ring
-        }
-        old0 = __shfl_sync(gmask, old0, gshift);
-        if (old0 < key_k) fail = true;
+        // reservation of the first simplex: early out on the block already in registers (a better point kills it or keeps
+        // it in its outer ring); anything that slips in later is caught by the ownership check of commit
+        if (sb.kill < key_k || sb.ring < key_k) fail = true;
+        else if (gl == 0) atomicMin(&OWK(m, s), key_k);
     }
     if (!fail) {
         ScrView sv = scr_view(A.scr, slot, -1);
-        if (gl == 0) { sv.k[0] = s; if (STAGE) { sk[0] = s; sn[0] = stn; } }
+        if (gl == 0) { sv.k[0] = s; sk[0] = s; sn[0] = stn; }
         __syncwarp(gmask);
         nk = 1;
         int head = 0;
@@ -244,66 +218,6 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
             const int tail = nk;
             const int items = (tail - head) * M;
             for (int base = 0; base < items && !lost; base += G) {
-#if VOR_DEDUP
-                // Lanes of one batch that reach the same neighbour n (a ring simplex seen from two killed simplices of
-                // the same level) elect ONE of them with match.any: it gathers and tests n, the others take its verdict
-                // by shuffle.  Saves the ~6 % duplicate tests (7 gather instructions each) and makes the claim of a
-                // newly killed simplex unique without looking at the value an atomic returns.
-                const int j = base + gl;
-                bool pushK = false, pushB = false, lostLane = false;
-                int newT = 0, fcode = 0, ocode = 0;
-                int4 nnb = make_int4(-1, -1, -1, -1);
-                const bool active = j < items;
-                int t = 0, i = 0, code = -1;
-                int n = -1 - (int)(threadIdx.x & 31);      // unique dummy: inactive lanes and hull facets match nobody
-                if (active) {
-                    const int e = head + j / M;
-                    i = j % M;
-                    if (STAGE && e < SK) { t = sk[e]; code = reinterpret_cast<const int *>(sn)[e * 4 + i]; }
-                    else { t = sv.k[e]; code = TNI(m, t, i); }
-                    if (code >= 0) n = code >> 2;
-                    else { pushB = true; fcode = t * 4 + i; ocode = code; }
-                }
-                const unsigned same = __match_any_sync(gmask, n);
-                const int leader = __ffs(same) - 1;
-                const bool lead = n >= 0 && leader == (int)(threadIdx.x & 31);
-                enum { V_MINE = 0, V_LOST = 1, V_RING = 2, V_NEW = 3 };
-                int verdict = V_MINE;
-                if (lead) {
-                    // the owner pair and the record of n are independent gathers: issue both before looking at either
-                    const int2 ow = __ldcg(reinterpret_cast<const int2 *>(&OWK(m, n)));   // x = kill word, y = ring word
-                    int4 nverts;
-                    if (STAGE) load_rec_cg(m, n, nverts, nnb);   // vertex ids + neighbour codes: one 256-bit gather
-                    else nverts = __ldcg(&TV(m, n));
-                    if (ow.x == key_k) verdict = V_MINE;            // already in my cavity
-                    else if (ow.x < key_k) verdict = V_LOST;        // a better point kills n (or n is dead)
-                    else if (ow.y == key_o) verdict = V_RING;       // already tested by me: not in conflict
-                    else {
-                        tests++;
-                        const typename Gm::Verts nv = Gm::load(m, nverts);
-                        if (Gm::conflict(cx, nv, p)) {
-                            if (ow.y < key_k) verdict = V_LOST;     // a better point keeps n in its outer ring
-                            else if (RED) { atomicMin(&OWK(m, n), key_k); verdict = V_NEW; }
-                            else {
-                                const int old = atomicMin(&OWK(m, n), key_k);
-                                verdict = old < key_k ? V_LOST : (old != key_k ? V_NEW : V_MINE);
-                            }
-                        } else {
-                            // outer-ring mark: fire and forget (RED, no round trip).  Rings may be shared; a better
-                            // point that KILLS n was either seen above or is caught by the ownership check of commit.
-                            atomicMin(&OWR(m, n), key_o);
-                            verdict = V_RING;
-                        }
-                    }
-                }
-                verdict = __shfl_sync(gmask, verdict, leader);
-                if (n >= 0) {
-                    if (verdict == V_LOST) lostLane = true;
-                    else if (verdict == V_RING) { pushB = true; fcode = t * 4 + i; ocode = code; }
-                    else if (verdict == V_NEW && lead) { pushK = true; newT = n; }
-                }
-                if (__any_sync(gmask, lostLane || (!EXACT && cx.failed))) { lost = true; break; }
-#else
                 const int j = base + gl;
                 bool pushK = false, pushB = false, lostLane = false;
                 int newT = 0, fcode = 0, ocode = 0;
@@ -313,28 +227,31 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
                     const int e = head + j / M;
                     const int i = j % M;
                     int t, code;
-                    if (STAGE && e < SK) { t = sk[e]; code = reinterpret_cast<const int *>(sn)[e * 4 + i]; }
+                    if (e < SK) { t = sk[e]; code = reinterpret_cast<const int *>(sn)[e * 4 + i]; }   // the cavity so far is staged in shared memory
                     else { t = sv.k[e]; code = TNI(m, t, i); }
                     if (code < 0) {
                         pushB = true; fcode = t * 4 + i; ocode = code;
                     } else {
                         const int n = code >> 2;
-                        // the owner pair and the record of n are independent gathers: issue both before looking at either
-                        const int2 ow = __ldcg(reinterpret_cast<const int2 *>(&OWK(m, n)));   // x = kill word, y = ring word
-                        int4 nverts;
-                        if (STAGE) load_rec_cg(m, n, nverts, nnb);   // vertex ids + neighbour codes: one 256-bit gather
-                        else nverts = __ldcg(&TV(m, n));
-                        if (ow.x == key_k) {
+                        const OwnBlk blk = load_blk(m, n);      // ownership words + sphere: ONE 256-bit gather
+                        if (VOR_SPEC) nnb = load_nbr(m.tet, n);
+                        if (blk.kill == key_k) {
                             // already in my cavity
-                        } else if (ow.x < key_k) {
+                        } else if (blk.kill < key_k) {
                             lostLane = true;           // a better point kills n (or n is dead)
-                        } else if (ow.y == key_o) {
+                        } else if (blk.ring == key_o) {
                             pushB = true; fcode = t * 4 + i; ocode = code;   // already tested by me: not in conflict
                         } else {
                             tests++;
-                            const typename Gm::Verts nv = Gm::load(m, nverts);
-                            if (Gm::conflict(cx, nv, p)) {
-                                if (ow.y < key_k) lostLane = true;   // a better point keeps n in its outer ring
+                            int conf = sphere_test(blk, rq);
+                            if (conf == 0) {
+                                atomicAdd(&m.cnt->sph_undecided, 1ULL);
+                                conf = conflict_slow<D, (EXACT != 0)>(m.pts, m.tet, m.cnt, n, p.x, p.y, pt_z<D>(p));
+                                if (conf == 2) { cx.failed = true; conf = 0; }
+                            }
+                            if (conf > 0) {
+                                if (!VOR_SPEC) nnb = load_nbr(m.tet, n);
+                                if (blk.ring < key_k) lostLane = true;   // a better point keeps n in its outer ring
                                 else if (RED) {
                                     atomicMin(&OWK(m, n), key_k);
                                     claim = n;
@@ -343,7 +260,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
                                     if (old < key_k) lostLane = true;
                                     else if (old != key_k) { pushK = true; newT = n; }   // first lane to claim it appends it
                                 }
-                            } else {
+                            } else if (!cx.failed) {
                                 // outer-ring mark: fire and forget (RED, no round trip).  Rings may be shared; a better
                                 // point that KILLS n was either seen above or is caught by the ownership check of commit.
                                 atomicMin(&OWR(m, n), key_o);
@@ -357,7 +274,6 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
                     const unsigned same = __match_any_sync(gmask, claim);
                     if (claim >= 0 && (__ffs(same) - 1) == (threadIdx.x & 31)) { pushK = true; newT = claim; }
                 }
-#endif
                 const unsigned mk = (__ballot_sync(gmask, pushK) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
                 const unsigned mb = (__ballot_sync(gmask, pushB) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
                 const int ck = __popc(mk), cb = __popc(mb);
@@ -379,7 +295,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
                 if (pushK) {
                     const int pos = nk + __popc(mk & lt);
                     sv.k[pos] = newT;
-                    if (STAGE && pos < SK) { sk[pos] = newT; sn[pos] = nnb; }
+                    if (pos < SK) { sk[pos] = newT; sn[pos] = nnb; }
                 }
                 if (pushB) { const int pos = nb + __popc(mb & lt); sv.f[pos] = fcode; sv.o[pos] = ocode; }
                 nk += ck;
@@ -418,57 +334,251 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
     }
 }
 
-// One group per attempt slot (grid = slots), or -- option "persist" -- resident warps that pull slots from per-SM
-// queues: SM i works through the i-th contiguous range of the Morton-ordered slots, so the simplices and vertices it
-// gathers in one round come from one compact region of the mesh (and of the store) instead of every 148th block of
-// it; the ranges of SMs that finish early are drained by the others.
-// The hot twin needs fewer registers than the kernel with the exact path: two-warp blocks at 56 registers (36 warps per
-// SM instead of 32) measured 88.7 vs 92.1 ms per 10M points; 48 registers spill too much (110 ms).
+// ------------------------------------------------------------------------------------------
+// hot attempt kernel: one warp per point, NO determinant code at all.
+// Everything it decides, it decides from the 32 B blocks (ownership words + certified sphere filter):
+//   locate   walk on the power distance pow(p, t) = |p - c_t|^2 - r_t^2.  The radical hyperplane of the circumspheres of two
+//            adjacent simplices is the hyperplane of their common facet, so "the neighbour across facet i has a smaller
+//            power" <=> "p lies beyond facet i": descending the power IS the visibility walk of the orientation
+//            predicate, evaluated from the cached spheres (lane i < M gathers the block and the neighbour codes of neighbour
+//            i: one round trip per step, steepest descent).  It stops at the first simplex whose sphere CERTAINLY
+//            contains p: any member of the conflict region will do, the flood finds the rest.  The float values only
+//            steer the walk; a walk that gets stuck (p within the filter's shell of a facet or a sphere, a duplicate
+//            point, a simplex without a filter) hands the point to the exact twin.
+//   flood    as attempt_one, but a test the sphere filter leaves undecided (~1e-5 of them) abandons the attempt and
+//            hands the point to the exact twin (slowFlag[v] = key base of this round; from the next round on this kernel
+//            appends the point's slot to the round's list of slots for the exact twin, k_attempt_slow).
+// With neither orient3d nor insphere in its call tree the kernel runs spill-free at 56 registers (116 needed before: the
+// version with the walk predicates inside moved 6x more local-memory than global-memory sectors, ncu round 2).
+// ------------------------------------------------------------------------------------------
 #ifndef VOR_HOT_BLOCK
 #define VOR_HOT_BLOCK 64
 #endif
 #ifndef VOR_HOT_REGS
 #define VOR_HOT_REGS 56
 #endif
-template <int EXACT> struct AttemptLaunch {
-    static constexpr int block = EXACT ? VOR_ATTEMPT_BLOCK : VOR_HOT_BLOCK;
-    static constexpr int regs = EXACT ? VOR_ATTEMPT_REGS : VOR_HOT_REGS;
-    static constexpr int minBlocks = (65536 / (regs * block)) > 32 ? 32 : (65536 / (regs * block));
-};
-template <int D, int G, int RED, int STAGE, int EXACT>
-__global__ void __launch_bounds__(AttemptLaunch<EXACT>::block, AttemptLaunch<EXACT>::minBlocks) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
-    // the cavity found so far, staged in shared memory: ids and neighbour codes of the first SK killed simplices, so a
-    // flood level starts from two shared-memory reads instead of two dependent L2 round trips (scratch, then record)
-    __shared__ int s_kid[AttemptLaunch<EXACT>::block / G][STAGE ? VOR_SK : 1];
-    __shared__ int4 s_knb[AttemptLaunch<EXACT>::block / G][STAGE ? VOR_SK : 1];
-    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;   // group = attempt slot
-    if (gid >= rsel.nsel) return;
-    attempt_one<D, G, RED, STAGE, EXACT>(A, rsel, gid, s_kid[threadIdx.x / G], s_knb[threadIdx.x / G]);
+#ifndef VOR_HOT_WALK
+#define VOR_HOT_WALK 48           // power-descent steps before the point goes to the exact twin
+#endif
+__device__ __forceinline__ double pow_mid(const OwnBlk &b, const RelPt &q) {
+    const double dx = q.x - (double)b.cx, dy = q.y - (double)b.cy, dz = q.z - (double)b.cz;
+    // a simplex without a filter (rout2 = inf) never attracts the walk
+    return (dx * dx + dy * dy + dz * dz) - 0.5 * ((double)b.rin2 + (double)b.rout2);
 }
+template <int D>
+__global__ void __launch_bounds__(VOR_HOT_BLOCK, (65536 / (VOR_HOT_REGS * VOR_HOT_BLOCK)) > 32 ? 32 : (65536 / (VOR_HOT_REGS * VOR_HOT_BLOCK)))
+k_attempt_hot(AttemptArgs<D> A, RoundSel rsel) {
+    constexpr int M = Dim<D>::M;
+    constexpr int SK = VOR_SK;
+    __shared__ int s_kid[VOR_HOT_BLOCK / 32][VOR_SK];
+    __shared__ int4 s_knb[VOR_HOT_BLOCK / 32][VOR_SK];
+    const Mesh<D> &m = A.m;
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int gl = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) m.cnt->sph_lo = m.cnt->ntets;   // k_spheres of the last round is done
+    if (slot >= rsel.nsel) return;
+    int *const sk = s_kid[threadIdx.x >> 5];
+    int4 *const sn = s_knb[threadIdx.x >> 5];
+    const int a = slot_entry(rsel, slot);
+    if (a >= rsel.nact) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }
+    const int v = A.act[a];
+    int s = m.seed[v];
+    if (s < 0) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }   // already inserted
+    const int fl = A.slowFlag[v];
+    if (fl != 0) {
+        // the exact twin's point: queue its slot for this round unless the flag is of this very round
+        if (gl == 0) {
+            A.scr.slotStatus[slot] = ST_LOST;
+            if (fl != A.keybase) A.scr.slowSlots[atomicAdd(&m.cnt->nslow, 1)] = slot;
+        }
+        return;
+    }
+    const RelPt rq = rel_pt(m, m.pts[v]);
+    const uint32_t q = bij_hash((uint32_t)slot, A.bits, A.salt);   // unique among the slots of this round
+    const int key_k = A.keybase | (int)(q << 1);
+    const int key_o = key_k | 1;
+    int nk = 0, nb = 0, big = -1;
+    unsigned steps = 0, tests = 0;
+    bool give = false;                     // hand the point to the exact twin
+    bool lost = false;
 
-constexpr int NQUEUE = 148;       // per-SM slot queues of the persistent kernels (one per SM of the B200)
-template <int D, int RED>
-__global__ void __launch_bounds__(VOR_ATTEMPT_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_ATTEMPT_BLOCK)) k_attempt_persist(AttemptArgs<D> A, RoundSel rsel, int *qctr) {
-    __shared__ int s_kid[VOR_ATTEMPT_BLOCK / 32][VOR_SK];
-    __shared__ int4 s_knb[VOR_ATTEMPT_BLOCK / 32][VOR_SK];
-    unsigned smid;
-    asm("mov.u32 %0, %%smid;" : "=r"(smid));
-    const int lane = threadIdx.x & 31;
-    const int per = (rsel.nsel + NQUEUE - 1) / NQUEUE;
-    for (int r = 0; r < NQUEUE; r++) {
-        const int qi = (int)((smid + (unsigned)r) % (unsigned)NQUEUE);
-        const int lo = qi * per, size = min(per, rsel.nsel - lo);
-        if (size <= 0) continue;
-        if (r > 0 && *(volatile int *)&qctr[qi] >= size) continue;     // drained
-        for (;;) {
-            int g = 0;
-            if (lane == 0) g = atomicAdd(&qctr[qi], 1);
-            g = __shfl_sync(0xffffffffu, g, 0);
-            if (g >= size) break;
-            attempt_one<D, 32, RED, VOR_ATT_STAGE, 1>(A, rsel, lo + g, s_kid[threadIdx.x / 32], s_knb[threadIdx.x / 32]);
-            __syncwarp();
+    // -- forwarding, then power descent to a simplex whose sphere certainly contains p
+    OwnBlk sb = load_blk(m, s);
+    int4 stn = load_nbr(m.tet, s);
+    while (sb.kill < 0) { s = ~sb.kill; sb = load_blk(m, s); stn = load_nbr(m.tet, s); }
+    while (sphere_test(sb, rq) <= 0) {
+        if (++steps > VOR_HOT_WALK) { give = true; break; }
+        const double pw0 = pow_mid(sb, rq);
+        double pw = INFINITY;
+        OwnBlk nbk = sb;
+        int4 nnn = stn;
+        const int code = gl < M ? get4(stn, gl) : -1;
+        if (code >= 0) {
+            nbk = load_blk(m, code >> 2);
+            nnn = load_nbr(m.tet, code >> 2);
+            pw = pow_mid(nbk, rq);
+        }
+        // steepest descent: lane with the smallest power among the M neighbours
+        double best = pw;
+        int who = gl;
+#pragma unroll
+        for (int d = 1; d < 4; d <<= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, d);
+            const int ow = __shfl_xor_sync(0xffffffffu, who, d);
+            if (ob < best || (ob == best && ow < who)) { best = ob; who = ow; }
+        }
+        best = __shfl_sync(0xffffffffu, best, 0);
+        who = __shfl_sync(0xffffffffu, who, 0);
+        if (!(best < pw0)) { give = true; break; }          // stuck: undecidable from the filters
+        s = __shfl_sync(0xffffffffu, code, who) >> 2;
+        sb.kill = __shfl_sync(0xffffffffu, nbk.kill, who); sb.ring = __shfl_sync(0xffffffffu, nbk.ring, who);
+        sb.cx = __shfl_sync(0xffffffffu, nbk.cx, who); sb.cy = __shfl_sync(0xffffffffu, nbk.cy, who); sb.cz = __shfl_sync(0xffffffffu, nbk.cz, who);
+        sb.rin2 = __shfl_sync(0xffffffffu, nbk.rin2, who); sb.rout2 = __shfl_sync(0xffffffffu, nbk.rout2, who);
+        stn.x = __shfl_sync(0xffffffffu, nnn.x, who); stn.y = __shfl_sync(0xffffffffu, nnn.y, who);
+        stn.z = __shfl_sync(0xffffffffu, nnn.z, who); stn.w = __shfl_sync(0xffffffffu, nnn.w, who);
+    }
+    if (!give) {
+        if (gl == 0 && steps) m.seed[v] = s;
+        // reservation of the first simplex: early out on the block in registers; what slips in later is caught by commit
+        if (sb.kill < key_k || sb.ring < key_k) lost = true;
+        else if (gl == 0) atomicMin(&OWK(m, s), key_k);
+    }
+    if (!give && !lost) {
+        tests = gl == 0 ? 1u : 0u;
+        ScrView sv = scr_view(A.scr, slot, -1);
+        if (gl == 0) { sv.k[0] = s; sk[0] = s; sn[0] = stn; }
+        __syncwarp();
+        nk = 1;
+        int head = 0;
+        while (head < nk && !lost && !give) {
+            const int tail = nk;
+            const int items = (tail - head) * M;
+            for (int base = 0; base < items; base += 32) {
+                const int j = base + gl;
+                bool pushB = false, lostLane = false, giveLane = false;
+                int fcode = 0, ocode = 0;
+                int claim = -1 - gl;       // simplex this lane wants to kill (unique dummy otherwise)
+                int4 nnb = make_int4(-1, -1, -1, -1);
+                if (j < items) {
+                    const int e = head + j / M;
+                    const int i = j % M;
+                    int t, code;
+                    if (e < SK) { t = sk[e]; code = reinterpret_cast<const int *>(sn)[e * 4 + i]; }   // the cavity so far is staged in shared memory
+                    else { t = sv.k[e]; code = TNI(m, t, i); }
+                    if (code < 0) {
+                        pushB = true; fcode = t * 4 + i; ocode = code;
+                    } else {
+                        const int n = code >> 2;
+                        const OwnBlk blk = load_blk(m, n);      // ownership words + sphere: ONE 256-bit gather
+                        if (VOR_SPEC) nnb = load_nbr(m.tet, n);
+                        if (blk.kill == key_k) {
+                            // already in my cavity
+                        } else if (blk.kill < key_k) {
+                            lostLane = true;           // a better point kills n (or n is dead)
+                        } else if (blk.ring == key_o) {
+                            pushB = true; fcode = t * 4 + i; ocode = code;   // already tested by me: not in conflict
+                        } else {
+                            tests++;
+                            const int conf = sphere_test(blk, rq);
+                            if (conf > 0) {
+                                if (!VOR_SPEC) nnb = load_nbr(m.tet, n);
+                                if (blk.ring < key_k) lostLane = true;   // a better point keeps n in its outer ring
+                                else { atomicMin(&OWK(m, n), key_k); claim = n; }
+                            } else if (conf < 0) {
+                                atomicMin(&OWR(m, n), key_o);            // outer-ring mark: fire and forget
+                                pushB = true; fcode = t * 4 + i; ocode = code;
+                            } else giveLane = true;                      // inside the filter's shell: the exact twin decides
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, giveLane)) { give = true; break; }
+                if (__any_sync(0xffffffffu, lostLane)) { lost = true; break; }
+                const unsigned same = __match_any_sync(0xffffffffu, claim);
+                const bool pushK = claim >= 0 && (__ffs(same) - 1) == gl;
+                const unsigned mk = __ballot_sync(0xffffffffu, pushK);
+                const unsigned mb = __ballot_sync(0xffffffffu, pushB);
+                const int ck = __popc(mk), cb = __popc(mb);
+                if (nk + ck > sv.capk || nb + cb > sv.capb) {
+                    // spill to an overflow slot (contiguous, much larger)
+                    if (big >= 0) { if (gl == 0) set_err(m.cnt, ERR_CAPACITY); lost = true; break; }
+                    if (gl == 0) big = atomicAdd(&m.cnt->nbig, 1);
+                    big = __shfl_sync(0xffffffffu, big, 0);
+                    if (big >= A.scr.nbig) { lost = true; break; }
+                    const ScrView bv = scr_view(A.scr, slot, big);
+                    for (int x = gl; x < nk; x += 32) bv.k[x] = sv.k[x];
+                    for (int x = gl; x < nb; x += 32) { bv.f[x] = sv.f[x]; bv.o[x] = sv.o[x]; }
+                    sv = bv;
+                    if (gl == 0) A.scr.slotBig[slot] = big;
+                    __syncwarp();
+                    if (nk + ck > sv.capk || nb + cb > sv.capb) { if (gl == 0) set_err(m.cnt, ERR_CAPACITY); lost = true; break; }
+                }
+                const unsigned lt = (1u << gl) - 1u;
+                if (pushK) {
+                    const int pos = nk + __popc(mk & lt);
+                    sv.k[pos] = claim;
+                    if (pos < SK) { sk[pos] = claim; sn[pos] = nnb; }
+                }
+                if (pushB) { const int pos = nb + __popc(mb & lt); sv.f[pos] = fcode; sv.o[pos] = ocode; }
+                nk += ck;
+                nb += cb;
+                __syncwarp();
+            }
+            head = tail;
         }
     }
+    const int status = (give || lost) ? ST_LOST : ST_OK;
+    if (gl == 0) {
+        if (give) {
+            // hand the point to the exact twin (from the next round on); marks left under this round's key are stale then
+            A.slowFlag[v] = A.keybase;
+            atomicAdd(&m.cnt->nflag_set, 1);
+        }
+        A.scr.slotStatus[slot] = status;
+        A.scr.slotNk[slot] = nk;
+        A.scr.slotNb[slot] = nb;
+        if (big < 0) A.scr.slotBig[slot] = -1;
+    }
+    if (A.stats) {
+        for (int d = 16; d > 0; d >>= 1) tests += __shfl_xor_sync(0xffffffffu, tests, d);
+        if (gl == 0) {
+            atomicAdd(&m.cnt->walk_steps, (unsigned long long)steps);
+            atomicAdd(&m.cnt->tests, (unsigned long long)tests);
+            atomicAdd(&m.cnt->attempts, 1ULL);
+            if (status != ST_OK) atomicAdd(&m.cnt->aborted, 1ULL);
+            else atomicAdd(&m.cnt->tests_ok, (unsigned long long)tests);
+        }
+    }
+}
+
+// the exact twin behind the hot kernel: the slots the hot kernel queued this round (points flagged in earlier rounds)
+template <int D, int RED>
+__global__ void __launch_bounds__(VOR_ATTEMPT_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_ATTEMPT_BLOCK)) k_attempt_slow(AttemptArgs<D> A, RoundSel rsel) {
+    __shared__ int s_kid[VOR_ATTEMPT_BLOCK / 32][VOR_SK];
+    __shared__ int4 s_knb[VOR_ATTEMPT_BLOCK / 32][VOR_SK];
+    const int n = min(A.m.cnt->nslow, A.scr.nslots);
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < n; idx += nwarps) {
+        attempt_one<D, 32, RED, 1>(A, rsel, A.scr.slowSlots[idx], s_kid[threadIdx.x >> 5], s_knb[threadIdx.x >> 5]);
+        __syncwarp();
+    }
+}
+
+// One group per attempt slot (grid = slots).  The hot twin needs fewer registers than the kernel with the exact path.
+template <int EXACT> struct AttemptLaunch {
+    static constexpr int block = VOR_ATTEMPT_BLOCK;
+    static constexpr int regs = VOR_ATTEMPT_REGS;
+    static constexpr int minBlocks = (65536 / (regs * block)) > 32 ? 32 : (65536 / (regs * block));
+};
+template <int D, int G, int RED, int EXACT>
+__global__ void __launch_bounds__(AttemptLaunch<EXACT>::block, AttemptLaunch<EXACT>::minBlocks) k_attempt_coop(AttemptArgs<D> A, RoundSel rsel) {
+    // the cavity found so far, staged in shared memory: ids and neighbour codes of the first SK killed simplices, so that a
+    // flood level starts from shared memory instead of two dependent round trips (scratch, then record)
+    __shared__ int s_kid[AttemptLaunch<EXACT>::block / G][VOR_SK];
+    __shared__ int4 s_knb[AttemptLaunch<EXACT>::block / G][VOR_SK];
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;   // group = attempt slot
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.m.cnt->sph_lo = A.m.cnt->ntets;   // k_spheres of the last round is done
+    if (gid >= rsel.nsel) return;
+    attempt_one<D, G, RED, EXACT>(A, rsel, gid, s_kid[threadIdx.x / G], s_knb[threadIdx.x / G]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -562,7 +672,7 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
     const int gl = threadIdx.x & (G - 1);
     const unsigned gmask = group_mask<G>();
     const int gshift = (threadIdx.x & 31) & ~(G - 1);
-    if (gid == 0 && gl == 0) m.cnt->nbig = 0;           // overflow slots are per round (attempt is over)
+    if (gid == 0 && gl == 0) { m.cnt->nbig = 0; m.cnt->nslow = 0; }   // overflow slots and the exact twin's queue are per round (attempt is over)
     if (gid >= rsel.nsel) return;
     const int slot = gid;
     if (A.scr.slotStatus[slot] != ST_OK) return;
@@ -606,14 +716,7 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
         }
     }
     if (__any_sync(gmask, bad)) return;
-    // Slot recycling (fast path): new simplex j < nk takes the slot of killed simplex j, only the surplus comes from
-    // the bump allocator.  The store stays compact (no dead slots: 4x smaller footprint at 10M points), a new simplex
-    // lies where the simplices it replaces lay (spatial locality of the store is inherited, not diluted by time), and
-    // a pending point whose seed was killed finds a live simplex of the right neighbourhood in the same slot.
-    // The kill word of a recycled slot keeps this winner's key: every other contender of this round has a worse key
-    // on it and loses; from the next round on it is a stale mark (epochs count down).
-    const bool reuse = fast && !(stats & 4);
-    const int nfresh = reuse ? max(nb - nk, 0) : nb;
+    const int nfresh = nb;
     int base = 0;
     if (gl == 0) base = atomicAdd(&m.cnt->ntets, nfresh);
     base = __shfl_sync(gmask, base, gshift);
@@ -621,7 +724,7 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
         // no room: leave the mesh untouched (the point stays pending), retire the part of the block that exists and
         // tell the host to grow the store
         for (int j = gl; j < nfresh; j += G)
-            if (base + j < m.cap) OWK(m, base + j) = -1;
+            if (base + j < m.cap) store_rec(m, base + j, make_int4(-1, -1, -1, -1), make_int4(-1, -1, -1, -1));   // k_spheres marks it dead
         if (gl == 0) m.cnt->oom_soft = 1;
         return;
     }
@@ -629,9 +732,7 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
     if (!fast) {
         commit_global<D, G>(m, sv, nk, nb, v, base, gl, gmask);
     } else {
-        const int nreuse = reuse ? min(nk, nb) : 0;
-        auto slot_of = [&](int j) -> int { return j < nreuse ? ids[j] : base + (j - nreuse); };
-        first = slot_of(0);
+        auto slot_of = [&](int j) -> int { return base + j; };
         // id -> local index (open addressing, at most 3/8 full)
         for (int e = gl; e < nk; e += G) {
             unsigned h = ((unsigned)ids[e] * 2654435761u) >> 25;
@@ -698,12 +799,12 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
                     cur = ln; enter = jb; exitf = y;
                 }
             }
-            store_rec(m, T, verts, nbr);
+            store_rec(m, T, verts, nbr);   // its ownership + sphere block is written by k_spheres, next in the stream
             if (outer >= 0) TNI(m, outer >> 2, outer & 3) = T * 4 + i;
         }
-        // phase C: killed simplices whose slot is not recycled die; a dead simplex forwards to a new simplex on one
-        // of its own boundary facets (interior simplices: to the first new simplex)
-        for (int e = gl + nreuse; e < nk; e += G) OWK(m, ids[e]) = ~slot_of(fw[e]);
+        // phase C: the killed simplices die; a dead simplex forwards to a new simplex on one of its own boundary
+        // facets (interior simplices: to the first new simplex)
+        for (int e = gl; e < nk; e += G) OWK(m, ids[e]) = ~slot_of(fw[e]);
     }
     if (gl == 0) {
         m.ptTet[v] = first;
@@ -714,6 +815,27 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
             atomicAdd(&m.cnt->killed, (unsigned long long)nk);
             atomicAdd(&m.cnt->created, (unsigned long long)nb);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// spheres: ownership words (free) + certified circumsphere filter (sphere.cuh) of the simplices created by the commit
+// kernel just before it in the stream -- the slots [cnt->sph_lo, cnt->ntets) of the bump allocator.  One thread per new
+// simplex: its record and block are contiguous (coalesced), the new simplices of one cavity are neighbours in the store
+// and share their vertices (L1 hits).  Kept out of the commit kernel: the ~150 FP64 operations of a sphere would cost the
+// ridge pivots their registers (measured: commit 43 -> 132 ms per 10M points when fused).  cnt->sph_lo is advanced by the
+// first thread of the next attempt kernel (the allocator does not move during an attempt kernel).
+// ------------------------------------------------------------------------------------------
+#ifndef VOR_SPH_MINB
+#define VOR_SPH_MINB 2
+#endif
+template <int D>
+__global__ void __launch_bounds__(256, VOR_SPH_MINB) k_spheres(Mesh<D> m) {
+    const int lo = m.cnt->sph_lo, hi = min(m.cnt->ntets, m.cap);
+    for (int t = lo + blockIdx.x * blockDim.x + threadIdx.x; t < hi; t += gridDim.x * blockDim.x) {
+        const int4 tv = TV(m, t);
+        if (tv.x < 0) { OWK(m, t) = -1; continue; }              // slot retired by a winner that found no room: dead
+        store_blk(m, t, sphere_of(m, tv));
     }
 }
 

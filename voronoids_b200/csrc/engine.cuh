@@ -38,20 +38,13 @@ struct EngineOptions {
     int verbose = 0;
     int profile = 0;             // CUDA-event time per kernel class (attempt / check / retri / setup)
     int coop = 1;                // lane-group cooperative kernels (GPU build); 0 = thread-per-point bodies
-    int group = 32;              // lanes per point: 32 (a warp per point, fastest at every round size measured) or 8;
-                                 // 0 = 32 for rounds up to coop_switch points, group_big above
-    int coop_switch = 12288;
-    int group_big = 8;
     int bulk_locate = 1;         // locate every point of a stage at its start (thread per point) instead of in its first attempt
     int select_mode = 1;         // 1 = stratified selection along the Morton-ordered active list, 0 = random subset
     int rounds_per_sync = 8;     // rounds launched back to back between two host read-backs of the counters
-    int prewalk = 0;             // walk kernel in front of the attempt kernel: 4 = 4 lanes per point, 1 = thread per point, 0 = off
     int commit_smem = 1;         // commit retriangulates cavities staged in shared memory (0 = through the global store)
     int split_exact = 1;         // attempt kernel as a hot twin without exact predicates + an exact twin for the points it flags
-    int stage_below = 0;         // rounds with fewer attempts run the attempt kernel that stages the cavity in shared memory
-    int persist = 0;             // rounds of at least this many attempts run the persistent attempt kernel (0 = never)
-    int recycle = 0;             // winners write new simplices into the slots of the simplices they kill (commit_smem path)
     int red = 1;                 // kill reservation as a fire-and-forget reduction (match.any dedup), see k_attempt_coop
+    double compact_frac = 0.85;  // the active list is compacted (at a host read-back) once fewer than this fraction of it is pending
     double tet_factor = 0.0;     // simplex slots per vertex (0 = default: 31 in 3D, 7.5 in 2D)
 };
 
@@ -63,19 +56,13 @@ inline void options_from_env(EngineOptions &o) {
     if (const char *e = getenv("VOR_STATS")) o.stats = atoi(e);
     if (const char *e = getenv("VOR_VERBOSE")) o.verbose = atoi(e);
     if (const char *e = getenv("VOR_TET_FACTOR")) o.tet_factor = atof(e);
+    if (const char *e = getenv("VOR_COMPACT_FRAC")) o.compact_frac = atof(e);
     if (const char *e = getenv("VOR_COOP")) o.coop = atoi(e);
-    if (const char *e = getenv("VOR_GROUP")) o.group = atoi(e);
-    if (const char *e = getenv("VOR_GROUP_BIG")) o.group_big = atoi(e);
-    if (const char *e = getenv("VOR_COOP_SWITCH")) o.coop_switch = atoi(e);
     if (const char *e = getenv("VOR_ROUNDS_PER_SYNC")) o.rounds_per_sync = atoi(e);
     if (const char *e = getenv("VOR_SELECT_MODE")) o.select_mode = atoi(e);
     if (const char *e = getenv("VOR_BULK_LOCATE")) o.bulk_locate = atoi(e);
-    if (const char *e = getenv("VOR_PREWALK")) o.prewalk = atoi(e);
     if (const char *e = getenv("VOR_RED")) o.red = atoi(e);
     if (const char *e = getenv("VOR_COMMIT_SMEM")) o.commit_smem = atoi(e);
-    if (const char *e = getenv("VOR_RECYCLE")) o.recycle = atoi(e);
-    if (const char *e = getenv("VOR_PERSIST")) o.persist = atoi(e);
-    if (const char *e = getenv("VOR_STAGE_BELOW")) o.stage_below = atoi(e);
     if (const char *e = getenv("VOR_SPLIT_EXACT")) o.split_exact = atoi(e);
     if (const char *e = getenv("VOR_CAPK")) { o.capk = atoi(e); o.capb = 2 * o.capk + 4; }
 }
@@ -112,7 +99,8 @@ template <int D> class Engine {
     // scratch
     Scratch scr{};
     bool slowPending = false, splitDisabled = false;
-    int *act = nullptr, *act2 = nullptr, *blockCnt = nullptr, *qctr = nullptr, *slowFlag = nullptr;
+    int flagPending = 0;
+    int *act = nullptr, *act2 = nullptr, *blockCnt = nullptr, *slowFlag = nullptr;
     long long *d_misc = nullptr;
     long long insertedTotal = 0;
     long long remainingInCall = 0;   // points of the current insert call not inserted yet
@@ -137,9 +125,9 @@ template <int D> class Engine {
         prof.on = opt.profile != 0;
     }
     ~Engine() {
-        be::dfree(mesh.pts); be::dfree(mesh.tet); be::dfree(mesh.owner); be::dfree(mesh.seed);
+        be::dfree(mesh.pts); be::dfree(mesh.tet); if (!VOR_INTERLEAVE) be::dfree(mesh.owner); be::dfree(mesh.seed);
         be::dfree(mesh.ptTet); be::dfree(mesh.cnt); be::dfree(inputIdx); be::dfree(vidOfInput); be::dfree(keysAll);
-        be::dfree(d_boxLo); be::dfree(d_boxHi); be::dfree(act); be::dfree(act2); be::dfree(blockCnt); be::dfree(d_edges); be::dfree(qctr); be::dfree(slowFlag);
+        be::dfree(d_boxLo); be::dfree(d_boxHi); be::dfree(act); be::dfree(act2); be::dfree(blockCnt); be::dfree(d_edges); be::dfree(slowFlag);
         free_scratch();
         be::dfree(d_misc);
         be::hfree_pinned(hcnt);
@@ -196,16 +184,19 @@ template <int D> class Engine {
         long long nc = std::max(need, (long long)mesh.cap + mesh.cap / 2);
         nc = std::min(nc, (1LL << 29) - 1);
         const int old = mesh.cap;
-        grow(mesh.tet, 2 * (size_t)old, 2 * (size_t)nc);
-        grow(mesh.owner, 2 * (size_t)old, 2 * (size_t)nc);       // kill word + ring word per simplex
-        fill_i(mesh.owner + 2 * (size_t)old, OWNER_FREE, 2 * (size_t)(nc - old));
+        // record + ownership / sphere block per simplex (sphere.cuh: one 64 B line when interleaved); a slot is written whole
+        // by the round that creates the simplex (store_rec, store_blk) and nothing reads it before, so new capacity needs
+        // no initialisation
+        grow(mesh.tet, REC4 * (size_t)old, REC4 * (size_t)nc);
+        if (VOR_INTERLEAVE) mesh.owner = reinterpret_cast<int *>(mesh.tet);
+        else grow(mesh.owner, OWS * (size_t)old, OWS * (size_t)nc);
         mesh.cap = (int)nc;
         if (opt.verbose) fprintf(stderr, "[vor] simplex capacity -> %lld\n", nc);
     }
     void free_scratch() {
         be::dfree(scr.killed); be::dfree(scr.bfacet); be::dfree(scr.bouter); be::dfree(scr.slotAct); be::dfree(scr.slotNk);
         be::dfree(scr.slotNb); be::dfree(scr.slotStatus); be::dfree(scr.slotBig); be::dfree(scr.bigK); be::dfree(scr.bigF);
-        be::dfree(scr.bigO); be::dfree(scr.winners); be::dfree(scr.wbase);
+        be::dfree(scr.bigO); be::dfree(scr.winners); be::dfree(scr.wbase); be::dfree(scr.slowSlots);
         scr = Scratch{};
     }
     void ensure_scratch(int nslots) {
@@ -224,6 +215,7 @@ template <int D> class Engine {
         scr.slotBig = (int *)be::dmalloc(sizeof(int) * (size_t)nslots);
         scr.winners = (int *)be::dmalloc(sizeof(int) * (size_t)nslots);
         scr.wbase = (int *)be::dmalloc(sizeof(int) * (size_t)nslots);
+        scr.slowSlots = (int *)be::dmalloc(sizeof(int) * (size_t)nslots);
         scr.nbig = opt.big_slots;
         scr.bigCapK = opt.big_capk;
         scr.bigCapB = 2 * opt.big_capk + 4;
@@ -367,14 +359,53 @@ template <int D> class Engine {
             rtet[2 * (size_t)s] = v;
             rtet[2 * (size_t)s + 1] = int4{-1, -1, -1, -1};
         }
+        // origin of the float sphere centres: centre of the union of the sets' boxes; every legal query point lies
+        // inside a super simplex, so |p - origin| <= reach and fl(p - origin) is off by at most EPS * reach per axis
+        {
+            double ulo[3] = {INFINITY, INFINITY, INFINITY}, uhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int s = 0; s < nsets; s++)
+                for (int k = 0; k < D; k++) {
+                    ulo[k] = std::fmin(ulo[k], boxLo[(size_t)s * D + k]);
+                    uhi[k] = std::fmax(uhi[k], boxHi[(size_t)s * D + k]);
+                }
+            double org[3] = {0.0, 0.0, 0.0}, reach = 0.0;
+            for (int k = 0; k < D; k++) org[k] = 0.5 * (ulo[k] + uhi[k]);
+            for (int s = 0; s < nsets; s++)
+                for (int j = 0; j < M; j++) {
+                    double d1 = 0.0;
+                    for (int k = 0; k < D; k++) d1 += std::fabs(superXYZ[((size_t)s * M + j) * D + k] - org[k]);
+                    reach = std::fmax(reach, d1);
+                }
+            mesh.sref.ox = org[0]; mesh.sref.oy = org[1]; mesh.sref.oz = org[2];
+            mesh.sref.qerr = 8.0 * SPH_EPS * reach;
+        }
+        std::vector<int> rblk((size_t)8 * nsets);
+        for (int s = 0; s < nsets; s++) {
+            const SphereBlk sb = sphere_host(&sp[(size_t)s * M]);
+            int *w = &rblk[(size_t)8 * s];
+            w[0] = OWNER_FREE; w[1] = OWNER_FREE; w[2] = f2i(sb.cx); w[3] = f2i(sb.cy); w[4] = f2i(sb.cz); w[5] = f2i(sb.rin2); w[6] = f2i(sb.rout2); w[7] = 0;
+        }
+        std::vector<int4> rline;   // must outlive the asynchronous copy: synchronised at the end of create()
+        if (VOR_INTERLEAVE) {
+            rline.resize((size_t)REC4 * nsets);
+            for (int s = 0; s < nsets; s++) {
+                memcpy(&rline[(size_t)REC4 * s], &rblk[(size_t)8 * s], sizeof(int) * 8);
+                rline[(size_t)REC4 * s + TVO4] = rtet[2 * (size_t)s];
+                rline[(size_t)REC4 * s + TVO4 + 1] = rtet[2 * (size_t)s + 1];
+            }
+            be::h2d(mesh.tet, rline.data(), sizeof(int4) * rline.size(), stream);
+        } else {
+            be::h2d(mesh.owner, rblk.data(), sizeof(int) * rblk.size(), stream);
+            be::h2d(mesh.tet, rtet.data(), sizeof(int4) * 2 * (size_t)nsets, stream);
+        }
         be::h2d(mesh.pts, sp.data(), sizeof(Pt) * (size_t)nsuper, stream);
-        be::h2d(mesh.tet, rtet.data(), sizeof(int4) * 2 * (size_t)nsets, stream);
         be::h2d(mesh.seed, rseed.data(), sizeof(int) * (size_t)nsuper, stream);
         fill_i(mesh.ptTet, 0, (size_t)nsuper);
         fill_i(inputIdx, -1, (size_t)nsuper);
         nv = nsuper;
         memset(hcnt, 0, sizeof(Counters));
         hcnt->ntets = nsets;
+        hcnt->sph_lo = nsets;
         push_counters();
         be::sync(stream);
     }
@@ -382,6 +413,8 @@ template <int D> class Engine {
     static void set_host_pt(double2 &p, const double *s) { p.x = s[0]; p.y = s[1]; }
     static int orient_host(PredCtx &cx, const double4 *p) { return orient3d(cx, p[0], p[1], p[2], p[3]); }
     static int orient_host(PredCtx &cx, const double2 *p) { return orient2d(cx, p[0], p[1], p[2]); }
+    SphereBlk sphere_host(const double4 *p) const { return sphere_make(p[0], p[1], p[2], p[3], mesh.sref); }
+    SphereBlk sphere_host(const double2 *p) const { return sphere_make(p[0], p[1], p[2], mesh.sref); }
 
     // ------------------------------------------------------------------ insertion  (add_points_to_tree)
     // d_in: n x D points on the device; h_setOff: nsets+1 offsets into d_in (nullptr => one set)
@@ -506,49 +539,42 @@ template <int D> class Engine {
         const double byRemaining = (double)remainingInCall * (newPerPoint * 0.85) + 65536.0;
         return (long long)std::min(byRounds, byRemaining) + 4096;
     }
-    template <int G> void launch_round(const AttemptArgs<D> &aa, const CheckArgs<D> &ca, const RoundSel &sel) {
+    template <int G> void launch_round(const AttemptArgs<D> &aa, const CheckArgs<D> &ca, const RoundSel &sel, bool slowNow) {
         const unsigned grid = (unsigned)(((long long)sel.nsel * G + VOR_COOP_BLOCK - 1) / VOR_COOP_BLOCK);
         const unsigned agrid = (unsigned)(((long long)sel.nsel * G + VOR_ATTEMPT_BLOCK - 1) / VOR_ATTEMPT_BLOCK);
         prof.start(0, stream);
-        if (opt.prewalk == 4) { k_walk_coop<D, 4><<<(unsigned)(((long long)sel.nsel * 4 + 127) / 128), 128, 0, stream>>>(aa, sel); be::g_launches++; }
-        else if (opt.prewalk == 1) { k_walk_coop<D, 1><<<(unsigned)((sel.nsel + 127) / 128), 128, 0, stream>>>(aa, sel); be::g_launches++; }
-        bool launched = false;
-        if constexpr (G == 32) {
-            if (opt.persist && sel.nsel >= opt.persist) {
-                // resident warps pulling slots from per-SM queues (contiguous slot range per SM)
-                if (!qctr) qctr = (int *)be::dmalloc(sizeof(int) * 256);
-                be::dmemset(qctr, 0, sizeof(int) * 256, stream);
-                const unsigned pgrid = 148u * (unsigned)std::min(32, 65536 / (VOR_ATTEMPT_REGS * VOR_ATTEMPT_BLOCK));
-                if (opt.red) k_attempt_persist<D, 1><<<pgrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel, qctr);
-                else k_attempt_persist<D, 0><<<pgrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel, qctr);
-                launched = true;
-            } else if (opt.red) {
-                if (sel.nsel < opt.stage_below) k_attempt_coop<D, G, 1, 1, 1><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel);
-                else if (aa.slowFlag) {
-                    // hot twin without the exact predicates in its call tree; while flagged points are pending (host
-                    // knowledge, one read-back old) the exact twin follows and attempts only those
-                    const unsigned hgrid = (unsigned)(((long long)sel.nsel * G + VOR_HOT_BLOCK - 1) / VOR_HOT_BLOCK);
-                    k_attempt_coop<D, G, 1, 0, 0><<<hgrid, VOR_HOT_BLOCK, 0, stream>>>(aa, sel);
-                    if (slowPending) {
-                        AttemptArgs<D> as = aa;
-                        as.thr = 2u;
-                        k_attempt_coop<D, G, 1, 0, 1><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(as, sel);
-                        be::g_launches++;
-                    }
-                } else k_attempt_coop<D, G, 1, 0, 1><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel);
-                launched = true;
+        if (opt.red && aa.slowFlag) {
+            // hot twin without the exact predicates in its call tree; while flagged points are pending (host
+            // knowledge, one read-back old) the exact twin follows and attempts only those
+            const unsigned hgrid = (unsigned)(((long long)sel.nsel * G + VOR_HOT_BLOCK - 1) / VOR_HOT_BLOCK);
+            k_attempt_hot<D><<<hgrid, VOR_HOT_BLOCK, 0, stream>>>(aa, sel);
+            if (slowNow) {
+                // the slots the hot kernel queued (points it flagged in earlier rounds); a small grid-stride launch
+                AttemptArgs<D> as = aa;
+                as.thr = 2u;
+                k_attempt_slow<D, 1><<<(unsigned)std::min<long long>(agrid, 148LL * 8), VOR_ATTEMPT_BLOCK, 0, stream>>>(as, sel);
+                be::g_launches++;
             }
-        }
-        if (!launched) {
+        } else if (opt.red) {
+            k_attempt_coop<D, G, 1, 1><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(aa, sel);
+        } else {
             AttemptArgs<D> af = aa;
             af.slowFlag = nullptr;
-            k_attempt_coop<D, G, 0, VOR_ATT_STAGE, 1><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(af, sel);
+            k_attempt_coop<D, G, 0, 1><<<agrid, VOR_ATTEMPT_BLOCK, 0, stream>>>(af, sel);
         }
         prof.stop(stream);
         prof.start(2, stream);
-        k_commit_coop<D, G><<<grid, VOR_COOP_BLOCK, 0, stream>>>(ca, act, sel, (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2) | (opt.recycle ? 0 : 4));
+        k_commit_coop<D, G><<<grid, VOR_COOP_BLOCK, 0, stream>>>(ca, act, sel, (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2));
         prof.stop(stream);
-        be::g_launches += 2;
+        prof.start(1, stream);
+        {
+            // new simplices of the round: at most ~36 per attempted point; grid-stride over whatever the allocator handed out
+            const long long want = ((long long)sel.nsel * (D == 3 ? 36 : 9) + 255) / 256;
+            k_spheres<D><<<(unsigned)std::max(1LL, std::min(want, 148LL * 16)), 256, 0, stream>>>(mesh);
+        }
+        prof.stop(stream);
+        be::g_launches += 3;
+        be::check_launch("round kernels");
     }
     void run_stage_pipelined(int lo, int hi) {
         const int total = hi - lo;
@@ -588,15 +614,20 @@ template <int D> class Engine {
                 const bool split = opt.split_exact && !splitDisabled;
                 AttemptArgs<D> aa{mesh, scr, act, bits, roundSalt, 0u, stride, sel.offset, keybase, opt.stats, split ? slowFlag : nullptr};
                 CheckArgs<D> ca{mesh, scr, bits, roundSalt, keybase, split ? slowFlag : nullptr};
-                const int G = opt.group ? opt.group : (nsel > opt.coop_switch ? opt.group_big : 32);
-                if (G == 8) launch_round<8>(aa, ca, sel); else launch_round<32>(aa, ca, sel);
+                // the exact twin is pure latency for a handful of points (~26 us per launch): it runs once per batch of
+                // rounds, and in every round once the flagged points are most of what is left of the stage
+                const bool slowNow = slowPending && (r == R - 1 || 4LL * flagPending >= (long long)pending);
+                launch_round<32>(aa, ca, sel, slowNow);
                 epoch--;
                 rs.rounds++;
             }
             pull_counters();
             check_device_error("round");
             slowPending = hcnt->nflag_set > hcnt->nflag_done;
-            if (hcnt->nflag_set > 512) splitDisabled = true;
+            flagPending = hcnt->nflag_set - hcnt->nflag_done;
+            // an input that keeps leaving the filters (near-degenerate: the jittered lattice) is better off with the one
+            // kernel that has the exact path inside
+            if ((long long)hcnt->nflag_set > 512 + insertedTotal / 32) splitDisabled = true;
             const long long done = (long long)(win_total() - win0) + (long long)(hcnt->ndup - dup0);
             const int newPending = total - (int)done;
             insertedTotal += (long long)(pending - newPending);
@@ -608,7 +639,10 @@ template <int D> class Engine {
                 // some winners found no room: retire the slots handed out beyond the old capacity and grow
                 const int oldcap = mesh.cap;
                 ensure_simplices((long long)hcnt->ntets + batch_margin(R, nsel, newPerPoint));
-                if (hcnt->ntets > oldcap) fill_i(mesh.owner + 2 * (size_t)oldcap, -1, 2 * (size_t)(std::min(hcnt->ntets, mesh.cap) - oldcap));
+                if (hcnt->ntets > oldcap) {
+                    MarkDeadArgs md{mesh.owner, oldcap};
+                    VOR_LAUNCH(MarkDeadArgs, mark_dead_body, std::min(hcnt->ntets, mesh.cap) - oldcap, md, stream);
+                }
                 hcnt->oom_soft = 0;
                 be::h2d(&mesh.cnt->oom_soft, &hcnt->oom_soft, sizeof(int), stream);
             }
@@ -618,12 +652,12 @@ template <int D> class Engine {
             if (opt.verbose > 2) {
                 int f[8];
                 validate(f);
-                if (f[0] | f[1] | f[2] | f[3] | f[4]) {
+                if (f[0] | f[1] | f[2] | f[3] | f[4] | f[5]) {
                     fprintf(stderr, "[vor] VALIDATION FAILED after round %llu: %d %d %d %d %d\n", rs.rounds, f[0], f[1], f[2], f[3], f[4]);
                     fail(ERR_CUDA, "debug validation failed");
                 }
             }
-            if (pending > 0 && nact > 4096 && pending < nact / 2) {
+            if (pending > 0 && nact > 4096 && (double)pending < opt.compact_frac * (double)nact) {
                 nact = compact_active(nact);
                 if (nact != pending) fail(ERR_CUDA, "active list compaction lost points");
             }
@@ -699,7 +733,7 @@ template <int D> class Engine {
             if (opt.verbose > 2) {
                 int f[8];
                 validate(f);
-                if (f[0] | f[1] | f[2] | f[3] | f[4]) {
+                if (f[0] | f[1] | f[2] | f[3] | f[4] | f[5]) {
                     fprintf(stderr, "[vor] VALIDATION FAILED after round %llu: %d %d %d %d %d\n", rs.rounds, f[0], f[1], f[2], f[3], f[4]);
                     fail(ERR_CUDA, "debug validation failed");
                 }
@@ -707,7 +741,7 @@ template <int D> class Engine {
             if (nw + dropped == 0) {
                 if (++stall > 64) fail(ERR_WALK, "no progress in 64 consecutive rounds");
             } else stall = 0;
-            if (pending > 0 && nact > 4096 && pending < nact / 2) {
+            if (pending > 0 && nact > 4096 && (double)pending < opt.compact_frac * (double)nact) {
                 nact = compact_active(nact);
                 if (nact != pending) fail(ERR_CUDA, "active list compaction lost points");
             }

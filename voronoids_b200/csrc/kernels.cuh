@@ -15,11 +15,14 @@
 //   tet[2t+1] int4 neighbour codes: (neighbour << 2 | slot in neighbour that    } testing a simplex also brings its
 //             points back), -1 = outside the super simplex; slot i is opposite  } adjacency into L1/L2 for the next
 //             vertex i.  The reference keeps an unordered Vec (delaunay_tree.rs:15).   BFS level / walk step
-//   owner[2t]   "kill word"  >= 0: smallest key of the points that want to KILL t this round (OWNER_FREE when untouched)
+//   owner[8t..8t+7]  one 32 B block per simplex (sphere.cuh): ownership words + certified circumsphere filter, so that
+//               ONE 256-bit gather decides a conflict test (the reference caches centre/radius too, delaunay_tree.rs:11-16)
+//   owner[8t]   "kill word"  >= 0: smallest key of the points that want to KILL t this round (OWNER_FREE when untouched)
 //               <  0: simplex is dead, ~owner = a simplex created by the insertion that killed it (forwarding)
-//   owner[2t+1] "ring word"  smallest key of the points that have t in the OUTER RING of their cavity this round.
+//   owner[8t+1] "ring word"  smallest key of the points that have t in the OUTER RING of their cavity this round.
 //               Two winners may share an outer-ring simplex (they patch different neighbour slots of it); only
 //               kill/kill and kill/ring overlaps exclude each other, and exactly the point with the worse key loses.
+//   owner[8t+2..6]  float centre (relative to Mesh::sref origin), rin2, rout2
 //   seed[v]   pending point: a simplex to start its walk from; -1 once inserted
 //   ptTet[v]  a simplex created by v's insertion (seed for later points near v)
 //
@@ -36,6 +39,7 @@
 // conflict region of one is unchanged by the other (new circumspheres lie inside the union of the two old ones).
 #pragma once
 #include "predicates.cuh"
+#include "sphere.cuh"
 
 namespace vor {
 
@@ -46,19 +50,20 @@ template <> struct Dim<2> { using Pt = double2; static constexpr int M = 3; };
 template <int D> struct Mesh {
     typename Dim<D>::Pt *pts;
     int4 *tet;    // interleaved records: tet[2t] = vertex ids, tet[2t+1] = neighbour codes (one 32 B sector per simplex)
-    int *owner;   // 2 words per simplex: kill word, ring word (see above)
+    int *owner;   // OWS = 8 words per simplex: kill word, ring word, sphere filter (see above, sphere.cuh)
     int *seed;
     int *ptTet;
     Counters *cnt;
     int cap;      // simplex slots allocated
     int nsuper;   // vertices [0, nsuper) are super vertices
+    SphereRef sref;   // origin of the float centres + query rounding allowance
 };
 
-template <int D> VOR_HD int &OWK(const Mesh<D> &m, int t) { return m.owner[2 * (size_t)t]; }       // kill word / dead + forwarding
-template <int D> VOR_HD int &OWR(const Mesh<D> &m, int t) { return m.owner[2 * (size_t)t + 1]; }   // ring word
-template <int D> VOR_HD int4 &TV(const Mesh<D> &m, int t) { return m.tet[2 * (size_t)t]; }
-template <int D> VOR_HD int4 &TN(const Mesh<D> &m, int t) { return m.tet[2 * (size_t)t + 1]; }
-template <int D> VOR_HD int &TNI(const Mesh<D> &m, int t, int i) { return reinterpret_cast<int *>(m.tet)[8 * (size_t)t + 4 + i]; }
+template <int D> VOR_HD int &OWK(const Mesh<D> &m, int t) { return m.owner[OWS * (size_t)t]; }       // kill word / dead + forwarding
+template <int D> VOR_HD int &OWR(const Mesh<D> &m, int t) { return m.owner[OWS * (size_t)t + 1]; }   // ring word
+template <int D> VOR_HD int4 &TV(const Mesh<D> &m, int t) { return m.tet[REC4 * (size_t)t + TVO4]; }
+template <int D> VOR_HD int4 &TN(const Mesh<D> &m, int t) { return m.tet[REC4 * (size_t)t + TVO4 + 1]; }
+template <int D> VOR_HD int &TNI(const Mesh<D> &m, int t, int i) { return reinterpret_cast<int *>(m.tet)[4 * (REC4 * (size_t)t + TVO4) + 4 + i]; }
 
 // One simplex record (vertex ids + neighbour codes, one 32 B sector) or one 3D vertex (double4, one sector) moves with
 // ONE 256-bit instruction (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256).  Measured on the B200 (tools/micro/gather_bench.cu):
@@ -69,7 +74,7 @@ template <int D> VOR_HD void load_rec(const Mesh<D> &m, int t, int4 &tv, int4 &t
 #ifdef __CUDA_ARCH__
     asm volatile("ld.global.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(tv.x), "=r"(tv.y), "=r"(tv.z), "=r"(tv.w), "=r"(tn.x), "=r"(tn.y), "=r"(tn.z), "=r"(tn.w)
-                 : "l"(m.tet + 2 * (size_t)t));
+                 : "l"(m.tet + REC4 * (size_t)t + TVO4));
 #else
     tv = TV(m, t); tn = TN(m, t);
 #endif
@@ -78,7 +83,7 @@ template <int D> VOR_HD void load_rec_cg(const Mesh<D> &m, int t, int4 &tv, int4
 #ifdef __CUDA_ARCH__
     asm volatile("ld.global.cg.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(tv.x), "=r"(tv.y), "=r"(tv.z), "=r"(tv.w), "=r"(tn.x), "=r"(tn.y), "=r"(tn.z), "=r"(tn.w)
-                 : "l"(m.tet + 2 * (size_t)t));
+                 : "l"(m.tet + REC4 * (size_t)t + TVO4));
 #else
     tv = TV(m, t); tn = TN(m, t);
 #endif
@@ -86,7 +91,7 @@ template <int D> VOR_HD void load_rec_cg(const Mesh<D> &m, int t, int4 &tv, int4
 template <int D> VOR_HD void store_rec(const Mesh<D> &m, int t, const int4 &tv, const int4 &tn) {
 #ifdef __CUDA_ARCH__
     asm volatile("st.global.v8.s32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
-                 :: "r"(tv.x), "r"(tv.y), "r"(tv.z), "r"(tv.w), "r"(tn.x), "r"(tn.y), "r"(tn.z), "r"(tn.w), "l"(m.tet + 2 * (size_t)t)
+                 :: "r"(tv.x), "r"(tv.y), "r"(tv.z), "r"(tv.w), "r"(tn.x), "r"(tn.y), "r"(tn.z), "r"(tn.w), "l"(m.tet + REC4 * (size_t)t + TVO4)
                  : "memory");
 #else
     TV(m, t) = tv; TN(m, t) = tn;
@@ -103,6 +108,41 @@ VOR_HD double4 load_pt(const double4 *p) {
 }
 VOR_HD double2 load_pt(const double2 *p) { return *p; }
 
+// ---- the 32 B ownership + sphere block of a simplex (sphere.cuh)
+struct OwnBlk { int kill, ring; float cx, cy, cz, rin2, rout2; int spare; };
+// one 256-bit gather, L2 only (the ownership words are updated by other SMs during the attempt kernel)
+template <int D> VOR_HD OwnBlk load_blk(const Mesh<D> &m, int t) {
+    OwnBlk b;
+#ifdef __CUDA_ARCH__
+    int c0, c1, c2, c3, c4;
+    asm volatile("ld.global.cg.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(b.kill), "=r"(b.ring), "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3), "=r"(c4), "=r"(b.spare)
+                 : "l"(m.owner + OWS * (size_t)t));
+    b.cx = __int_as_float(c0); b.cy = __int_as_float(c1); b.cz = __int_as_float(c2); b.rin2 = __int_as_float(c3); b.rout2 = __int_as_float(c4);
+#else
+    const int *w = m.owner + OWS * (size_t)t;
+    b.kill = w[0]; b.ring = w[1]; b.cx = i2f(w[2]); b.cy = i2f(w[3]); b.cz = i2f(w[4]); b.rin2 = i2f(w[5]); b.rout2 = i2f(w[6]); b.spare = w[7];
+#endif
+    return b;
+}
+// a NEW simplex: ownership words free, sphere filter of its vertices (one 256-bit store)
+template <int D> VOR_HD void store_blk(const Mesh<D> &m, int t, const SphereBlk &s) {
+#ifdef __CUDA_ARCH__
+    asm volatile("st.global.v8.s32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+                 :: "r"(OWNER_FREE), "r"(OWNER_FREE), "r"(__float_as_int(s.cx)), "r"(__float_as_int(s.cy)), "r"(__float_as_int(s.cz)),
+                    "r"(__float_as_int(s.rin2)), "r"(__float_as_int(s.rout2)), "r"(0), "l"(m.owner + OWS * (size_t)t)
+                 : "memory");
+#else
+    int *w = m.owner + OWS * (size_t)t;
+    w[0] = OWNER_FREE; w[1] = OWNER_FREE; w[2] = f2i(s.cx); w[3] = f2i(s.cy); w[4] = f2i(s.cz); w[5] = f2i(s.rin2); w[6] = f2i(s.rout2); w[7] = 0;
+#endif
+}
+// query point relative to the origin of the float centres
+struct RelPt { double x, y, z; };
+template <int D> VOR_HD RelPt rel_pt(const Mesh<D> &m, const double4 &p) { RelPt q; q.x = p.x - m.sref.ox; q.y = p.y - m.sref.oy; q.z = p.z - m.sref.oz; return q; }
+template <int D> VOR_HD RelPt rel_pt(const Mesh<D> &m, const double2 &p) { RelPt q; q.x = p.x - m.sref.ox; q.y = p.y - m.sref.oy; q.z = 0.0; return q; }
+VOR_HD int sphere_test(const OwnBlk &b, const RelPt &q) { return sphere_test(b.cx, b.cy, b.cz, b.rin2, b.rout2, q.x, q.y, q.z); }
+
 struct Scratch {
     int *killed, *bfacet, *bouter;     // contiguous per slot: entry j of slot s at [s * cap + j] (coalesced for a lane group)
     int *slotAct, *slotNk, *slotNb, *slotStatus, *slotBig;
@@ -110,6 +150,7 @@ struct Scratch {
     int *bigK, *bigF, *bigO;           // overflow slots, contiguous per slot
     int nbig, bigCapK, bigCapB;
     int *winners, *wbase;
+    int *slowSlots;                    // slots queued for the exact twin of the attempt kernel this round (coop_kernels.cuh)
 };
 
 enum : int { ST_LOST = 0, ST_OK = 1 };
@@ -183,6 +224,21 @@ template <> struct Geo<2> {
     template <class CX> static VOR_HD int orient(CX &cx, const Verts &t) { return orient2d(cx, t.p0, t.p1, t.p2); }
 };
 
+// sphere filter of a simplex given its vertex ids (gathers the coordinates)
+VOR_HD SphereBlk sphere_of(const Mesh<3> &m, const int4 &v) {
+    return sphere_make(load_pt(m.pts + v.x), load_pt(m.pts + v.y), load_pt(m.pts + v.z), load_pt(m.pts + v.w), m.sref);
+}
+VOR_HD SphereBlk sphere_of(const Mesh<2> &m, const int4 &v) { return sphere_make(m.pts[v.x], m.pts[v.y], m.pts[v.z], m.sref); }
+
+// conflict test of simplex n against p (q = p relative to the sphere origin): the stored sphere decides, the
+// determinant predicate (FP64 filter -> exact) takes the undecided shell.  delaunay_tree.rs:40-46 / geometry.rs:91-97.
+template <int D, class CX> VOR_HD int conflict_at(CX &cx, const Mesh<D> &m, int n, const OwnBlk &b, const typename Dim<D>::Pt &p, const RelPt &q) {
+    const int sv = sphere_test(b, q);
+    if (sv) return sv > 0;
+    atomic_add_ull(&m.cnt->sph_undecided, 1ULL);
+    return Geo<D>::conflict(cx, Geo<D>::load(m, TV(m, n)), p);
+}
+
 // ------------------------------------------------------------------------------------------
 // attempt: locate + conflict region + reservation
 // ------------------------------------------------------------------------------------------
@@ -216,16 +272,20 @@ template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
     A.scr.slotBig[slot] = -1;
     PredCtx cx{m.cnt};
     const typename G::Pt p = m.pts[v];
+    const RelPt rq = rel_pt(m, p);
 
     // -- forwarding: a dead seed points at a simplex created by its killer
     int o;
     while ((o = OWK(m, s)) < 0) s = ~o;
 
-    // -- visibility walk
+    // -- visibility walk; it may stop at ANY simplex in conflict with p (the conflict region is connected and the
+    // flood below finds all of it from any member): the stored sphere of the simplex the walk stands in is tested first
     unsigned rot = (unsigned)v * 2654435761u;
     unsigned steps = 0;
     typename G::Verts tvv = G::load(m, TV(m, s));
+    bool hit = false;
     for (;;) {
+        if (sphere_test(load_blk(m, s), rq) > 0) { hit = true; break; }
         const int mk = G::beyond_mask(cx, tvv, p);
         if (mk == 0) break;
         int go = 0;
@@ -247,7 +307,7 @@ template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
     const int key_k = A.keybase | (int)(q << 1);
     const int key_o = key_k | 1;
     unsigned tests = 1;
-    if (!G::conflict(cx, tvv, p)) {
+    if (!hit && !G::conflict(cx, tvv, p)) {
         // p coincides with a vertex of its containing simplex: duplicate input point.  Drop it.
         m.seed[v] = -1;
         atomic_add_i(&m.cnt->ndup, 1);
@@ -268,13 +328,13 @@ template <int D> VOR_HD void attempt_body(const AttemptArgs<D> &A, int a) {
                 int isout = 1;
                 if (code >= 0) {
                     const int n = code >> 2;
-                    const int ow = OWK(m, n), orr = OWR(m, n);
+                    const OwnBlk blk = load_blk(m, n);
+                    const int ow = blk.kill, orr = blk.ring;
                     if (ow == key_k) continue;               // already in my cavity
                     if (ow < key_k) goto lost;               // a better point kills it (or it is dead)
                     if (orr != key_o) {                      // not yet classified by me (or a better point shares the ring)
                         tests++;
-                        const typename G::Verts nv = G::load(m, TV(m, n));
-                        if (G::conflict(cx, nv, p)) {
+                        if (conflict_at(cx, m, n, blk, p, rq)) {
                             if (orr < key_k) goto lost;          // a better point keeps n in its outer ring
                             if (atomic_min_i(&OWK(m, n), key_k) < key_k) goto lost;
                             isout = 0;
@@ -431,6 +491,7 @@ template <int D> VOR_HD void retri_body(const RetriArgs<D> &A, int w) {
         int4 verts = TV(m, t);
         set4(verts, i, v);
         TV(m, T) = verts;
+        store_blk(m, T, sphere_of(m, verts));
         TNI(m, T, i) = outer;
         if (M == 3) TNI(m, T, 3) = -1;
         if (outer >= 0) TNI(m, outer >> 2, outer & 3) = T * 4 + i;
@@ -490,9 +551,12 @@ template <int D> VOR_HD void retri_body(const RetriArgs<D> &A, int w) {
 struct ResetOwnerArgs { int *owner; const Counters *cnt; };
 VOR_HD void reset_owner_body(const ResetOwnerArgs &A, int t) {
     if (t >= A.cnt->ntets) return;   // the launch covers the whole store: the host's simplex count may be a batch behind
-    if (A.owner[2 * (size_t)t] >= 0) A.owner[2 * (size_t)t] = OWNER_FREE;
-    A.owner[2 * (size_t)t + 1] = OWNER_FREE;
+    if (A.owner[OWS * (size_t)t] >= 0) A.owner[OWS * (size_t)t] = OWNER_FREE;
+    A.owner[OWS * (size_t)t + 1] = OWNER_FREE;
 }
+
+struct MarkDeadArgs { int *owner; int first; };   // slots handed out beyond the capacity of the store: dead, never referenced
+VOR_HD void mark_dead_body(const MarkDeadArgs &A, int i) { A.owner[OWS * (size_t)(A.first + i)] = -1; }
 
 struct FillArgs { int *p; int val; };
 VOR_HD void fill_body(const FillArgs &A, int i) { A.p[i] = A.val; }

@@ -119,7 +119,8 @@ VOR_HD void edge_sum_body(const EdgeSumArgs &A, int i) {
 // ---- validation
 template <int D> struct ValidateArgs {
     Mesh<D> m;
-    int *fail;   // [8] failure counters: 0 orientation, 1 dead neighbour, 2 asymmetric adjacency, 3 facet mismatch, 4 not Delaunay
+    int *fail;   // [8] failure counters: 0 orientation, 1 dead neighbour, 2 asymmetric adjacency, 3 facet mismatch, 4 not Delaunay,
+                 // 5 stored sphere filter certifies a verdict the exact predicate contradicts
     unsigned long long *nlive;
 };
 template <int D> VOR_HD void validate_body(const ValidateArgs<D> &A, int t) {
@@ -133,6 +134,9 @@ template <int D> VOR_HD void validate_body(const ValidateArgs<D> &A, int t) {
     const int4 tn = TN(m, t);
     const typename G::Verts vt = G::load(m, tv);
     if (G::orient(cx, vt) <= 0) atomic_add_i(&A.fail[0], 1);
+    const OwnBlk blk = load_blk(m, t);
+    for (int k = 0; k < M; k++)   // own vertices lie ON the sphere: never certainly inside
+        if (sphere_test(blk, rel_pt(m, m.pts[get4(tv, k)])) > 0) atomic_add_i(&A.fail[5], 1);
     for (int i = 0; i < M; i++) {
         const int code = get4(tn, i);
         if (code < 0) continue;
@@ -150,7 +154,11 @@ template <int D> VOR_HD void validate_body(const ValidateArgs<D> &A, int t) {
             ok &= found;
         }
         if (!ok) { atomic_add_i(&A.fail[3], 1); continue; }
-        if (G::conflict(cx, vt, m.pts[get4(nv, jb)])) atomic_add_i(&A.fail[4], 1);
+        const typename G::Pt opp = m.pts[get4(nv, jb)];   // closest vertices to the sphere: the filter's hardest queries
+        const int exact = G::conflict(cx, vt, opp);
+        if (exact) atomic_add_i(&A.fail[4], 1);
+        const int sv = sphere_test(blk, rel_pt(m, opp));
+        if (sv != 0 && (sv > 0) != (exact != 0)) atomic_add_i(&A.fail[5], 1);
     }
 }
 
@@ -448,6 +456,25 @@ VOR_HD void pred_batch_body(const PredBatchArgs &A, int i) {
         A.out[i] = insphere(cx, double4{r[0], r[1], r[2], 0}, double4{r[3], r[4], r[5], 0}, double4{r[6], r[7], r[8], 0}, double4{r[9], r[10], r[11], 0},
                             double4{r[12], r[13], r[14], 0});
     }
+}
+
+// cached-circumsphere filter (sphere.cuh) on packed rows of M simplex vertices + 1 query: out = +1 certainly strictly
+// inside, -1 certainly not, 0 undecided; blocks (optional) = cx, cy, cz, rin2, rout2 as stored
+struct SphereBatchArgs { const double *rows; int *out; float *blocks; SphereRef ref; int dim; };
+VOR_HD void sphere_batch_body(const SphereBatchArgs &A, int i) {
+    SphereBlk b;
+    double qx, qy, qz = 0.0;
+    if (A.dim == 3) {
+        const double *r = A.rows + (size_t)i * 15;
+        b = sphere_make(double4{r[0], r[1], r[2], 0}, double4{r[3], r[4], r[5], 0}, double4{r[6], r[7], r[8], 0}, double4{r[9], r[10], r[11], 0}, A.ref);
+        qx = r[12] - A.ref.ox; qy = r[13] - A.ref.oy; qz = r[14] - A.ref.oz;
+    } else {
+        const double *r = A.rows + (size_t)i * 8;
+        b = sphere_make(double2{r[0], r[1]}, double2{r[2], r[3]}, double2{r[4], r[5]}, A.ref);
+        qx = r[6] - A.ref.ox; qy = r[7] - A.ref.oy;
+    }
+    A.out[i] = sphere_test(b.cx, b.cy, b.cz, b.rin2, b.rout2, qx, qy, qz);
+    if (A.blocks) { float *o = A.blocks + (size_t)i * 5; o[0] = b.cx; o[1] = b.cy; o[2] = b.cz; o[3] = b.rin2; o[4] = b.rout2; }
 }
 
 } // namespace vor

@@ -190,7 +190,7 @@ template <int D> VOR_HD void init_seeds_body(const SeedArgs<D> &A, int j) {
         if (best >= 0) seed = A.ptTet[best];
     }
     int o;
-    while ((o = A.owner[2 * (size_t)seed]) < 0) seed = ~o;
+    while ((o = A.owner[OWS * (size_t)seed]) < 0) seed = ~o;
     A.seed[v] = seed;
 }
 

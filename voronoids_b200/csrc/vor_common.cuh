@@ -140,6 +140,8 @@ struct Counters {
     // in its own 32 B sector.  The host folds them (Engine::win_total / created_all).
     unsigned long long part[128][4];
     int nflag_set, nflag_done;       // points handed to / finished by the exact twin of the attempt kernel
+    int sph_lo, nslow;                // simplex slots below sph_lo have their sphere block (k_spheres); slots queued for the exact twin
+    unsigned long long sph_undecided; // conflict tests the stored sphere filter left to the determinant predicate
 };
 constexpr int NPART = 128;
 

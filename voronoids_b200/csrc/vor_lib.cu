@@ -3,6 +3,6 @@
 #include "backend_cuda.cuh"
 #include "engine.cuh"
 
-namespace vor { namespace be { unsigned long long g_launches = 0; Pool g_pool; HostPool g_hostpool; Staging g_staging; } }
+namespace vor { namespace be { std::atomic<unsigned long long> g_launches{0}; Pool g_pool; HostPool g_hostpool; Staging g_staging_dev[MAX_DEVICES]; } }
 
 #include "capi.inl"
