@@ -88,6 +88,7 @@ int vor_set_option(const char *name, double value) {
     else if (n == "split_exact") g_opts.split_exact = (int)value;
     else if (n == "tet_factor") g_opts.tet_factor = value;
     else if (n == "compact_frac") g_opts.compact_frac = value;
+    else if (n == "stage_log") g_opts.stage_log = (int)value;
     else if (n == "capk") { g_opts.capk = (int)value; g_opts.capb = 2 * g_opts.capk + 4; }
     else if (n == "big_slots") g_opts.big_slots = (int)value;
     else if (n == "big_capk") g_opts.big_capk = (int)value;

@@ -366,19 +366,11 @@ __device__ __forceinline__ double pow_mid(const OwnBlk &b, const RelPt &q) {
     return (dx * dx + dy * dy + dz * dz) - 0.5 * ((double)b.rin2 + (double)b.rout2);
 }
 template <int D>
-__global__ void __launch_bounds__(VOR_HOT_BLOCK, (65536 / (VOR_HOT_REGS * VOR_HOT_BLOCK)) > 32 ? 32 : (65536 / (VOR_HOT_REGS * VOR_HOT_BLOCK)))
-k_attempt_hot(AttemptArgs<D> A, RoundSel rsel) {
+__device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const RoundSel &rsel, const int slot, int *const sk, int4 *const sn) {
     constexpr int M = Dim<D>::M;
     constexpr int SK = VOR_SK;
-    __shared__ int s_kid[VOR_HOT_BLOCK / 32][VOR_SK];
-    __shared__ int4 s_knb[VOR_HOT_BLOCK / 32][VOR_SK];
     const Mesh<D> &m = A.m;
-    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int gl = threadIdx.x & 31;
-    if (blockIdx.x == 0 && threadIdx.x == 0) m.cnt->sph_lo = m.cnt->ntets;   // k_spheres of the last round is done
-    if (slot >= rsel.nsel) return;
-    int *const sk = s_kid[threadIdx.x >> 5];
-    int4 *const sn = s_knb[threadIdx.x >> 5];
     const int a = slot_entry(rsel, slot);
     if (a >= rsel.nact) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }
     const int v = A.act[a];
@@ -550,6 +542,22 @@ k_attempt_hot(AttemptArgs<D> A, RoundSel rsel) {
     }
 }
 
+// Resident warps with a static stride over the slots (grid = what fits on the machine, engine.cuh): a third to a half of
+// the slots of a round hold points that are already inserted or are the exact twin's; with one block per pair of slots
+// the SMs spent their time launching blocks that exit at once (ncu, round 2: 24 of 36 warps resident on average).
+template <int D>
+__global__ void __launch_bounds__(VOR_HOT_BLOCK, (65536 / (VOR_HOT_REGS * VOR_HOT_BLOCK)) > 32 ? 32 : (65536 / (VOR_HOT_REGS * VOR_HOT_BLOCK)))
+k_attempt_hot(AttemptArgs<D> A, RoundSel rsel) {
+    __shared__ int s_kid[VOR_HOT_BLOCK / 32][VOR_SK];
+    __shared__ int4 s_knb[VOR_HOT_BLOCK / 32][VOR_SK];
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.m.cnt->sph_lo = A.m.cnt->ntets;   // k_spheres of the last round is done
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < rsel.nsel; slot += nwarps) {
+        attempt_hot_one<D>(A, rsel, slot, s_kid[threadIdx.x >> 5], s_knb[threadIdx.x >> 5]);
+        __syncwarp();
+    }
+}
+
 // the exact twin behind the hot kernel: the slots the hot kernel queued this round (points flagged in earlier rounds)
 template <int D, int RED>
 __global__ void __launch_bounds__(VOR_ATTEMPT_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_ATTEMPT_BLOCK)) k_attempt_slow(AttemptArgs<D> A, RoundSel rsel) {
@@ -660,21 +668,21 @@ __device__ __noinline__ void commit_global(const Mesh<D> &m, const ScrView sv, i
 // shared memory with ONE level of independent gathers, checked, and retriangulated there: markers, the ridge pivots
 // of pair_simplices (delaunay_tree.rs:674-695) and the forwarding choice never leave the SM; HBM sees one full 32 B
 // record per new simplex, one back-pointer per outer facet and one dead mark per killed simplex.
+constexpr int COMMIT_HS = 128;
+template <int D> struct CommitSmem {
+    int4 tv[VOR_CK], tn[VOR_CK];
+    int id[VOR_CK], fw[VOR_CK], hash[COMMIT_HS], f[VOR_CB], o[VOR_CB];
+};
 template <int D, int G>
-__global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, const int *act, RoundSel rsel, int stats) {
+__device__ __forceinline__ void commit_one(const CheckArgs<D> &A, const int *act, const RoundSel &rsel, int stats, const int slot, CommitSmem<D> &sm) {
     constexpr int M = Dim<D>::M;
-    constexpr int CK = VOR_CK, CB = VOR_CB, HS = 128, GPB = VOR_COOP_BLOCK / G;
+    constexpr int CK = VOR_CK, CB = VOR_CB, HS = COMMIT_HS;
     static_assert(HS >= 2 * CK, "hash must stay at most half full");
-    __shared__ int4 s_tv[GPB][CK], s_tn[GPB][CK];
-    __shared__ int s_id[GPB][CK], s_fw[GPB][CK], s_hash[GPB][HS], s_f[GPB][CB], s_o[GPB][CB];
     const Mesh<D> &m = A.m;
-    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gid = slot;
     const int gl = threadIdx.x & (G - 1);
     const unsigned gmask = group_mask<G>();
     const int gshift = (threadIdx.x & 31) & ~(G - 1);
-    if (gid == 0 && gl == 0) { m.cnt->nbig = 0; m.cnt->nslow = 0; }   // overflow slots and the exact twin's queue are per round (attempt is over)
-    if (gid >= rsel.nsel) return;
-    const int slot = gid;
     if (A.scr.slotStatus[slot] != ST_OK) return;
     const int a = slot_entry(rsel, slot);
     const int v = act[a];
@@ -683,9 +691,8 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
     const ScrView sv = scr_view(A.scr, slot, A.scr.slotBig[slot]);
     const int nk = A.scr.slotNk[slot], nb = A.scr.slotNb[slot];
     const bool fast = !(stats & 2) && nk <= CK && nb <= CB;   // stats bit 1: force the global-store path (A/B switch)
-    const int grp = threadIdx.x / G;
-    int4 *const tvs = s_tv[grp], *const tns = s_tn[grp];
-    int *const ids = s_id[grp], *const fw = s_fw[grp], *const hash = s_hash[grp], *const sf = s_f[grp], *const so = s_o[grp];
+    int4 *const tvs = sm.tv, *const tns = sm.tn;
+    int *const ids = sm.id, *const fw = sm.fw, *const hash = sm.hash, *const sf = sm.f, *const so = sm.o;
     int *const tni = reinterpret_cast<int *>(tns);
 
     // -- ownership check; the fast path loads the cavity in the same level of gathers
@@ -815,6 +822,18 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
             atomicAdd(&m.cnt->killed, (unsigned long long)nk);
             atomicAdd(&m.cnt->created, (unsigned long long)nb);
         }
+    }
+}
+// resident groups with a static stride over the slots (see k_attempt_hot): most slots of a round hold no winner
+template <int D, int G>
+__global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, const int *act, RoundSel rsel, int stats) {
+    __shared__ CommitSmem<D> s_cav[VOR_COOP_BLOCK / G];
+    const unsigned gmask = group_mask<G>();
+    if (blockIdx.x == 0 && threadIdx.x == 0) { A.m.cnt->nbig = 0; A.m.cnt->nslow = 0; }   // overflow slots and the exact twin's queue are per round (attempt is over)
+    const int ngroups = (gridDim.x * blockDim.x) / G;
+    for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) / G; slot < rsel.nsel; slot += ngroups) {
+        commit_one<D, G>(A, act, rsel, stats, slot, s_cav[threadIdx.x / G]);
+        __syncwarp(gmask);
     }
 }
 

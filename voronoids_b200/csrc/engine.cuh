@@ -34,6 +34,7 @@ struct EngineOptions {
     double attempt_div = 64.0;   // otherwise attempt about (inserted vertices)/attempt_div points per round: about n/60
                                  // disjoint footprints fit into a mesh of n vertices, so denser attempts only lose (measured)
     int stage0 = 256;            // size of the first stage
+    int stage_log = 1;           // stage sizes grow by 2^stage_log
     int stats = 0;               // accumulate W/E/K/C counters (atomics; keep off when timing)
     int verbose = 0;
     int profile = 0;             // CUDA-event time per kernel class (attempt / check / retri / setup)
@@ -44,6 +45,8 @@ struct EngineOptions {
     int commit_smem = 1;         // commit retriangulates cavities staged in shared memory (0 = through the global store)
     int split_exact = 1;         // attempt kernel as a hot twin without exact predicates + an exact twin for the points it flags
     int red = 1;                 // kill reservation as a fire-and-forget reduction (match.any dedup), see k_attempt_coop
+    int smem_pad = 0;            // diagnostics: extra dynamic shared memory per block of the round kernels (caps resident warps)
+    int persist_waves = 1000000; // grid of the round kernels = resident blocks x this (1 = persistent warps; large = one block per slot pair)
     double compact_frac = 0.85;  // the active list is compacted (at a host read-back) once fewer than this fraction of it is pending
     double tet_factor = 0.0;     // simplex slots per vertex (0 = default: 31 in 3D, 7.5 in 2D)
 };
@@ -53,10 +56,13 @@ inline void options_from_env(EngineOptions &o) {
     if (const char *e = getenv("VOR_MIN_ATTEMPT")) o.min_attempt = atoi(e);
     if (const char *e = getenv("VOR_ATTEMPT_DIV")) o.attempt_div = atof(e);
     if (const char *e = getenv("VOR_STAGE0")) o.stage0 = atoi(e);
+    if (const char *e = getenv("VOR_STAGE_LOG")) o.stage_log = atoi(e);
     if (const char *e = getenv("VOR_STATS")) o.stats = atoi(e);
     if (const char *e = getenv("VOR_VERBOSE")) o.verbose = atoi(e);
     if (const char *e = getenv("VOR_TET_FACTOR")) o.tet_factor = atof(e);
     if (const char *e = getenv("VOR_COMPACT_FRAC")) o.compact_frac = atof(e);
+    if (const char *e = getenv("VOR_PERSIST_WAVES")) o.persist_waves = std::max(1, atoi(e));
+    if (const char *e = getenv("VOR_SMEM_PAD")) o.smem_pad = atoi(e);
     if (const char *e = getenv("VOR_COOP")) o.coop = atoi(e);
     if (const char *e = getenv("VOR_ROUNDS_PER_SYNC")) o.rounds_per_sync = atoi(e);
     if (const char *e = getenv("VOR_SELECT_MODE")) o.select_mode = atoi(e);
@@ -100,6 +106,7 @@ template <int D> class Engine {
     Scratch scr{};
     bool slowPending = false, splitDisabled = false;
     int flagPending = 0;
+    int occHot = -1, occCommit = -1;   // resident blocks of the round kernels on this device
     int *act = nullptr, *act2 = nullptr, *blockCnt = nullptr, *slowFlag = nullptr;
     long long *d_misc = nullptr;
     long long insertedTotal = 0;
@@ -442,7 +449,7 @@ template <int D> class Engine {
         be::h2d(d_s0, s0.data(), sizeof(int) * (size_t)nsets, stream);
         callSalt = mix64(callSalt + (uint64_t)ninput);
         prof.start(3, stream);
-        KeyArgs<D> ka{d_in, d_off, d_boxLo, d_boxHi, d_s0, k0, v0, nsets, setBits, axisBits, callSalt};
+        KeyArgs<D> ka{d_in, d_off, d_boxLo, d_boxHi, d_s0, k0, v0, nsets, setBits, axisBits, callSalt, std::max(1, opt.stage_log)};
         VOR_LAUNCH(KeyArgs<D>, keys_body<D>, n, ka, stream);
         uint64_t *kdst = keysAll + (nv - nsuper);
         be::sort_pairs(k0, kdst, v0, v1, (size_t)n, stream);
@@ -540,14 +547,24 @@ template <int D> class Engine {
         return (long long)std::min(byRounds, byRemaining) + 4096;
     }
     template <int G> void launch_round(const AttemptArgs<D> &aa, const CheckArgs<D> &ca, const RoundSel &sel, bool slowNow) {
-        const unsigned grid = (unsigned)(((long long)sel.nsel * G + VOR_COOP_BLOCK - 1) / VOR_COOP_BLOCK);
+        // resident warps: as many blocks as fit on the machine (occupancy queried once), each warp strides over the slots
+        if (occHot < 0) {
+            int dev = 0, nsm = 148, o1 = 1, o2 = 1;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_attempt_hot<D>, VOR_HOT_BLOCK, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_commit_coop<D, G>, VOR_COOP_BLOCK, 0);
+            occHot = std::max(1, o1) * nsm;
+            occCommit = std::max(1, o2) * nsm;
+        }
+        const unsigned grid = (unsigned)std::min<long long>(((long long)sel.nsel * G + VOR_COOP_BLOCK - 1) / VOR_COOP_BLOCK, (long long)occCommit * opt.persist_waves);
         const unsigned agrid = (unsigned)(((long long)sel.nsel * G + VOR_ATTEMPT_BLOCK - 1) / VOR_ATTEMPT_BLOCK);
         prof.start(0, stream);
         if (opt.red && aa.slowFlag) {
             // hot twin without the exact predicates in its call tree; while flagged points are pending (host
             // knowledge, one read-back old) the exact twin follows and attempts only those
-            const unsigned hgrid = (unsigned)(((long long)sel.nsel * G + VOR_HOT_BLOCK - 1) / VOR_HOT_BLOCK);
-            k_attempt_hot<D><<<hgrid, VOR_HOT_BLOCK, 0, stream>>>(aa, sel);
+            const unsigned hgrid = (unsigned)std::min<long long>(((long long)sel.nsel * G + VOR_HOT_BLOCK - 1) / VOR_HOT_BLOCK, (long long)occHot * opt.persist_waves);
+            k_attempt_hot<D><<<hgrid, VOR_HOT_BLOCK, (size_t)opt.smem_pad, stream>>>(aa, sel);
             if (slowNow) {
                 // the slots the hot kernel queued (points it flagged in earlier rounds); a small grid-stride launch
                 AttemptArgs<D> as = aa;
@@ -564,7 +581,7 @@ template <int D> class Engine {
         }
         prof.stop(stream);
         prof.start(2, stream);
-        k_commit_coop<D, G><<<grid, VOR_COOP_BLOCK, 0, stream>>>(ca, act, sel, (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2));
+        k_commit_coop<D, G><<<grid, VOR_COOP_BLOCK, (size_t)opt.smem_pad, stream>>>(ca, act, sel, (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2));
         prof.stop(stream);
         prof.start(1, stream);
         {

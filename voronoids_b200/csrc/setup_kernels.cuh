@@ -91,6 +91,7 @@ template <int D> struct KeyArgs {
     int setBits;               // bits of the set field
     int axisBits;              // Morton bits per axis
     uint64_t salt;
+    int stageLog;              // stage sizes grow by 2^stageLog (1: doubling)
 };
 template <int D> VOR_HD void keys_body(const KeyArgs<D> &A, int i) {
     // set of point i
@@ -104,7 +105,7 @@ template <int D> VOR_HD void keys_body(const KeyArgs<D> &A, int i) {
     const uint64_t r = mix64(A.salt ^ (uint64_t)(i - A.setOff[s])) % (uint64_t)cnt;
     const uint64_t s0 = (uint64_t)A.setS0[s];
     int stage = 0;
-    if (r >= s0) { uint64_t x = r / s0; stage = 1; while (x > 1) { x >>= 1; stage++; } }
+    if (r >= s0) { uint64_t x = r / s0; int lg = 0; while (x > 1) { x >>= 1; lg++; } stage = 1 + lg / A.stageLog; }
     uint64_t code = 0;
     const double scale = (double)((1u << A.axisBits) - 1u);
     for (int k = 0; k < D; k++) {
