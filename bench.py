@@ -43,7 +43,6 @@ WORKLOADS = {
     "b3_64x100k": (3, "batch", 6_400_000, 1000, "batch of 64 independent 3D uniform sets x 100k points per GPU (configs[4] shape)"),
 }
 BATCH_SETS, BATCH_SIZE = 64, 100_000
-CPU_SAMPLE = {3: 150_000, 2: 400_000}  # points of the same workload given to the CPU baseline (about 10-30 s)
 
 
 def algorithmic_bytes(dim, K, Cn, W=1.0):
@@ -119,33 +118,98 @@ def make_points(name, rank):
     return pointgen.make(kind, n, dim, seed + 7919 * rank), dim, n, desc
 
 
-def cpu_reference_run(name, steps, warmup, as_arm):
-    """The reference's CPU implementation (port) on a bounded sample of the workload, all host threads."""
-    from oracle import oracle as O
-    dim, kind, n, seed, desc = WORKLOADS[name]
-    ns = min(n, CPU_SAMPLE[dim])
+def host_threads():
+    """Threads the CPU arm may use: the cores this process is allowed on.  Passed to the restatement EXPLICITLY, because
+    torch.distributed.run exports OMP_NUM_THREADS=1 to its workers."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def reference_points(name, ns):
     from voronoids_b200 import pointgen
+    dim, kind, n, seed, desc = WORKLOADS[name]
     if kind == "batch":
-        ns = min(BATCH_SIZE, CPU_SAMPLE[dim])   # one set of the batch (sets are independent units)
-        pts = pointgen.uniform(ns, dim, seed)
-    else:
-        pts = pointgen.make(kind, n, dim, seed)[:ns] if kind != "uniform" else pointgen.uniform(ns, dim, seed)
-    cores = O.lib().vo_ref_max_threads()
-    times = []
-    reps = (warmup + steps) if as_arm else 1
-    for i in range(reps):
-        t0 = time.perf_counter()
-        r = O.RefDelaunay(pts, mode="delaunay")
-        dt = time.perf_counter() - t0
-        if r.err:
-            raise RuntimeError(f"reference restatement failed with code {r.err} (the Rust original would panic here)")
-        if not as_arm or i >= warmup:
-            times.append(dt)
-        del r
-    t = sum(times) / len(times)
-    sample = (f"first {ns} points of {name} through vo_ref_delaunay (lib.rs:104-125: "
-              f"{min(ns, 100000)} sequential inserts + {max(ns - 100000, 0)} via add_points_to_tree), {cores} OpenMP threads")
-    return {"value": ns / t, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample}, t, ns
+        return pointgen.uniform(min(ns, BATCH_SIZE), dim, seed)   # one set of the batch (sets are independent units)
+    if kind == "uniform":
+        return pointgen.uniform(ns, dim, seed)                    # counter-based generator: a prefix of the workload
+    return pointgen.make(kind, n, dim, seed)[:ns]
+
+
+def reference_once(pts, nthreads):
+    """The reference's own CPU path on `pts` (oracle/refcpu.cpp, restatement of kazewong/Voronoids lib.rs:104-125):
+    DelaunayTree::new, the first 100,000 points one by one (TreeUpdate::new + insert_point), the rest in ONE
+    add_points_to_tree call (make_queue -> find_placement -> rounds of insert_points_parallel).  Phases timed apart."""
+    from oracle import oracle as O
+    L = O.lib()
+    p, pp = O._d(pts)
+    n, dim = p.shape
+    n_seq = min(n, 100_000)
+    t0 = time.perf_counter()
+    h = L.vo_ref_create(dim, pp, n)
+    e = L.vo_ref_insert_sequential(h, pp, n_seq, 0)
+    t1 = time.perf_counter()
+    if not e and n > n_seq:
+        rest = np.ascontiguousarray(p[n_seq:])
+        e = L.vo_ref_add_points_to_tree(h, rest.ctypes.data_as(C.POINTER(C.c_double)), n - n_seq, n_seq, nthreads)
+    t2 = time.perf_counter()
+    L.vo_ref_destroy(h)
+    if e:
+        raise RuntimeError(f"reference restatement failed with code {e} (the Rust original would panic here)")
+    return {"n": n, "n_sequential": n_seq, "n_parallel": n - n_seq, "t_total": t2 - t0, "t_sequential": t1 - t0, "t_parallel": t2 - t1}
+
+
+CPU_FULL_SAMPLE = {3: 1_000_000, 2: 1_000_000}   # examples/parallel_insert.rs:7-9 shape: 100k sequential + 900k parallel
+
+
+def cpu_sample_record(name, nthreads, ns, with_one_core):
+    """One run of the reference path on the first `ns` points of the workload -> the cpu_baseline object."""
+    dim = WORKLOADS[name][0]
+    r = reference_once(reference_points(name, ns), nthreads)
+    rec = {"value": r["n"] / r["t_total"], "unit": "points/s", "cores": nthreads, "kind": "port",
+           "sample": (f"first {r['n']} points of {name} through the restated lib.rs:104-125 path: {r['n_sequential']} sequential inserts "
+                      f"({r['t_sequential']:.1f} s) + {r['n_parallel']} in one add_points_to_tree call ({r['t_parallel']:.1f} s), "
+                      f"{nthreads} OpenMP threads passed explicitly"),
+           "sequential_phase_pts_per_s": r["n_sequential"] / r["t_sequential"] if r["t_sequential"] > 0 else None,
+           "parallel_phase_pts_per_s": (r["n_parallel"] / r["t_parallel"]) if r["n_parallel"] else None}
+    if with_one_core:
+        # the same path on ONE thread, on a smaller sample (100k sequential + 100k parallel)
+        r1 = reference_once(reference_points(name, min(ns, 200_000)), 1)
+        rec["one_core"] = {"value": r1["n"] / r1["t_total"], "unit": "points/s", "sample": f"first {r1['n']} points, 1 thread",
+                           "parallel_phase_pts_per_s": (r1["n_parallel"] / r1["t_parallel"]) if r1["n_parallel"] else None}
+    return rec
+
+
+def reference_arm(name, steps, warmup):
+    """bench.py --impl reference: K timed steps of the reference's CPU path, each on a bounded sample of the workload
+    sized so that the whole run ends within a few minutes; W warm-up steps on a small sample (a CPU has nothing to warm
+    but its thread pool and page cache)."""
+    dim = WORKLOADS[name][0]
+    nthreads = host_threads()
+    budget_s = float(os.environ.get("VOR_REF_BUDGET_S", "420"))
+    # calibration + warm-up: 150k points (100k sequential + 50k parallel)
+    cal = reference_once(reference_points(name, 150_000), nthreads)
+    for _ in range(max(0, warmup - 1)):
+        reference_once(reference_points(name, 150_000), nthreads)
+    r_seq = cal["n_sequential"] / max(cal["t_sequential"], 1e-9)
+    r_par = (cal["n_parallel"] / max(cal["t_parallel"], 1e-9)) if cal["n_parallel"] else r_seq
+    per_step = budget_s / max(steps, 1)
+    ns = int(min(CPU_FULL_SAMPLE[dim], max(300_000, 100_000 + (per_step - 100_000 / r_seq) * r_par)))
+    ns = min(ns, WORKLOADS[name][2] if WORKLOADS[name][1] != "batch" else BATCH_SIZE)
+    pts = reference_points(name, ns)
+    runs = [reference_once(pts, nthreads) for _ in range(steps)]
+    t = sum(r["t_total"] for r in runs) / len(runs)
+    tp = sum(r["t_parallel"] for r in runs) / len(runs)
+    ts = sum(r["t_sequential"] for r in runs) / len(runs)
+    n = runs[0]["n"]
+    cb = {"value": n / t, "unit": "points/s", "cores": nthreads, "kind": "port",
+          "sample": (f"each step: first {n} points of {name} through the restated lib.rs:104-125 path ({runs[0]['n_sequential']} sequential "
+                     f"inserts, {ts:.1f} s + {runs[0]['n_parallel']} in one add_points_to_tree call, {tp:.1f} s), {nthreads} OpenMP threads "
+                     f"passed explicitly; sample sized for {steps} steps in ~{budget_s:.0f} s; warm-up steps on 150k points"),
+          "sequential_phase_pts_per_s": runs[0]["n_sequential"] / ts if ts > 0 else None,
+          "parallel_phase_pts_per_s": (runs[0]["n_parallel"] / tp) if runs[0]["n_parallel"] and tp > 0 else None}
+    return cb, t, n
 
 
 def main():
@@ -167,11 +231,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cb, t, ns = cpu_reference_run(name, args.steps, args.warmup, as_arm=True)
+        cb, t, ns = reference_arm(name, args.steps, args.warmup)
+        cfg = bench_config(desc, n, dim, args.gpus)
+        cfg["reference_sample"] = f"each CPU step runs the first {ns} points of this workload (bounded sample, see cpu_baseline.sample)"
         line = {"impl": "reference", "metric": "delaunay_points_inserted_per_sec", "value": cb["value"], "unit": "points/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": bench_config(desc, n, dim, args.gpus),
+                "config": cfg,
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line), flush=True)
@@ -274,36 +340,30 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     t_attempt = sd["profile_ms"]["attempt"] * 1e-3
     achieved = (n * b_attempt / t_attempt / 1e9) if t_attempt > 0 else None
-    # DRAM traffic of the kernel from the committed ncu --set full capture (bytes per attempted point), scaled to the
-    # average launch of this run
+    # DRAM traffic of the kernel from the committed ncu --set full capture of one full-size round (bytes per attempt
+    # slot of that launch), scaled to the average launch of this run
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "attempt_traffic.json")))
         if tr.get("dim") == dim:
-            traffic = tr["dram_bytes_per_attempted_point"] * sd["attempts"] / max(sd["profile_launches"]["attempt"], 1)
+            traffic = tr["dram_bytes_per_slot"] * sd["slots"] / max(sd["profile_launches"]["attempt"], 1)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_attempt_coop (locate + conflict + reservation)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_attempt_hot + its exact twin k_attempt_slow (locate + conflict + reservation)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                "achieved_note": "algorithmic bytes of all launches / summed CUDA-event time of all launches (launch sizes vary by 4 orders of magnitude)",
+                "achieved_note": "algorithmic bytes of all launches (SURVEY.md 8d formula, measured K and C) / summed CUDA-event time of all "
+                                 "launches (launch sizes vary by 4 orders of magnitude)",
                 "algorithmic_bytes_per_point_kernel": b_attempt, "algorithmic_bytes_per_point_path": b_total,
                 "kernel_launches": sd["profile_launches"]["attempt"], "kernel_ms_total": sd["profile_ms"]["attempt"],
                 "path_frac": (value / world) * b_total / (peak * 1e9),
                 "counters_per_point": {"W_walk_steps_all_attempts": sd["walk_steps"] / n, "E_tests_all_attempts": sd["tests"] / n,
                                        "K_killed": K, "C_created": Cn, "attempts_per_point": sd["attempts"] / n,
                                        "rounds": sd["rounds"], "exact_calls": sd["exact_calls"], "exact_zero": sd["exact_zero"],
-                                       "aborted_attempts": sd["aborted"] / n, "E_tests_completed_attempts": sd["tests_completed"] / n},
+                                       "aborted_attempts": sd["aborted"] / n, "E_tests_completed_attempts": sd["tests_completed"] / n,
+                                       "sphere_filter_undecided_tests": sd["sphere_undecided"], "points_via_exact_twin": sd["flagged"],
+                                       "attempt_slots_launched": sd["slots"] / n},
                 "step_ms_by_kernel": sd["profile_ms"]}
-    # the resource that is actually saturated (profiles/r1_gather_microbench.md): scattered gather
-    # instructions per lane and second once the footprint exceeds the TLB reach.  Instructions the attempt kernel
-    # issues by construction: 4 per attempt (active entry, seed, point, owner), 5 per walk step (record + 4 vertices),
-    # 7 per in-sphere test (owner pair, record, 4 vertices, reduction); L1 hits on shared vertices are included, so the
-    # fraction can exceed 1 of the miss-only ceiling measured by tools/micro/gather_bench.cu (38.2 G/s over 16 GB).
-    if dim == 3 and t_attempt > 0:
-        g_instr = 4.0 * sd["attempts"] + 5.0 * sd["walk_steps"] + 7.0 * sd["tests"]
-        roofline["gather"] = {"bound": "scattered-load instruction rate beyond the TLB reach", "achieved": g_instr / t_attempt / 1e9,
-                              "peak": 38.2, "unit": "G gather instructions/s", "frac": g_instr / t_attempt / 1e9 / 38.2,
-                              "peak_source": "tools/micro/gather_bench.cu on this pool's B200 (profiles/r1_gather_microbench.md)"}
 
     # ---- end to end through the public API with host buffers (H2D + D2H inside the timed region)
     e2e = None
@@ -336,7 +396,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline, _, _ = cpu_reference_run(name, 1, 0, as_arm=False)
+        cpu_baseline = cpu_sample_record(name, host_threads(), CPU_FULL_SAMPLE[dim], with_one_core=True)
 
     if rank == 0:
         line = {"metric": "delaunay_points_inserted_per_sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,

@@ -140,8 +140,9 @@ vor_status vor_tree_super_simplex(vor_tree *t, size_t set, double *super_vertice
 /* engine statistics: [rounds, attempts, winners, owner_resets, compactions, stages,
  *                     walk_steps W, in-sphere tests E, killed K, created C, exact_calls, exact_zero, duplicates, simplex_slots,
  *                     attempts that lost during the flood, in-sphere tests of the attempts that completed,
- *                     conflict tests the cached-sphere filter left to the determinant, points handed to the exact twin] */
-#define VOR_N_STATS 18
+ *                     conflict tests the cached-sphere filter left to the determinant, points handed to the exact twin,
+ *                     attempt slots launched (all rounds)] */
+#define VOR_N_STATS 19
 vor_status vor_tree_stats(vor_tree *t, uint64_t *stats);
 
 /* with option "profile": CUDA-event milliseconds per kernel class [attempt, check, retri, setup] followed by the

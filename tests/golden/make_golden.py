@@ -2,7 +2,7 @@
 computed in the build container by the exact oracle and cross-checked against scipy/Qhull on P u S where Qhull
 finishes quickly.  The reference itself (Rust) cannot run here, see DESIGN.md "Oracle".
 
-    python tests/golden/make_golden.py [--big]      (--big adds the 10M-point case, ~3 min / ~20 GB)
+    python tests/golden/make_golden.py [--big] [--only name,name]   (--big adds the 10M / 5M-point cases, minutes / ~20 GB)
 """
 import json
 import os
@@ -30,7 +30,9 @@ CASES = [
     ("l3_500k", 3, "lattice", 500_000, 2, False),
     ("u3_set1000_100k", 3, "uniform", 100_000, 1000, False),  # configs[4]: set 0 of the batch
 ]
-BIG = [("u3_10m", 3, "uniform", 10_000_000, 0, False)]   # configs[2]
+BIG = [("u3_10m", 3, "uniform", 10_000_000, 0, False),    # configs[2]
+       ("c3_5m", 3, "clustered", 5_000_000, 1, False),    # configs[3] at full size
+       ("l3_5m", 3, "lattice", 5_000_000, 2, False)]
 
 
 def run(case):
@@ -70,6 +72,9 @@ if __name__ == "__main__":
     if os.path.exists(path):
         old = {r["name"]: r for r in json.load(open(path))["cases"]}
     cases = CASES + (BIG if "--big" in sys.argv else [])
+    if "--only" in sys.argv:
+        only = set(sys.argv[sys.argv.index("--only") + 1].split(","))
+        cases = [c for c in CASES + BIG if c[0] in only]
     for c in cases:
         old[c[0]] = run(c)
     json.dump({"generator": "tests/golden/make_golden.py", "rng": "splitmix64 counter RNG, voronoids_b200/pointgen.py",

@@ -84,11 +84,15 @@ def test_gpu_errors_are_loud(gpu_lib):
     assert ei.value.status == 2
 
 
-@pytest.mark.parametrize("name", ["u3_10k", "u3_100k", "u3_1m", "u2_10k", "u2_1m", "c3_100k", "l3_100k", "c3_500k", "l3_500k", "u3_set1000_100k"])
+@pytest.mark.parametrize("name", ["u3_10k", "u3_100k", "u3_1m", "u2_10k", "u2_1m", "c3_100k", "l3_100k", "c3_500k", "l3_500k", "u3_set1000_100k",
+                                  "c3_5m", "l3_5m"])   # the last two: BASELINE.json configs[3] at its stated size
 def test_gpu_golden_vectors(gpu_lib, oracle, golden, name):
     g = golden[name]
     t = _capi.Tree(gpu_lib, pointgen.make(g["kind"], g["n"], g["dim"], g["seed"]))
     try:
+        if g["n"] >= 5_000_000:
+            ok, fails = t.check_delaunay()
+            assert ok, fails
         e = t.edges()
         assert len(e) == g["n_edges"]
         assert oracle.edge_sha256(e) == g["sha256"]
@@ -122,6 +126,42 @@ def test_gpu_full_size_10m(gpu_lib, oracle, golden):
             assert cnt["simplices"] == g["live_simplices"]
     finally:
         t.close()
+
+
+def test_gpu_python_lazy_getters_and_device_input(gpu_lib, oracle, golden):
+    """`import voronoids` (lib.rs:127-134) on a 1M-point tree: device-resident input through __cuda_array_interface__ and
+    DLPack (no host copy of the coordinates), `.simplices` / `.vertices` as lazy mappings (an item in < 1 ms, nothing of
+    size O(n) materialised as Python objects)."""
+    import time
+    import torch
+    import voronoids
+    pts = pointgen.uniform(1_000_000, 3, 0)
+    d = torch.from_numpy(pts).cuda()
+    tree = voronoids.delaunay(d)
+    e = tree.edges()
+    g = golden["u3_1m"]
+    assert len(e) == g["n_edges"] and oracle.edge_sha256(e) == g["sha256"]
+    S = tree.simplices
+    assert not isinstance(S, dict) and len(S) == g["live_simplices"] + 4
+    t0 = time.perf_counter()
+    for k in range(5, 2005):
+        S[k]
+    assert (time.perf_counter() - t0) / 2000 < 1e-3
+    k = 5 + len(S) // 2
+    assert all(k in S[j].neighbors for j in S[k].neighbors)
+    V = tree.vertices
+    assert V[8 + 12345].point == pts[12345].tolist() and all((8 + 12345) in S[t].vertices for t in V[8 + 12345].simplex)
+    tree.close()
+
+    class OnlyDLPack:   # an array type that speaks DLPack but not __cuda_array_interface__
+        def __init__(self, t): self.t = t
+        def __dlpack__(self, stream=None): return self.t.__dlpack__()
+        def __dlpack_device__(self): return self.t.__dlpack_device__()
+    small = torch.from_numpy(pointgen.uniform(50_000, 2, 3)).cuda()
+    t2 = voronoids.delaunay(OnlyDLPack(small))
+    assert np.array_equal(t2.edges(), oracle.ExactDelaunay(small.cpu().numpy()).edges())
+    with pytest.raises(ValueError):
+        voronoids.delaunay(small.float())
 
 
 @pytest.mark.parametrize("dim", [2, 3])

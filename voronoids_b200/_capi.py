@@ -52,9 +52,9 @@ SYMBOLS = {
     "vor_set_option": (C.c_int, [C.c_char_p, C.c_double]),
     "vor_tree_set_stream": (None, [tree_p, C.c_void_p]),
 }
-N_STATS = 18
+N_STATS = 19
 STAT_NAMES = ("rounds", "attempts", "winners", "owner_resets", "compactions", "stages", "walk_steps", "tests", "killed", "created",
-              "exact_calls", "exact_zero", "duplicates", "simplex_slots", "aborted", "tests_completed", "sphere_undecided", "flagged")
+              "exact_calls", "exact_zero", "duplicates", "simplex_slots", "aborted", "tests_completed", "sphere_undecided", "flagged", "slots")
 
 
 def delaunay_batch_devices(lib, points, set_offsets, devices):
@@ -149,6 +149,20 @@ class Tree:
             self._check(lib.vor_tree_create_batch(self.dim, pp, off.ctypes.data_as(i64p), len(off) - 1, device, C.byref(self._h)))
             if insert:
                 self._check(lib.vor_tree_insert_batch(self._h, pp, off.ctypes.data_as(i64p)))
+
+    @classmethod
+    def from_device(cls, lib, ptr, n, dim, device=0, stream=None):
+        """DelaunayTree::new + insertion of every point from a DEVICE buffer of n x dim float64 (row-major, contiguous):
+        vor_tree_create_device + vor_tree_insert_device, no host copy of the coordinates."""
+        self = cls.__new__(cls)
+        self._lib = lib
+        self._h = tree_p()
+        self.duplicates = False
+        self.dim, self.n = dim, n
+        sp = C.c_void_p(stream) if stream else None
+        self._check(lib.vor_tree_create_device(dim, C.c_void_p(ptr), n, device, sp, C.byref(self._h)))
+        self._check(lib.vor_tree_insert_device(self._h, C.c_void_p(ptr), n, 1))
+        return self
 
     def _check(self, st):
         if st == 3:

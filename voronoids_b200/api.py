@@ -15,6 +15,8 @@ Ids: vertices 0..dim = super simplex, dim+1..2dim+1 = ghost copies, 2(dim+1)+i =
 sequential numbering, delaunay_tree.rs:173-174).  Simplex ids 1..dim+1 are the reference's ghost simplices
 (:467-502); real simplices follow in engine order (the reference's own ids depend on its insertion order).
 """
+from collections.abc import Mapping
+
 import numpy as np
 
 from . import _capi
@@ -52,24 +54,156 @@ _GHOSTS = {3: {1: [4, 0, 1, 2], 2: [5, 0, 2, 3], 3: [6, 0, 3, 1], 4: [7, 1, 2, 3
            2: {1: [3, 0, 1], 2: [4, 0, 2], 3: [5, 1, 2]}}
 
 
+# which ghost simplex lies behind a hull facet of the super simplex: the facet misses exactly one super vertex
+_GHOST_OF_MISSING = {3: np.array([4, 2, 3, 1]), 2: np.array([3, 2, 1])}
+
+
+class SimplexMap(Mapping):
+    """`DelaunayTree.simplices` (lib.rs:87-101) as a lazy mapping id -> PySimplex over the exported numpy arrays: an item
+    is built when it is asked for; nothing of size O(n) is materialised in Python objects (the PyO3 getter copies
+    the whole DashMap into a dict on every access, README.md:24)."""
+
+    def __init__(self, tree):
+        self._tree = tree
+        self._dim = tree.dim
+        self._m = tree.dim + 1
+        self._v, self._nb, self._c, self._r = tree.simplex_arrays()
+        self._first = self._m + 1          # ids 1..M are the reference's ghost simplices
+        self._n = len(self._v)
+        if self._n == 1 and int(self._v.max()) < self._m:
+            self._n = 0                    # nothing inserted yet: the only live simplex is the root, id 0 in the reference
+        self._ghost_nb = None
+
+    def _ghost_code(self):
+        """[n, M] ghost id behind every hull facet (0 where the facet is interior), computed once with numpy."""
+        if self._ghost_nb is None:
+            hull = self._nb < 0
+            tot = self._m * (self._m - 1) // 2       # 0 + 1 + ... + dim
+            face_sum = self._v.sum(axis=1, keepdims=True) - self._v
+            missing = np.where(hull, tot - face_sum, 0)
+            self._ghost_nb = np.where(hull, _GHOST_OF_MISSING[self._dim][np.clip(missing, 0, self._m - 1)], 0)
+        return self._ghost_nb
+
+    def __len__(self):
+        return self._n + self._m + (1 if self._n == 0 else 0)
+
+    def __iter__(self):
+        if self._n == 0:
+            yield 0
+        yield from range(1, self._m + 1)
+        yield from range(self._first, self._first + self._n)
+
+    def __contains__(self, k):
+        try:
+            k = int(k)
+        except (TypeError, ValueError):
+            return False
+        return (1 <= k < self._first + self._n) or (k == 0 and self._n == 0)
+
+    def __getitem__(self, k):
+        k = int(k)
+        ghosts = _GHOSTS[self._dim]
+        if k == 0 and self._n == 0:   # nothing inserted yet: the root simplex is alive (delaunay_tree.rs:458-466)
+            sv, cen, rad = self._tree._t.super_simplex()
+            return PySimplex(list(range(self._m)), cen.tolist(), rad, list(ghosts))
+        if 1 <= k <= self._m:
+            if self._n == 0:
+                return PySimplex(list(ghosts[k]), [0.0] * self._dim, 0.0, [0])
+            rows = np.nonzero((self._ghost_code() == k).any(axis=1))[0]
+            return PySimplex(list(ghosts[k]), [0.0] * self._dim, 0.0, (rows + self._first).tolist())
+        i = k - self._first
+        if not 0 <= i < self._n:
+            raise KeyError(k)
+        nb = self._nb[i]
+        if (nb < 0).any():
+            g = self._ghost_code()[i]
+            neigh = [int(self._first + nb[q]) if nb[q] >= 0 else int(g[q]) for q in range(self._m)]
+        else:
+            neigh = (nb + self._first).tolist()
+        return PySimplex(self._v[i].tolist(), self._c[i].tolist(), float(self._r[i]), neigh)
+
+
+class VertexMap(Mapping):
+    """`DelaunayTree.vertices` (lib.rs:73-85) as a lazy mapping id -> PyVertex over the exported CSR arrays."""
+
+    def __init__(self, tree):
+        self._dim = tree.dim
+        self._m = tree.dim + 1
+        self._coords, self._off, self._simps = tree._t.vertices()
+        self._first = self._m + 1
+        self._n = len(self._off) - 1
+        self._ghost_inc = {}
+        for gid, g in _GHOSTS[self._dim].items():
+            for q in g:
+                self._ghost_inc.setdefault(q, []).append(gid)
+
+    def __len__(self):
+        return self._n
+
+    def __iter__(self):
+        return iter(range(self._n))
+
+    def __contains__(self, k):
+        try:
+            return 0 <= int(k) < self._n
+        except (TypeError, ValueError):
+            return False
+
+    def __getitem__(self, k):
+        k = int(k)
+        if not 0 <= k < self._n:
+            raise KeyError(k)
+        inc = (self._simps[self._off[k]:self._off[k + 1]].astype(np.int64) + self._first).tolist()
+        return PyVertex(self._coords[k].tolist(), inc + self._ghost_inc.get(k, []))
+
+
+def _device_array(points):
+    """(ptr, n, dim, device, keepalive) when `points` lives on a CUDA device (__cuda_array_interface__ or DLPack), else None."""
+    cai = getattr(points, "__cuda_array_interface__", None)
+    keep = points
+    if cai is None and hasattr(points, "__dlpack__") and hasattr(points, "__dlpack_device__"):
+        dev_type, _ = points.__dlpack_device__()
+        if int(dev_type) != 2:                      # kDLCUDA
+            return None
+        import torch                                # plumbing only: DLPack capsule -> tensor -> pointer
+        keep = torch.from_dlpack(points)
+        cai = keep.__cuda_array_interface__
+    if cai is None:
+        return None
+    shape, typestr, strides = tuple(cai["shape"]), cai["typestr"], cai.get("strides")
+    if len(shape) != 2 or shape[1] not in (2, 3) or typestr not in ("<f8", "=f8", "|f8"):
+        raise ValueError("device points must be float64 [n, 2] or [n, 3]")
+    if strides is not None and tuple(strides) != (shape[1] * 8, 8):
+        raise ValueError("device points must be C-contiguous")
+    device = getattr(getattr(keep, "device", None), "index", None)
+    if device is None:
+        device = getattr(getattr(keep, "device", None), "id", 0) or 0
+    return int(cai["data"][0]), int(shape[0]), int(shape[1]), int(device), keep
+
+
 class DelaunayTree:
     """DelaunayTree<N,M> on the device (delaunay_tree.rs:24-30)."""
 
-    def __init__(self, points, device=0, _tree=None):
-        p = np.ascontiguousarray(points, dtype=np.float64)
-        if p.ndim != 2 or p.shape[1] not in (2, 3):
-            raise ValueError("points must be [n, 2] or [n, 3]")
-        self.dim = p.shape[1]
-        self._t = _tree if _tree is not None else _capi.Tree(lib(), p, device=device, insert=False)
+    def __init__(self, points, device=0, _tree=None, _dim=None):
+        if _tree is not None and _dim is not None:
+            self.dim = _dim
+            self._t = _tree
+        else:
+            p = np.ascontiguousarray(points, dtype=np.float64)
+            if p.ndim != 2 or p.shape[1] not in (2, 3):
+                raise ValueError("points must be [n, 2] or [n, 3]")
+            self.dim = p.shape[1]
+            self._t = _tree if _tree is not None else _capi.Tree(lib(), p, device=device, insert=False)
         self._cache = None
-        self._chunks = []   # inserted point arrays (kept by reference; concatenated only if .vertices is asked for)
+        self._smap = self._vmap = None
+        self._chunks = []   # inserted point arrays (kept by reference)
 
     new = classmethod(lambda cls, points, device=0: cls(points, device))
 
     # ---- mutation
     def add_points_to_tree(self, points):
         """delaunay_tree.rs:336-386"""
-        self._cache = None
+        self._cache = self._smap = self._vmap = None
         p = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, self.dim)
         self._t.insert(p, mode=1)
         self._chunks.append(p)
@@ -78,7 +212,7 @@ class DelaunayTree:
 
     def insert_point(self, point):
         """TreeUpdate::new + insert_point (delaunay_tree.rs:710-739, :125-211) for one point."""
-        self._cache = None
+        self._cache = self._smap = self._vmap = None
         p = np.asarray(point, dtype=np.float64).reshape(1, self.dim)
         self._t.insert(p, mode=0)
         self._chunks.append(p)
@@ -130,65 +264,20 @@ class DelaunayTree:
             self._cache = self._t.simplices(circumspheres=True)
         return self._cache
 
-    # ---- reference-shaped views (built on demand, like the PyO3 getters that copy the maps on every access)
+    # ---- reference-shaped views: lazy mappings over numpy arrays (the PyO3 getters copy whole maps on every access)
     @property
     def simplices(self):
-        m = self.dim + 1
-        v, nb, c, r = self.simplex_arrays()
-        first = m + 1  # ids 1..M are the ghosts
-        ghosts = _GHOSTS[self.dim]
-        face_to_ghost = {frozenset(g[1:]): gid for gid, g in ghosts.items()}
-        out = {}
-        ghost_nb = {gid: [] for gid in ghosts}
-        vl, nl, cl, rl = v.tolist(), nb.tolist(), c.tolist(), r.tolist()
-        for i in range(len(vl)):
-            neigh = []
-            for k in range(m):
-                j = nl[i][k]
-                if j >= 0:
-                    neigh.append(first + j)
-                else:
-                    gid = face_to_ghost[frozenset(vl[i][q] for q in range(m) if q != k)]
-                    neigh.append(gid)
-                    ghost_nb[gid].append(first + i)
-            out[first + i] = PySimplex(vl[i], cl[i], rl[i], neigh)
-        if not vl:  # nothing inserted yet: the root simplex 0 is alive (delaunay_tree.rs:458-466)
-            sv, cen, rad = self._t.super_simplex()
-            out[0] = PySimplex(list(range(m)), cen.tolist(), rad, list(ghosts))
-            ghost_nb = {gid: [0] for gid in ghosts}
-        for gid, g in ghosts.items():
-            out[gid] = PySimplex(list(g), [0.0] * self.dim, 0.0, ghost_nb[gid])
-        return out
+        """id -> PySimplex (lib.rs:87-101)"""
+        if self._smap is None:
+            self._smap = SimplexMap(self)
+        return self._smap
 
     @property
     def vertices(self):
-        m = self.dim + 1
-        sv = self._t.super_simplex()[0]
-        n_real = self._t.counts()["vertices"] - 2 * m
-        first = m + 1
-        # Vertex.simplex from the device (vor_tree_export_vertices): CSR of export indices per reference vertex id
-        _, off, simps = self._t.vertices()
-        ids = (simps.astype(np.int64) + first).tolist()
-        inc = {q: ids[off[q]:off[q + 1]] for q in range(len(off) - 1) if off[q + 1] > off[q]}
-        ghosts = _GHOSTS[self.dim]
-        for gid, g in ghosts.items():
-            for q in g:
-                inc.setdefault(q, []).append(gid)
-        out = {}
-        # super + ghost coordinates (delaunay_tree.rs:407-412 / :559-566)
-        ghost_of = {3: [0, 0, 0, 1], 2: [0, 1, 2]}[self.dim]
-        for k in range(m):
-            out[k] = PyVertex(sv[k].tolist(), inc.get(k, []))
-            out[m + k] = PyVertex(sv[ghost_of[k]].tolist(), inc.get(m + k, []))
-        pts = self._points()
-        for i in range(n_real):
-            out[2 * m + i] = PyVertex(pts[i].tolist(), inc.get(2 * m + i, []))
-        return out
-
-    def _points(self):
-        if len(self._chunks) != 1:
-            self._chunks = [np.concatenate(self._chunks, axis=0) if self._chunks else np.zeros((0, self.dim))]
-        return self._chunks[0]
+        """id -> PyVertex (lib.rs:73-85)"""
+        if self._vmap is None:
+            self._vmap = VertexMap(self)
+        return self._vmap
 
     def close(self):
         self._t.close()
@@ -204,6 +293,13 @@ def delaunay(points, device=0):
     The reference inserts the first 1e5 points one by one and the rest through add_points_to_tree; both produce
     the (unique) Delaunay triangulation of points + super vertices, which is what the device rounds compute.
     """
+    dev = _device_array(points)
+    if dev is not None:
+        # zero-copy input: points already on a CUDA device (__cuda_array_interface__ / DLPack): no host round trip
+        ptr, n, dim, dev_index, keep = dev
+        t = PyDelauanyTree(None, _tree=_capi.Tree.from_device(lib(), ptr, n, dim, device=dev_index), _dim=dim)
+        t._device_points = keep
+        return t
     p = np.ascontiguousarray(points, dtype=np.float64)
     if p.ndim != 2 or p.shape[1] not in (2, 3):
         raise ValueError("points must be [n, 2] or [n, 3]")

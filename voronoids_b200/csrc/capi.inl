@@ -439,7 +439,7 @@ vor_status vor_tree_stats(vor_tree *t, uint64_t *s) {
             s[0] = e.rs.rounds; s[1] = e.rs.attempts; s[2] = e.rs.winners; s[3] = e.rs.owner_resets; s[4] = e.rs.compactions; s[5] = e.rs.stages;
             s[6] = c.walk_steps; s[7] = c.tests; s[8] = c.killed; s[9] = c.created; s[10] = c.exact_calls; s[11] = c.exact_zero;
             s[12] = (uint64_t)c.ndup; s[13] = (uint64_t)c.ntets; s[14] = c.aborted; s[15] = c.tests_ok; s[16] = c.sph_undecided;
-            s[17] = (uint64_t)c.nflag_set;
+            s[17] = (uint64_t)c.nflag_set; s[18] = e.rs.slots;
             return VOR_OK;
         });
     });

@@ -79,7 +79,7 @@ struct EngineError {
 };
 
 struct RunStats {
-    unsigned long long rounds = 0, attempts = 0, winners = 0, owner_resets = 0, compactions = 0, stages = 0;
+    unsigned long long rounds = 0, attempts = 0, winners = 0, owner_resets = 0, compactions = 0, stages = 0, slots = 0;
 };
 
 template <int D> class Engine {
@@ -637,6 +637,7 @@ template <int D> class Engine {
                 launch_round<32>(aa, ca, sel, slowNow);
                 epoch--;
                 rs.rounds++;
+                rs.slots += (unsigned long long)nsel;
             }
             pull_counters();
             check_device_error("round");
