@@ -41,7 +41,12 @@ WORKLOADS = {
     # batch of independent sets (configs[4]): 64 sets x 100k points per GPU in ONE device store; set s of rank r uses
     # seed 1000 + 64 r + s
     "b3_64x100k": (3, "batch", 6_400_000, 1000, "batch of 64 independent 3D uniform sets x 100k points per GPU (configs[4] shape)"),
+    # BASELINE.json configs[4] at its stated size: 8,192 sets x 100k points, FIXED total split over the ranks in contiguous
+    # blocks (strong scaling), every rank streaming its block through vor_delaunay_batch_stream in chunks of 128 sets;
+    # set s uses seed 1000 + s whatever the rank count; STREAM_SETS overrides the set count (VOR_STREAM_SETS)
+    "b3_8192x100k": (3, "stream", 819_200_000, 1000, "batch of 8,192 independent 3D uniform sets x 100k points (BASELINE.json configs[4]), sharded over the GPUs"),
 }
+STREAM_SETS = int(os.environ.get("VOR_STREAM_SETS", "8192"))
 BATCH_SETS, BATCH_SIZE = 64, 100_000
 
 
@@ -130,7 +135,7 @@ def host_threads():
 def reference_points(name, ns):
     from voronoids_b200 import pointgen
     dim, kind, n, seed, desc = WORKLOADS[name]
-    if kind == "batch":
+    if kind in ("batch", "stream"):
         return pointgen.uniform(min(ns, BATCH_SIZE), dim, seed)   # one set of the batch (sets are independent units)
     if kind == "uniform":
         return pointgen.uniform(ns, dim, seed)                    # counter-based generator: a prefix of the workload
@@ -196,7 +201,7 @@ def reference_arm(name, steps, warmup):
     r_par = (cal["n_parallel"] / max(cal["t_parallel"], 1e-9)) if cal["n_parallel"] else r_seq
     per_step = budget_s / max(steps, 1)
     ns = int(min(CPU_FULL_SAMPLE[dim], max(300_000, 100_000 + (per_step - 100_000 / r_seq) * r_par)))
-    ns = min(ns, WORKLOADS[name][2] if WORKLOADS[name][1] != "batch" else BATCH_SIZE)
+    ns = min(ns, WORKLOADS[name][2] if WORKLOADS[name][1] not in ("batch", "stream") else BATCH_SIZE)
     pts = reference_points(name, ns)
     runs = [reference_once(pts, nthreads) for _ in range(steps)]
     t = sum(r["t_total"] for r in runs) / len(runs)
@@ -210,6 +215,104 @@ def reference_arm(name, steps, warmup):
           "sequential_phase_pts_per_s": runs[0]["n_sequential"] / ts if ts > 0 else None,
           "parallel_phase_pts_per_s": (runs[0]["n_parallel"] / tp) if runs[0]["n_parallel"] and tp > 0 else None}
     return cb, t, n
+
+
+def run_stream(args, name, rank, world, local_rank):
+    """configs[4]: a fixed batch of STREAM_SETS sets x 100k points, contiguous blocks of sets per rank, no data-path collective."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    import voronoids_b200 as vb
+    from voronoids_b200 import _capi, _lib, pointgen, sharding
+    lib = _lib.lib()
+    dim, kind, _, seed, desc = WORKLOADS[name]
+    n_total_sets = STREAM_SETS
+    mine = sharding.shard_range(n_total_sets, world, rank)
+    ns = len(mine)
+    n_pts = ns * BATCH_SIZE
+    # generated on the device, 512 sets at a time (same generator as pointgen.uniform, seed 1000 + s)
+    pts_dev = torch.empty((max(n_pts, 1), dim), dtype=torch.float64, device="cuda")
+    for lo in range(0, ns, 512):
+        k = min(512, ns - lo)
+        pts_dev[lo * BATCH_SIZE:(lo + k) * BATCH_SIZE] = pointgen.uniform_sets_torch(k, BATCH_SIZE, dim, seed + mine.start + lo)
+    off = np.arange(ns + 1, dtype=np.int64) * BATCH_SIZE
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        ne, ck = _capi.delaunay_batch_stream(lib, int(pts_dev.data_ptr()), off, device=local_rank, dim=dim) if ns else (np.zeros(0, np.uint64),) * 2
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), ne, ck
+
+    for _ in range(args.warmup):
+        step_device()
+    launches0 = lib.vor_kernel_launches()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_ms = []
+    for _ in range(args.steps):
+        ms, ne, ck = step_device()
+        t_ms.append(ms)
+    barrier()
+    clocks = sampler.stop()
+    launches = (lib.vor_kernel_launches() - launches0) // max(args.steps, 1)
+    tot = torch.tensor([sum(t_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tot.item()) / args.steps
+    n_all = n_total_sets * BATCH_SIZE
+    value = n_all / (ms_per_step * 1e-3)
+    per_set = sharding.gather_per_set({mine.start + i: (int(ne[i]), int(ck[i])) for i in range(ns)}, n_total_sets)
+    digest = hashlib.sha256(np.array(per_set, dtype=np.uint64).tobytes()).hexdigest()
+
+    # end to end: host buffers in (pageable, staged through pinned chunks, next chunk's copy under the current chunk's rounds),
+    # per-set results out
+    e2e = None
+    if not args.no_e2e:
+        pts_host = pts_dev.cpu().numpy()
+        def step_e2e():
+            t0 = time.perf_counter()
+            a, b = vb.delaunay_batch_stream(pts_host, off, device=local_rank) if ns else (None, None)
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0, a, b
+        step_e2e()
+        barrier()
+        dts = []
+        for _ in range(max(1, min(args.steps, 2))):
+            dt, a, b = step_e2e()
+            dts.append(dt)
+        barrier()
+        assert ns == 0 or (np.array_equal(a, ne) and np.array_equal(b, ck))
+        te = torch.tensor([sum(dts) / len(dts)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_all / float(te.item()), "unit": "points/s", "h2d_bytes_per_step": int(n_pts * dim * 8), "d2h_bytes_per_step": int(ns * 16),
+               "api": "voronoids_b200.delaunay_batch_stream(points, set_offsets) -> per-set (n_edges, checksum64)", "edges": int(sum(x[0] for x in per_set))}
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_sample_record(name, host_threads(), BATCH_SIZE, with_one_core=False)
+    if rank == 0:
+        cfg = bench_config(desc, n_all // world, dim, world)
+        cfg.update({"sets_total": n_total_sets, "points_per_set": BATCH_SIZE, "sets_per_gpu": -(-n_total_sets // world), "chunk_sets": 128,
+                    "parallelism": f"{n_total_sets} independent sets in contiguous blocks over {world} GPU(s); no data-path collective, per-set results gathered on the host",
+                    "per_set_results_sha256": digest})
+        line = {"metric": "delaunay_points_inserted_per_sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": None, "cpu_baseline": cpu_baseline, "e2e": e2e,
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
 
 
 def main():
@@ -251,6 +354,8 @@ def main():
     os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line (NCCL prints its version there otherwise)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if kind == "stream":
+        return run_stream(args, name, rank, world, local_rank)
     import voronoids_b200 as vb
     from voronoids_b200 import _capi, _lib
     lib = _lib.lib()

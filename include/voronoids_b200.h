@@ -37,7 +37,9 @@ typedef enum vor_status {
     VOR_ERR_DUPLICATE_POINT = 3, /* duplicate input points were dropped (undefined behaviour in the reference) */
     VOR_ERR_CUDA = 4,
     VOR_ERR_OOM = 5,
-    VOR_ERR_CAPACITY = 6,        /* a conflict region exceeded the overflow scratch */
+    VOR_ERR_CAPACITY = 6,        /* a conflict region exceeded the overflow scratch, or the tree would exceed its 2^29
+                                  * simplex slots (~19M 3D / ~85M 2D points per tree, all sets and inserts together;
+                                  * checked before the insert changes anything) */
     VOR_ERR_RANGE = 7,           /* coordinate dynamic range beyond the exact-arithmetic limb budget */
     VOR_ERR_OUTSIDE = 8,         /* a point lies outside the super simplex built by vor_tree_create */
     VOR_ERR_INTERNAL = 9,
@@ -67,6 +69,19 @@ vor_status vor_delaunay_batch(int dim, const double *points, const int64_t *set_
                               vor_tree **trees, int64_t *shard);
 vor_status vor_tree_create_batch_device(int dim, const double *d_points, const int64_t *set_offsets, size_t n_sets, int device,
                                         void *cuda_stream, vor_tree **out);
+
+/* Streaming batch driver (BASELINE.json configs[4]: 8,192 independent sets x 100k points; the caller-side pattern of
+ * examples/parallel_insert.rs:56-78): the sets are triangulated in chunks of at most chunk_sets sets / chunk_points points
+ * (0 = defaults: 128 sets, what one 2^29-slot store holds), one batch tree per chunk, stores recycled; with host input
+ * (points_on_device == 0) the copy of the next chunk overlaps the current chunk's rounds.  One device per call: run one
+ * call per device (thread or process) on contiguous blocks of sets -- the sets share nothing.
+ * Per set: n_edges[s], checksums[s] (order-independent 64-bit checksum of the set-local canonical edge list, the same
+ * function as vor_tree_edges_device); either may be NULL.  cb (optional) is called once per chunk with the chunk's
+ * canonical edge list on the host: indices are local to the chunk's first point (first_point = its offset in `points`);
+ * the list is only valid during the call. */
+typedef void (*vor_chunk_cb)(void *user, size_t first_set, size_t n_sets, int64_t first_point, const uint32_t *edges, size_t n_edges);
+vor_status vor_delaunay_batch_stream(int dim, const double *points, int points_on_device, const int64_t *set_offsets, size_t n_sets, int device,
+                                     size_t chunk_sets, size_t chunk_points, uint64_t *n_edges, uint64_t *checksums, vor_chunk_cb cb, void *user);
 void vor_tree_destroy(vor_tree *t);
 
 /* insert n more points; input index of points[i] = (points inserted so far) + i.
@@ -133,6 +148,10 @@ vor_status vor_find_placement(const int64_t *offsets, const int32_t *ids, size_t
  * stored circumsphere filter (the cached centre/radius of delaunay_tree.rs:11-16, here a certified filter) contradicting
  * the exact predicate on a simplex's own vertices or on the opposite vertices of its neighbours. */
 vor_status vor_tree_check_delaunay(vor_tree *t, int *ok, int32_t *fail_counts);
+/* TEST HOOK for the checker above (the reference's check_delaunay is never fed a broken mesh either,
+ * tests/test_delaunay_tree.rs:37): damages one interior simplex of a finished tree so that fail counter `kind`
+ * (0..5, order of fail_counts) must fire.  The tree is unusable for further inserts afterwards. */
+vor_status vor_debug_corrupt(vor_tree *t, int kind);
 
 /* bootstrap data: super-simplex vertices [(dim+1) x dim] per set, bounding-sphere centre [dim] and 10x radius */
 vor_status vor_tree_super_simplex(vor_tree *t, size_t set, double *super_vertices, double *center, double *radius);

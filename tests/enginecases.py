@@ -209,3 +209,52 @@ def case_batch_devices(lib, O, dim, devices, sizes=(1500, 300, 2000, 2, 777, 120
         for t in trees:
             if t is not None:
                 t.close()
+
+
+def case_check_delaunay_rejects(lib, dim, n=4000):
+    """check_delaunay (delaunay_tree.rs:512-541) must REJECT a damaged mesh: each of the six failure classes of the
+    checker is provoked through the test hook vor_debug_corrupt and must fire (the reference's own test discards the
+    checker's verdict, tests/test_delaunay_tree.rs:37, and never feeds it a broken mesh)."""
+    names = ["orientation", "dead neighbour", "asymmetric adjacency", "facet mismatch", "not Delaunay", "sphere filter"]
+    for kind in range(6):
+        t = _capi.Tree(lib, pointgen.uniform(n, dim, 21))
+        try:
+            ok, fails = t.check_delaunay()
+            assert ok and not fails.any()
+            assert lib.vor_debug_corrupt(t._h, kind) == 0
+            ok, fails = t.check_delaunay()
+            assert not ok, f"a mesh with a {names[kind]} defect was accepted"
+            assert fails[kind] > 0, (names[kind], fails)
+        finally:
+            t.close()
+    t = _capi.Tree(lib, pointgen.uniform(100, dim, 21))
+    assert lib.vor_debug_corrupt(t._h, 9) == 10     # VOR_ERR_ARG
+    t.close()
+
+
+def case_batch_stream(lib, O, dim, sizes, chunk_sets, chunk_points=0, sample=None, first_seed=1000):
+    """vor_delaunay_batch_stream: per-set (n_edges, checksum64) equal the exact oracle's for the sets in `sample`
+    (default: all), whatever the chunking; the per-chunk callback hands out the chunk's canonical edge list."""
+    sets = [pointgen.uniform(n, dim, first_seed + s) for s, n in enumerate(sizes)]
+    off = np.zeros(len(sets) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(sizes)
+    allp = np.concatenate(sets, axis=0)
+    got = {}
+
+    def on_chunk(first_set, n_sets, first_point, edges):
+        assert first_point == off[first_set]
+        for s in range(first_set, first_set + n_sets):
+            lo, hi = off[s] - first_point, off[s + 1] - first_point
+            a = np.searchsorted(edges[:, 0], lo, side="left")
+            b = np.searchsorted(edges[:, 0], hi, side="left")
+            got[s] = (edges[a:b].astype(np.int64) - lo).astype(np.uint32)
+    ne, ck = _capi.delaunay_batch_stream(lib, allp, off, chunk_sets=chunk_sets, chunk_points=chunk_points, on_chunk=on_chunk)
+    assert sorted(got) == list(range(len(sets)))
+    for s in (range(len(sets)) if sample is None else sample):
+        e = O.ExactDelaunay(sets[s]).edges()
+        assert int(ne[s]) == len(e) and int(ck[s]) == _capi.edge_checksum_host(e), s
+        assert np.array_equal(got[s], e)
+    # without a callback, and with everything in one chunk: same per-set results
+    ne2, ck2 = _capi.delaunay_batch_stream(lib, allp, off, chunk_sets=len(sets) + 5)
+    assert np.array_equal(ne, ne2) and np.array_equal(ck, ck2)
+    return ne, ck

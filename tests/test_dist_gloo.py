@@ -27,6 +27,12 @@ def _worker(rank, world, port, q):
     local, tree = sharding.triangulate_sets(lib, sets)
     tree.close()
     res = sharding.gather_per_set({mine[k]: v for k, v in local.items()}, N_SETS)
+    # the streaming driver on this rank's block (chunks of 2 sets): bench.py --workload b3_8192x100k does exactly this
+    off = np.zeros(len(sets) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(x) for x in sets])
+    ne, ck = _capi.delaunay_batch_stream(lib, np.concatenate(sets, axis=0), off, chunk_sets=2)
+    res_stream = sharding.gather_per_set({mine[k]: (int(ne[k]), int(ck[k])) for k in range(len(sets))}, N_SETS)
+    assert res_stream == res
     tmax = sharding.max_over_ranks(1.0 + rank)
     tot = sharding.sum_over_ranks(sum(SIZES[s] for s in mine))
     if rank == 0:

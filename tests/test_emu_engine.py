@@ -55,6 +55,16 @@ def test_emu_batch_over_devices(emu_lib, oracle, devices):
     ec.case_batch_devices(emu_lib, oracle, 3, devices)
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_emu_check_delaunay_rejects_broken_meshes(emu_lib, dim):
+    ec.case_check_delaunay_rejects(emu_lib, dim)
+
+
+@pytest.mark.parametrize("dim,chunk_sets,chunk_points", [(3, 3, 0), (2, 2, 0), (3, 100, 2500)])
+def test_emu_batch_stream(emu_lib, oracle, dim, chunk_sets, chunk_points):
+    ec.case_batch_stream(emu_lib, oracle, dim, [900, 300, 1200, 2, 777, 1000, 450], chunk_sets, chunk_points)
+
+
 def test_emu_overflow_scratch_and_compaction(emu_lib, oracle):
     # tiny regular slots force the overflow path; a small attempt budget forces many rounds + list compaction
     emu_lib.vor_set_option(b"capk", 8.0)
@@ -97,3 +107,11 @@ def test_emu_owner_epoch_reset(emu_lib, oracle):
         assert st["rounds"] > 50
     finally:
         emu_lib.vor_set_option(b"slot_cap", float(1 << 19))
+
+
+def test_cpp_header_program_on_the_emulation(emu_lib, oracle, tmp_path):
+    """include/voronoids.hpp compiles and a program written against it (the crate's API names) gives the oracle's edges;
+    linked to the kernel emulation here, to the product library in tests/test_gpu_engine.py"""
+    import os
+    import cppcase
+    cppcase.run(tmp_path, oracle, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "libvor_kernel_emu.so"), n=1500)

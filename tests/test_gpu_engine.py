@@ -1,5 +1,7 @@
 """Parity tests proper: the product library (hand-written sm_100a CUDA behind the C ABI) on a B200 against the
 exact oracle, the committed golden vectors, and size-independent properties at BASELINE.json's full sizes."""
+import os
+
 import numpy as np
 import pytest
 
@@ -8,6 +10,7 @@ import predcases as pc
 from voronoids_b200 import _capi, pointgen
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("dim,kind,n", [(3, "uniform", 10_000), (3, "uniform", 200_000), (2, "uniform", 200_000), (3, "clustered", 100_000),
@@ -126,6 +129,48 @@ def test_gpu_full_size_10m(gpu_lib, oracle, golden):
             assert cnt["simplices"] == g["live_simplices"]
     finally:
         t.close()
+
+
+def test_gpu_batch_stream_small(gpu_lib, oracle):
+    ec.case_batch_stream(gpu_lib, oracle, 3, [20_000, 300, 50_000, 2, 7777, 10_000, 30_000], chunk_sets=3)
+    ec.case_batch_stream(gpu_lib, oracle, 2, [20_000, 300, 50_000, 2, 7777, 10_000, 30_000], chunk_sets=100, chunk_points=60_000)
+
+
+@pytest.mark.slow
+def test_gpu_batch_stream_1024_sets_of_100k(gpu_lib, oracle, golden):
+    """BASELINE.json configs[4] at 1/8 of its set count on ONE GPU: 1,024 independent 3D sets x 100k points (102.4M points,
+    8 chunks of 128 sets) through the streaming driver, device-resident input generated on the device with the same
+    generator; a seeded sample of 16 sets + set 0 (golden u3_set1000_100k) against the exact oracle."""
+    import torch
+    import voronoids
+    n_sets, n = 1024, 100_000
+    d = pointgen.uniform_sets_torch(n_sets, n, 3, 1000)
+    off = np.arange(n_sets + 1, dtype=np.int64) * n
+    ne, ck = voronoids.delaunay_batch_stream(d, off)
+    g = golden["u3_set1000_100k"]
+    assert int(ne[0]) == g["n_edges"] and int(ck[0]) == g["checksum64"]
+    rng = np.random.default_rng(2026)
+    for s in sorted(rng.choice(n_sets, size=16, replace=False).tolist()):
+        pts = pointgen.uniform(n, 3, 1000 + s)
+        assert np.array_equal(d[s * n:(s + 1) * n].cpu().numpy(), pts)       # same generator on the device
+        e = oracle.ExactDelaunay(pts).edges()
+        assert int(ne[s]) == len(e) and int(ck[s]) == _capi.edge_checksum_host(e), s
+    assert (ne > 700_000).all() and len(set(ck.tolist())) == n_sets
+    # host input (copies of the chunks overlap the rounds): the first 256 sets give the same per-set results
+    h = d[:256 * n].cpu().numpy()
+    ne2, ck2 = voronoids.delaunay_batch_stream(h, off[:257])
+    assert np.array_equal(ne2, ne[:256]) and np.array_equal(ck2, ck[:256])
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_gpu_check_delaunay_rejects_broken_meshes(gpu_lib, dim):
+    ec.case_check_delaunay_rejects(gpu_lib, dim, n=50_000)
+
+
+def test_gpu_cpp_header_program(gpu_lib, oracle, tmp_path):
+    """a program written against include/voronoids.hpp (the C++ mirror of the Rust API), linked to the product library"""
+    import cppcase
+    cppcase.run(tmp_path, oracle, os.path.join(ROOT, "voronoids_b200", "libvoronoids_b200.so"), n=30_000)
 
 
 def test_gpu_python_lazy_getters_and_device_input(gpu_lib, oracle, golden):

@@ -14,7 +14,7 @@ plus what the reference leaves implicit: tree.edges() (canonical Delaunay graph)
 All compute runs in hand-written sm_100a CUDA behind the C ABI of include/voronoids_b200.h; the library is loaded
 lazily so that importing the package (and pointgen) works on a machine without the built extension.
 """
-from .api import DelaunayTree, PyDelauanyTree, PySimplex, PyVertex, delaunay, delaunay_batch  # noqa: F401
+from .api import DelaunayTree, PyDelauanyTree, PySimplex, PyVertex, delaunay, delaunay_batch, delaunay_batch_stream  # noqa: F401
 from . import geometry, scheduler  # noqa: F401
 
-__all__ = ["delaunay", "delaunay_batch", "DelaunayTree", "PyDelauanyTree", "PySimplex", "PyVertex", "geometry", "scheduler"]
+__all__ = ["delaunay", "delaunay_batch", "delaunay_batch_stream", "DelaunayTree", "PyDelauanyTree", "PySimplex", "PyVertex", "geometry", "scheduler"]

@@ -38,6 +38,9 @@ SYMBOLS = {
     "vor_make_queue": (C.c_int, [tree_p, dp, C.c_size_t, i64p, i32p, C.c_size_t, szp]),
     "vor_find_placement": (C.c_int, [i64p, i32p, C.c_size_t, u64p, C.c_int]),
     "vor_tree_check_delaunay": (C.c_int, [tree_p, C.POINTER(C.c_int), i32p]),
+    "vor_debug_corrupt": (C.c_int, [tree_p, C.c_int]),
+    "vor_delaunay_batch_stream": (C.c_int, [C.c_int, C.c_void_p, C.c_int, i64p, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, u64p, u64p, C.c_void_p,
+                                            C.c_void_p]),
     "vor_tree_super_simplex": (C.c_int, [tree_p, C.c_size_t, dp, dp, dp]),
     "vor_tree_stats": (C.c_int, [tree_p, u64p]),
     "vor_tree_profile": (C.c_int, [tree_p, dp]),
@@ -55,6 +58,35 @@ SYMBOLS = {
 N_STATS = 19
 STAT_NAMES = ("rounds", "attempts", "winners", "owner_resets", "compactions", "stages", "walk_steps", "tests", "killed", "created",
               "exact_calls", "exact_zero", "duplicates", "simplex_slots", "aborted", "tests_completed", "sphere_undecided", "flagged", "slots")
+
+
+CHUNK_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int64, C.POINTER(C.c_uint32), C.c_size_t)
+
+
+def delaunay_batch_stream(lib, points, set_offsets, device=0, chunk_sets=0, chunk_points=0, on_chunk=None, dim=None):
+    """vor_delaunay_batch_stream.  points: host float64 [n, dim] array, or an int device pointer (then pass dim).
+    Returns (n_edges uint64 [n_sets], checksum64 uint64 [n_sets]); on_chunk(first_set, n_sets, first_point, edges[m,2])."""
+    off = np.ascontiguousarray(set_offsets, dtype=np.int64)
+    ns = len(off) - 1
+    ne = np.zeros(ns, dtype=np.uint64)
+    ck = np.zeros(ns, dtype=np.uint64)
+    if isinstance(points, int):
+        ptr, on_dev = C.c_void_p(points), 1
+    else:
+        p = np.ascontiguousarray(points, dtype=np.float64)
+        dim = p.shape[1]
+        ptr, on_dev = C.c_void_p(p.ctypes.data), 0
+    cb = None
+    if on_chunk is not None:
+        def _cb(user, first_set, n_sets, first_point, edges, m):
+            a = np.ctypeslib.as_array(edges, shape=(m, 2)).copy() if m else np.zeros((0, 2), dtype=np.uint32)
+            on_chunk(int(first_set), int(n_sets), int(first_point), a)
+        cb = CHUNK_CB(_cb)
+    st = lib.vor_delaunay_batch_stream(dim, ptr, on_dev, off.ctypes.data_as(i64p), ns, device, chunk_sets, chunk_points,
+                                       ne.ctypes.data_as(u64p), ck.ctypes.data_as(u64p), C.cast(cb, C.c_void_p) if cb else None, None)
+    if st not in (0, 3):
+        raise VorError(st, lib.vor_last_error().decode())
+    return ne, ck
 
 
 def delaunay_batch_devices(lib, points, set_offsets, devices):

@@ -343,3 +343,18 @@ def delaunay_batch(point_sets, device=0):
     allp = np.concatenate(sets, axis=0)
     t = _capi.Tree(lib(), allp, device=device, set_offsets=off)
     return BatchResult(t, off)
+
+
+def delaunay_batch_stream(points, set_offsets, device=0, chunk_sets=0, chunk_points=0, on_chunk=None):
+    """Batches far beyond one device store (BASELINE.json configs[4]: 8,192 sets x 100k points; the batch loop of
+    examples/parallel_insert.rs:56-78): the sets are triangulated chunk by chunk (vor_delaunay_batch_stream), the copy of
+    the next chunk overlapping the rounds of the current one.  `points`: float64 [n, dim] on the host, or a device array
+    (__cuda_array_interface__ / DLPack) holding all sets.  Returns (n_edges, checksum64) per set as uint64 arrays;
+    on_chunk(first_set, n_sets, first_point, edges) receives every chunk's canonical edge list (chunk-local indices)."""
+    dev = _device_array(points)
+    if dev is not None:
+        ptr, n, dim, dev_index, keep = dev
+        return _capi.delaunay_batch_stream(lib(), ptr, set_offsets, device=dev_index, chunk_sets=chunk_sets, chunk_points=chunk_points,
+                                           on_chunk=on_chunk, dim=dim)
+    return _capi.delaunay_batch_stream(lib(), np.ascontiguousarray(points, dtype=np.float64), set_offsets, device=device, chunk_sets=chunk_sets,
+                                       chunk_points=chunk_points, on_chunk=on_chunk)

@@ -11,10 +11,12 @@ namespace {
 
 thread_local std::string g_err;
 vor::EngineOptions g_opts;
-bool g_opts_init = false;
+std::once_flag g_opts_once;
+std::mutex g_opts_mu;   // vor_delaunay_batch runs one host thread per device: options are read under this lock
 
 vor::EngineOptions current_options() {
-    if (!g_opts_init) { vor::options_from_env(g_opts); g_opts_init = true; }
+    std::call_once(g_opts_once, [] { vor::options_from_env(g_opts); });
+    std::lock_guard<std::mutex> lk(g_opts_mu);
     return g_opts;
 }
 
@@ -72,6 +74,7 @@ void vor_release_memory(void) { vor::be::release_cached(); }
 
 int vor_set_option(const char *name, double value) {
     current_options();
+    std::lock_guard<std::mutex> lk(g_opts_mu);
     const std::string n(name ? name : "");
     if (n == "slot_cap") g_opts.slot_cap = (int)value;
     else if (n == "min_attempt") g_opts.min_attempt = (int)value;
@@ -146,13 +149,17 @@ vor_status vor_delaunay_batch(int dim, const double *points, const int64_t *set_
     for (size_t d = 0; d < n_dev; d++) {
         trees[d] = nullptr;
         th.emplace_back([&, d]() {
-            const size_t lo = (size_t)shard[d], hi = (size_t)shard[d + 1];
-            if (hi <= lo) return;   // more devices than sets: nothing for this one
-            std::vector<int64_t> off(hi - lo + 1);
-            for (size_t s = lo; s <= hi; s++) off[s - lo] = set_offsets[s] - set_offsets[lo];
-            const double *p = points + (size_t)set_offsets[lo] * dim;
-            vor_status r = vor_tree_create_batch(dim, p, off.data(), hi - lo, devices[d], &trees[d]);
-            if (r == VOR_OK) r = vor_tree_insert_batch(trees[d], p, off.data());
+            // nothing may escape a thread body (std::terminate): allocation failures become a status like everything else
+            const vor_status r = guarded([&]() -> vor_status {
+                const size_t lo = (size_t)shard[d], hi = (size_t)shard[d + 1];
+                if (hi <= lo) return VOR_OK;   // more devices than sets: nothing for this one
+                std::vector<int64_t> off(hi - lo + 1);
+                for (size_t s = lo; s <= hi; s++) off[s - lo] = set_offsets[s] - set_offsets[lo];
+                const double *p = points + (size_t)set_offsets[lo] * dim;
+                vor_status q = vor_tree_create_batch(dim, p, off.data(), hi - lo, devices[d], &trees[d]);
+                if (q == VOR_OK) q = vor_tree_insert_batch(trees[d], p, off.data());
+                return q;
+            });
             if (r != VOR_OK && r != VOR_ERR_DUPLICATE_POINT) { st[d] = r; msg[d] = vor_last_error(); }   // g_err is thread-local
         });
     }
@@ -164,6 +171,102 @@ vor_status vor_delaunay_batch(int dim, const double *points, const int64_t *set_
             return st[d];
         }
     return VOR_OK;
+}
+
+// Streaming driver for batches far beyond one device store (BASELINE.json configs[4]: 8,192 sets x 100k points; the caller
+// pattern of examples/parallel_insert.rs:56-78, a loop over batches).  The sets of this call are cut into chunks of at
+// most `chunk_sets` sets / `chunk_points` points; every chunk is ONE batch tree (create + insert + edge list) whose store
+// goes back to the caching allocator for the next chunk; with host input the copy of chunk k+1 (pinned staging, its own
+// stream, a helper thread) overlaps the rounds of chunk k.  Results per set: edge count and checksum64 of the set-local
+// canonical edge list; `cb` (optional) receives every chunk's edge list (global input indices of this call, on the host).
+vor_status vor_delaunay_batch_stream(int dim, const double *points, int points_on_device, const int64_t *set_offsets, size_t n_sets, int device,
+                                     size_t chunk_sets, size_t chunk_points, uint64_t *n_edges, uint64_t *checksums, vor_chunk_cb cb, void *user) {
+    return guarded([&]() -> vor_status {
+        if (!points || !set_offsets || n_sets < 1 || (dim != 2 && dim != 3) || (!n_edges && !checksums && !cb)) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(device);
+        if (chunk_sets == 0) chunk_sets = 128;
+        if (chunk_points == 0) chunk_points = dim == 3 ? (size_t)13 << 20 : (size_t)48 << 20;   // 2^29 simplex slots per store
+        // chunk table
+        std::vector<size_t> cut{0};
+        for (size_t s = 0; s < n_sets;) {
+            size_t e = s;
+            while (e < n_sets && e - s < chunk_sets && (e == s || (size_t)(set_offsets[e + 1] - set_offsets[s]) <= chunk_points)) e++;
+            cut.push_back(e);
+            s = e;
+        }
+        const size_t nchunks = cut.size() - 1;
+        size_t maxPts = 0;
+        for (size_t c = 0; c < nchunks; c++) maxPts = std::max(maxPts, (size_t)(set_offsets[cut[c + 1]] - set_offsets[cut[c]]));
+        // host input: two device buffers, chunk c+1 is copied by a helper thread while chunk c is triangulated
+        std::unique_ptr<DevBuf> buf[2];
+        vor::be::Stream copyStream{};
+        bool haveCopyStream = false;
+#if VOR_GPU
+        if (!points_on_device) {
+            buf[0].reset(new DevBuf(sizeof(double) * maxPts * dim));
+            if (nchunks > 1) buf[1].reset(new DevBuf(sizeof(double) * maxPts * dim));
+            VOR_CUDA(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+            haveCopyStream = true;
+        }
+#else
+        if (!points_on_device) { buf[0].reset(new DevBuf(sizeof(double) * maxPts * dim)); if (nchunks > 1) buf[1].reset(new DevBuf(sizeof(double) * maxPts * dim)); }
+#endif
+        auto chunk_src = [&](size_t c) { return points + (size_t)set_offsets[cut[c]] * dim; };
+        auto chunk_n = [&](size_t c) { return (size_t)(set_offsets[cut[c + 1]] - set_offsets[cut[c]]); };
+        std::string copyErr;
+        auto copy_chunk = [&](size_t c) {
+            try {
+                vor::be::set_device(device);
+                vor::be::h2d_big(buf[c & 1]->p, chunk_src(c), sizeof(double) * chunk_n(c) * dim, copyStream);
+                vor::be::sync(copyStream);
+            } catch (const std::exception &e) { copyErr = e.what(); }
+        };
+        vor_status result = VOR_OK;
+        bool anyDup = false;
+        std::thread copier;
+        if (!points_on_device) copy_chunk(0);
+        for (size_t c = 0; c < nchunks && result == VOR_OK; c++) {
+            if (copier.joinable()) copier.join();
+            if (!copyErr.empty()) { g_err = "host to device copy: " + copyErr; result = VOR_ERR_CUDA; break; }
+            if (!points_on_device && c + 1 < nchunks) copier = std::thread(copy_chunk, c + 1);
+            const double *d_pts = points_on_device ? chunk_src(c) : (const double *)buf[c & 1]->p;
+            const size_t ns = cut[c + 1] - cut[c];
+            std::vector<int64_t> off(ns + 1);
+            for (size_t s = 0; s <= ns; s++) off[s] = set_offsets[cut[c] + s] - set_offsets[cut[c]];
+            vor_tree *t = nullptr;
+            vor_status r = vor_tree_create_batch_device(dim, d_pts, off.data(), ns, device, nullptr, &t);
+            if (r == VOR_OK) r = vor_tree_insert_batch_device(t, d_pts, off.data());
+            if (r == VOR_ERR_DUPLICATE_POINT) { anyDup = true; r = VOR_OK; }
+            if (r == VOR_OK) {
+                r = guarded([&]() -> vor_status {
+                    const std::vector<int> off32 = offsets32(off.data(), ns);
+                    std::vector<unsigned long long> cnt(ns), sum(ns);
+                    t->visit([&](auto &e) { e.per_set_edge_stats(off32.data(), cnt.data(), sum.data()); return 0; });
+                    for (size_t s = 0; s < ns; s++) {
+                        if (n_edges) n_edges[cut[c] + s] = cnt[s];
+                        if (checksums) checksums[cut[c] + s] = sum[s];
+                    }
+                    if (cb) {
+                        uint32_t *h = nullptr;
+                        long long m = 0;
+                        t->visit([&](auto &e) { h = e.edges_to_host_block(&m); return 0; });
+                        cb(user, cut[c], ns, (int64_t)set_offsets[cut[c]], h, (size_t)m);
+                        vor::be::g_hostpool.free(h);
+                    }
+                    return VOR_OK;
+                });
+            }
+            vor_tree_destroy(t);
+            if (r != VOR_OK) { g_err = "chunk " + std::to_string(c) + " (sets " + std::to_string(cut[c]) + ".." + std::to_string(cut[c + 1]) + "): " + g_err; result = r; }
+        }
+        if (copier.joinable()) copier.join();
+#if VOR_GPU
+        if (haveCopyStream) cudaStreamDestroy(copyStream);
+#endif
+        (void)haveCopyStream;
+        if (result == VOR_OK && anyDup) { g_err = "duplicate point(s) dropped"; return VOR_ERR_DUPLICATE_POINT; }
+        return result;
+    });
 }
 
 vor_status vor_tree_create(int dim, const double *points, size_t n, int device, vor_tree **out) {
@@ -256,6 +359,7 @@ vor_status vor_tree_edges(vor_tree *t, uint32_t *edges, size_t cap, size_t *n_ed
         return t->visit([&](auto &e) -> vor_status {
             const long long m = e.edges();
             if (n_edges) *n_edges = (size_t)m;
+            if (edges && (long long)cap < m) { g_err = "edge buffer too small: " + std::to_string(cap) + " < " + std::to_string(m); return VOR_ERR_ARG; }
             if (edges) e.copy_edges(edges, (long long)cap);
             return VOR_OK;
         });
@@ -385,10 +489,12 @@ vor_status vor_find_placement(const int64_t *offsets, const int32_t *ids, size_t
         for (size_t i = 0; i < n; i++)
             if (offsets[i + 1] <= offsets[i]) { g_err = "empty footprint (the reference panics: scheduler.rs:52)"; return VOR_ERR_NO_CONFLICT; }
         vor::be::Stream s = 0;
-        long long *d_off = (long long *)vor::be::dmalloc(sizeof(long long) * (n + 1));
-        int *d_ids = (int *)vor::be::dmalloc(sizeof(int) * (size_t)std::max(total, 1LL));
-        int *d_last = (int *)vor::be::dmalloc(sizeof(int) * (size_t)(maxid + 2));
-        unsigned long long *d_round = (unsigned long long *)vor::be::dmalloc(sizeof(unsigned long long) * n);
+        DevBuf b_off(sizeof(long long) * (n + 1)), b_ids(sizeof(int) * (size_t)std::max(total, 1LL)), b_last(sizeof(int) * (size_t)(maxid + 2)),
+            b_round(sizeof(unsigned long long) * n);   // RAII: nothing leaks when a copy or the launch throws
+        long long *d_off = (long long *)b_off.p;
+        int *d_ids = (int *)b_ids.p;
+        int *d_last = (int *)b_last.p;
+        unsigned long long *d_round = (unsigned long long *)b_round.p;
         static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
         vor::be::h2d(d_off, offsets, sizeof(long long) * (n + 1), s);
         vor::be::h2d(d_ids, ids, sizeof(int) * (size_t)total, s);
@@ -397,7 +503,6 @@ vor_status vor_find_placement(const int64_t *offsets, const int32_t *ids, size_t
         VOR_LAUNCH(vor::PlacementArgs, vor::placement_body, 1, pa, s);
         vor::be::d2h(placement, d_round, sizeof(unsigned long long) * n, s);
         vor::be::sync(s);
-        vor::be::dfree(d_off); vor::be::dfree(d_ids); vor::be::dfree(d_last); vor::be::dfree(d_round);
         return VOR_OK;
     });
 }
@@ -413,6 +518,14 @@ vor_status vor_tree_check_delaunay(vor_tree *t, int *ok, int32_t *fail_counts) {
             if (fail_counts) for (int i = 0; i < 6; i++) fail_counts[i] = f[i];
             return VOR_OK;
         });
+    });
+}
+
+vor_status vor_debug_corrupt(vor_tree *t, int kind) {
+    return guarded([&]() -> vor_status {
+        if (!t) { g_err = "null tree"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        return t->visit([&](auto &e) -> vor_status { e.debug_corrupt(kind); return VOR_OK; });
     });
 }
 

@@ -432,10 +432,17 @@ template <int D> class Engine {
         std::vector<int> off(nsets + 1);
         if (h_setOff) off.assign(h_setOff, h_setOff + nsets + 1);
         else { off[0] = 0; off[1] = n; }
+        const double tf = opt.tet_factor > 0 ? opt.tet_factor : (D == 3 ? 31.0 : 7.5);
+        // Simplex slots are never recycled and a neighbour code packs (slot << 2 | facet) into an int: a tree holds at
+        // most 2^29 - 1 slots, dead ones included (~27 slots are created per 3D point, ~6 per 2D point, over ALL sets and
+        // ALL inserts of the tree).  Refuse BEFORE any state is advanced; bigger batches go through
+        // vor_delaunay_batch_stream, which cuts them into stores of this size.
+        if ((long long)hcnt->ntets + (long long)((tf - (D == 3 ? 3.5 : 1.2)) * (double)n) > (1LL << 29) - 1)
+            fail(ERR_CAPACITY, "tree would exceed 2^29 simplex slots (about 19M 3D / 85M 2D points per tree, all sets and inserts together): "
+                               "use vor_delaunay_batch_stream for larger batches");
         ensure_vertices(nv + n);
         ensure_inputs(ninput + n);
-        const double tf = opt.tet_factor > 0 ? opt.tet_factor : (D == 3 ? 31.0 : 7.5);
-        ensure_simplices((long long)hcnt->ntets + (long long)(tf * (double)(n + 64)));
+        ensure_simplices(std::min((long long)hcnt->ntets + (long long)(tf * (double)(n + 64)), (1LL << 29) - 1));
 
         // ---- keys, sort, gather
         std::vector<int> s0(nsets);
@@ -904,6 +911,22 @@ template <int D> class Engine {
         return h;
     }
 
+    // per-set (edge count, checksum64 of the set-local edge list) of a batch tree; h_setOff = nsets + 1 input offsets
+    void per_set_edge_stats(const int *h_setOff, unsigned long long *h_cnt, unsigned long long *h_sum) {
+        const long long m = edges();
+        DevTmp<int> doff((size_t)nsets + 1);
+        DevTmp<unsigned long long> dc((size_t)nsets), ds((size_t)nsets);
+        be::h2d(doff.p, h_setOff, sizeof(int) * (size_t)(nsets + 1), stream);
+        be::dmemset(dc.p, 0, sizeof(unsigned long long) * (size_t)nsets, stream);
+        be::dmemset(ds.p, 0, sizeof(unsigned long long) * (size_t)nsets, stream);
+        const int run = 128;
+        SetEdgeArgs a{d_edges, m, doff.p, nsets, dc.p, ds.p, run};
+        VOR_LAUNCH(SetEdgeArgs, set_edge_stats_body, (int)((m + run - 1) / run), a, stream);
+        be::d2h(h_cnt, dc.p, sizeof(unsigned long long) * (size_t)nsets, stream);
+        be::d2h(h_sum, ds.p, sizeof(unsigned long long) * (size_t)nsets, stream);
+        be::sync(stream);
+    }
+
     // fail[0..4] as in ValidateArgs; returns number of live simplices
     unsigned long long validate(int *fail_out) {
         int *d_fail = (int *)be::dmalloc(sizeof(int) * 8);
@@ -920,6 +943,73 @@ template <int D> class Engine {
         be::dfree(d_live);
         pull_counters();
         return live;
+    }
+
+    // TEST HOOK (vor_debug_corrupt): damage the finished mesh in one of six ways so that check_delaunay has something to
+    // reject -- kind k makes fail counter k fire: 0 orientation, 1 dead neighbour, 2 asymmetric adjacency, 3 facet
+    // mismatch, 4 not Delaunay (a vertex moved into a neighbour's circumsphere), 5 sphere filter certifying nonsense.
+    void debug_corrupt(int kind) {
+        const int nt = hcnt->ntets;
+        if (nt > (1 << 24)) fail(ERR_ARG, "debug_corrupt is a test hook for small meshes");
+        std::vector<int4> rec((size_t)REC4 * nt);
+        std::vector<int> own;
+        be::d2h(rec.data(), mesh.tet, sizeof(int4) * rec.size(), stream);
+        if (!VOR_INTERLEAVE) { own.resize((size_t)OWS * nt); be::d2h(own.data(), mesh.owner, sizeof(int) * own.size(), stream); }
+        be::sync(stream);
+        auto killw = [&](int t) { return VOR_INTERLEAVE ? reinterpret_cast<const int *>(rec.data())[(size_t)OWS * t] : own[(size_t)OWS * t]; };
+        auto tv = [&](int t) -> int4 & { return rec[(size_t)REC4 * t + TVO4]; };
+        auto tn = [&](int t) -> int4 & { return rec[(size_t)REC4 * t + TVO4 + 1]; };
+        auto real = [&](int t) {
+            if (killw(t) < 0) return false;
+            for (int k = 0; k < M; k++) if (get4(tv(t), k) < nsuper || get4(tn(t), k) < 0) return false;
+            return true;
+        };
+        int t = -1;
+        for (int c = nt / 2; c < nt && t < 0; c++) {
+            if (!real(c)) continue;
+            bool ok = true;
+            for (int k = 0; k < M; k++) ok = ok && real(get4(tn(c), k) >> 2);
+            if (ok) t = c;
+        }
+        if (t < 0) fail(ERR_ARG, "debug_corrupt: no interior simplex found");
+        int4 v = tv(t), nb = tn(t);
+        auto put_rec = [&]() {
+            be::h2d(mesh.tet + REC4 * (size_t)t + TVO4, &v, sizeof(int4), stream);
+            be::h2d(mesh.tet + REC4 * (size_t)t + TVO4 + 1, &nb, sizeof(int4), stream);
+        };
+        if (kind == 0) { std::swap(v.x, v.y); put_rec(); }
+        else if (kind == 1) {
+            int d = -1;
+            for (int c = 0; c < nt && d < 0; c++) if (killw(c) < 0) d = c;
+            if (d < 0) fail(ERR_ARG, "debug_corrupt: no dead simplex");
+            nb.x = d * 4; put_rec();
+        } else if (kind == 2) { nb.x = (nb.x & ~3) | (((nb.x & 3) + 1) % M); put_rec(); }
+        else if (kind == 3) {
+            int other = -1;
+            for (int c = nt / 4; c < nt && other < 0; c++) {
+                if (!real(c) || c == t) continue;
+                const int cand = tv(c).x;
+                bool used = false;
+                for (int k = 0; k < M; k++) used = used || get4(v, k) == cand || get4(tv(nb.x >> 2), k) == cand;
+                if (!used) other = cand;
+            }
+            if (other < 0) fail(ERR_ARG, "debug_corrupt: no foreign vertex");
+            v.y = other; put_rec();
+        } else if (kind == 4) {
+            const int n0 = nb.x >> 2, j0 = nb.x & 3;
+            const int w = get4(tv(n0), j0);
+            Pt c{};
+            std::vector<Pt> pv(M);
+            for (int k = 0; k < M; k++) be::d2h(&pv[k], mesh.pts + get4(v, k), sizeof(Pt), stream);
+            be::sync(stream);
+            for (int k = 0; k < M; k++) { c.x += pv[k].x / M; c.y += pv[k].y / M; if constexpr (D == 3) c.z += pv[k].z / M; }
+            be::h2d(mesh.pts + w, &c, sizeof(Pt), stream);
+        } else if (kind == 5) {
+            const float big = 1e30f;
+            be::h2d(mesh.owner + OWS * (size_t)t + 5, &big, sizeof(float), stream);
+        } else fail(ERR_ARG, "debug_corrupt: kind must be 0..5");
+        be::sync(stream);
+        invalidate_outputs();
     }
 
     // live simplices in slot order: liveId[c] = slot, compactOf[slot] = c (-1 when dead); returns the count
@@ -1049,8 +1139,9 @@ template <int D> class Engine {
         if (h_verts || h_nbrs || h_center || h_radius) {
             int *d_verts = (int *)be::dmalloc(sizeof(int) * (size_t)n * M);
             int *d_nbrs = (int *)be::dmalloc(sizeof(int) * (size_t)n * M);
-            double *d_c = h_center ? (double *)be::dmalloc(sizeof(double) * (size_t)n * D) : nullptr;
-            double *d_r = h_center ? (double *)be::dmalloc(sizeof(double) * (size_t)n) : nullptr;
+            const bool spheres = h_center || h_radius;   // either may be asked for alone
+            double *d_c = spheres ? (double *)be::dmalloc(sizeof(double) * (size_t)n * D) : nullptr;
+            double *d_r = spheres ? (double *)be::dmalloc(sizeof(double) * (size_t)n) : nullptr;
             ExportFillArgs<D> fa{mesh, liveId, compactOf, inputIdx, d_verts, d_nbrs, d_c, d_r, idOffset};
             VOR_LAUNCH(ExportFillArgs<D>, export_fill_body<D>, n, fa, stream);
             if (h_verts) be::d2h(h_verts, d_verts, sizeof(int) * (size_t)n * M, stream);

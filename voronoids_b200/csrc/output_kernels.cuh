@@ -116,6 +116,34 @@ VOR_HD void edge_sum_body(const EdgeSumArgs &A, int i) {
     atomic_add_ull(A.sum, mix64(k));
 }
 
+// per-set edge count and order-independent checksum of a batch tree's canonical edge list (sets are independent units,
+// BASELINE.json configs[4]): the list is sorted by lo, so every set owns one contiguous range; a thread walks a run of
+// edges, folds them locally (indices made local to the set) and flushes once per set it meets.
+struct SetEdgeArgs { const uint32_t *edges; long long m; const int *setOff; int nsets; unsigned long long *cnt; unsigned long long *sum; int run; };
+VOR_HD void set_edge_stats_body(const SetEdgeArgs &A, int b) {
+    const long long lo = (long long)b * A.run, hi = lo + A.run < A.m ? lo + A.run : A.m;
+    if (lo >= hi) return;
+    int s = 0;
+    {   // set of the first edge: last set whose offset is <= its lo endpoint
+        const int first = (int)A.edges[2 * (size_t)lo];
+        int a = 0, z = A.nsets;
+        while (z - a > 1) { const int mid = (a + z) >> 1; if (A.setOff[mid] <= first) a = mid; else z = mid; }
+        s = a;
+    }
+    unsigned long long c = 0, acc = 0;
+    for (long long i = lo; i < hi; i++) {
+        const int el = (int)A.edges[2 * (size_t)i], eh = (int)A.edges[2 * (size_t)i + 1];
+        while (el >= A.setOff[s + 1]) {
+            if (c) { atomic_add_ull(&A.cnt[s], c); atomic_add_ull(&A.sum[s], acc); }
+            c = 0; acc = 0; s++;
+        }
+        const uint64_t k = ((uint64_t)(uint32_t)(el - A.setOff[s]) << 32) | (uint32_t)(eh - A.setOff[s]);
+        acc += mix64(k);
+        c++;
+    }
+    if (c) { atomic_add_ull(&A.cnt[s], c); atomic_add_ull(&A.sum[s], acc); }
+}
+
 // ---- validation
 template <int D> struct ValidateArgs {
     Mesh<D> m;

@@ -70,3 +70,25 @@ def make(kind, n, dim=3, seed=0):
     if kind == "lattice":
         return jittered_lattice(n, dim, seed)
     raise ValueError(kind)
+
+
+def uniform_sets_torch(n_sets, n, dim=3, first_seed=1000, device="cuda"):
+    """`n_sets` uniform sets of `n` points generated ON THE DEVICE (BASELINE.json configs[4]: set s uses seed first_seed + s),
+    bit-identical to uniform(n, dim, first_seed + s): the same splitmix64 in torch int64 arithmetic (two's complement
+    products wrap like uint64; logical right shifts are emulated by masking).  float64 tensor [n_sets * n, dim]."""
+    import torch
+
+    def lsr(x, k):   # logical shift right of an int64 holding a uint64 bit pattern
+        return (x >> k) & ((1 << (64 - k)) - 1)
+
+    def i64(c):      # uint64 constant -> the int64 with the same bits
+        return c - (1 << 64) if c >= (1 << 63) else c
+
+    gamma = i64(0x9E3779B97F4A7C15)
+    seeds = torch.arange(first_seed, first_seed + n_sets, dtype=torch.int64, device=device).view(n_sets, 1)
+    ctr = torch.arange(n * dim, dtype=torch.int64, device=device).view(1, n * dim)
+    z = seeds * gamma + ctr + gamma
+    z = (z ^ lsr(z, 30)) * i64(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * i64(0x94D049BB133111EB)
+    z = z ^ lsr(z, 31)
+    return (lsr(z, 11).to(torch.float64) * (2.0 ** -53)).view(n_sets * n, dim)
