@@ -148,6 +148,22 @@ vor_status vor_find_placement(const int64_t *offsets, const int32_t *ids, size_t
  * stored circumsphere filter (the cached centre/radius of delaunay_tree.rs:11-16, here a certified filter) contradicting
  * the exact predicate on a simplex's own vertices or on the opposite vertices of its neighbours. */
 vor_status vor_tree_check_delaunay(vor_tree *t, int *ok, int32_t *fail_counts);
+/* ---- slab mode: ONE triangulation spread over several GPUs (driver: voronoids_b200/slab.py) ----------
+ * Every slab must build the same super simplex as a single-GPU run of the whole set (delaunay_tree.rs:392-406 from
+ * geometry.rs:99-142): the slabs combine their local bounds (min / max), then their counts of points that fail the
+ * strict in_sphere test of the global half-diagonal sphere (sum), and bootstrap from both.  After inserting its own
+ * points, the shared coarse sample and a halo, a slab asks whether every simplex around a point it OWNS is a simplex
+ * of the global triangulation: the part of its circumsphere inside the data box must stay inside the range of `axis`
+ * in which the tree holds every global point -- that range, plus a shell of depth `shell` under the lateral faces of the
+ * data box (the empty cap of a hull simplex's nearly flat sphere is thin but wide).  n_uncertified == 0 is the
+ * certificate; otherwise need[0..1] is the range along the axis the halo would have to cover. */
+vor_status vor_slab_local_bounds(int dim, const double *d_points, size_t n, int device, double *lo, double *hi);
+vor_status vor_slab_count_outside(int dim, const double *d_points, size_t n, int device, const double *lo, const double *hi, uint64_t *count);
+vor_status vor_tree_create_bounds(int dim, const double *lo, const double *hi, uint64_t outside, size_t capacity_hint, int device, void *cuda_stream,
+                                  vor_tree **out);
+vor_status vor_tree_certify_slab(vor_tree *t, const uint8_t *owned, size_t n_owned, int axis, double range_lo, double range_hi, double shell,
+                                 uint64_t *n_uncertified, double *need);
+
 /* TEST HOOK for the checker above (the reference's check_delaunay is never fed a broken mesh either,
  * tests/test_delaunay_tree.rs:37): damages one interior simplex of a finished tree so that fail counter `kind`
  * (0..5, order of fail_counts) must fire.  The tree is unusable for further inserts afterwards. */

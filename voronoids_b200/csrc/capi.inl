@@ -521,6 +521,56 @@ vor_status vor_tree_check_delaunay(vor_tree *t, int *ok, int32_t *fail_counts) {
     });
 }
 
+// ---- slab mode: one triangulation over several GPUs, see voronoids_b200/slab.py for the driver
+vor_status vor_slab_local_bounds(int dim, const double *d_points, size_t n, int device, double *lo, double *hi) {
+    return guarded([&]() -> vor_status {
+        if ((dim != 2 && dim != 3) || !lo || !hi || n > 0x7fffffff) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(device);
+        if (dim == 2) vor::Engine<2>::local_bounds(d_points, (int)n, lo, hi, vor::be::Stream{});
+        else vor::Engine<3>::local_bounds(d_points, (int)n, lo, hi, vor::be::Stream{});
+        return VOR_OK;
+    });
+}
+vor_status vor_slab_count_outside(int dim, const double *d_points, size_t n, int device, const double *lo, const double *hi, uint64_t *count) {
+    return guarded([&]() -> vor_status {
+        if ((dim != 2 && dim != 3) || !lo || !hi || !count || n > 0x7fffffff) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(device);
+        *count = (uint64_t)(dim == 2 ? vor::Engine<2>::count_outside(d_points, (int)n, lo, hi, vor::be::Stream{})
+                                     : vor::Engine<3>::count_outside(d_points, (int)n, lo, hi, vor::be::Stream{}));
+        return VOR_OK;
+    });
+}
+vor_status vor_tree_create_bounds(int dim, const double *lo, const double *hi, uint64_t outside, size_t capacity_hint, int device, void *cuda_stream,
+                                  vor_tree **out) {
+    return guarded([&]() -> vor_status {
+        if (!out || (dim != 2 && dim != 3) || !lo || !hi || capacity_hint > 0x7fffffff) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(device);
+        std::unique_ptr<vor_tree> t(new vor_tree);
+        t->dim = dim;
+        t->device = device;
+        t->n_sets = 1;
+        t->stream = (vor::be::Stream)(uintptr_t)cuda_stream;
+        const int off[2] = {0, 0};
+        const int hint = (int)capacity_hint;
+        if (dim == 2) { t->e2.reset(new vor::Engine<2>(t->stream, current_options())); t->e2->create(nullptr, hint, off, 1, lo, hi, outside ? 1 : 0); }
+        else { t->e3.reset(new vor::Engine<3>(t->stream, current_options())); t->e3->create(nullptr, hint, off, 1, lo, hi, outside ? 1 : 0); }
+        *out = t.release();
+        return VOR_OK;
+    });
+}
+vor_status vor_tree_certify_slab(vor_tree *t, const uint8_t *owned, size_t n_owned, int axis, double range_lo, double range_hi, double shell,
+                                 uint64_t *n_uncertified, double *need) {
+    return guarded([&]() -> vor_status {
+        if (!t || !owned || !n_uncertified || !need || axis < 0 || axis >= t->dim) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        return t->visit([&](auto &e) -> vor_status {
+            if ((size_t)e.ninput != n_owned) { g_err = "owned flags must cover every inserted point"; return VOR_ERR_ARG; }
+            *n_uncertified = (uint64_t)e.certify_slab(owned, axis, range_lo, range_hi, shell, need);
+            return VOR_OK;
+        });
+    });
+}
+
 vor_status vor_debug_corrupt(vor_tree *t, int kind) {
     return guarded([&]() -> vor_status {
         if (!t) { g_err = "null tree"; return VOR_ERR_ARG; }

@@ -259,8 +259,14 @@ template <int D> class Engine {
     // ------------------------------------------------------------------ bootstrap  (DelaunayTree::new)
     // d_in: n x D points on the device (all the points the tree will ever see, as in the reference);
     // h_setOff: nsets+1 offsets (nullptr => one set)
-    void create(const double *d_in, int n, const int *h_setOff, int nsets_) {
+    // forcedLo/forcedHi/forcedOutside (single set): the bounding box and the "some point fails the strict in_sphere test of
+    // the half-diagonal sphere" count come from the caller instead of from d_in -- a slab of a point set that is spread
+    // over several GPUs bootstraps from the GLOBAL bounds so that every slab builds the same super simplex (d_in may be
+    // null, n is a capacity hint).
+    void create(const double *d_in, int n, const int *h_setOff, int nsets_, const double *forcedLo = nullptr, const double *forcedHi = nullptr,
+                int forcedOutside = 0) {
         nsets = nsets_ < 1 ? 1 : nsets_;
+        if (forcedLo && nsets != 1) fail(ERR_ARG, "forced bounds address single-set trees");
         nsuper = nsets * M;
         std::vector<int> off(nsets + 1);
         if (h_setOff) off.assign(h_setOff, h_setOff + nsets + 1);
@@ -273,14 +279,18 @@ template <int D> class Engine {
         ChunkDesc *d_chunks = (ChunkDesc *)be::dmalloc(sizeof(ChunkDesc) * (size_t)std::max(nch, 1));
         double *d_partial = (double *)be::dmalloc(sizeof(double) * 2 * D * (size_t)std::max(nch, 1));
         be::h2d(d_chunks, chunks.data(), sizeof(ChunkDesc) * (size_t)nch, stream);
-        BboxArgs<D> ba{d_in, d_chunks, d_partial};
-        VOR_LAUNCH(BboxArgs<D>, bbox_chunk_body<D>, nch, ba, stream);
         std::vector<double> partial((size_t)nch * 2 * D);
-        be::d2h(partial.data(), d_partial, sizeof(double) * partial.size(), stream);
-        be::sync(stream);
+        if (!forcedLo) {
+            BboxArgs<D> ba{d_in, d_chunks, d_partial};
+            VOR_LAUNCH(BboxArgs<D>, bbox_chunk_body<D>, nch, ba, stream);
+            be::d2h(partial.data(), d_partial, sizeof(double) * partial.size(), stream);
+            be::sync(stream);
+        }
         boxLo.assign((size_t)nsets * D, INFINITY);
         boxHi.assign((size_t)nsets * D, -INFINITY);
-        for (int c = 0; c < nch; c++)
+        if (forcedLo)
+            for (int k = 0; k < D; k++) { boxLo[k] = forcedLo[k]; boxHi[k] = forcedHi[k]; }
+        for (int c = 0; c < nch && !forcedLo; c++)
             for (int k = 0; k < D; k++) {
                 const int s = chunks[c].set;
                 boxLo[(size_t)s * D + k] = std::fmin(boxLo[(size_t)s * D + k], partial[(size_t)c * 2 * D + k]);
@@ -305,10 +315,12 @@ template <int D> class Engine {
         be::h2d(d_center, center.data(), sizeof(double) * (size_t)nsets * D, stream);
         be::h2d(d_radius, radius.data(), sizeof(double) * (size_t)nsets, stream);
         be::dmemset(d_outside, 0, sizeof(int) * (size_t)nsets, stream);
-        OutsideArgs<D> oa{d_in, d_chunks, d_center, d_radius, d_outside};
-        VOR_LAUNCH(OutsideArgs<D>, count_outside_body<D>, nch, oa, stream);
         std::vector<int> outside(nsets);
-        be::d2h(outside.data(), d_outside, sizeof(int) * (size_t)nsets, stream);
+        if (!forcedLo) {
+            OutsideArgs<D> oa{d_in, d_chunks, d_center, d_radius, d_outside};
+            VOR_LAUNCH(OutsideArgs<D>, count_outside_body<D>, nch, oa, stream);
+            be::d2h(outside.data(), d_outside, sizeof(int) * (size_t)nsets, stream);
+        } else outside[0] = forcedOutside;
         be::sync(stream);
         be::dfree(d_chunks); be::dfree(d_partial); be::dfree(d_center); be::dfree(d_radius); be::dfree(d_outside);
         // super simplex (delaunay_tree.rs:392-406 / :547-558); host libm cos/sin as rustc's f64::cos/sin
@@ -909,6 +921,76 @@ template <int D> class Engine {
         be::sync(stream);
         be::dfree(d_sum);
         return h;
+    }
+
+    // slab mode: local bounds of n device points, and how many of them fail the strict in_sphere test of
+    // the bounding sphere of the box [lo, hi] (geometry.rs:99-142) -- the two reductions a group of slabs has to combine
+    // (min / max / sum) before every slab can build the SAME super simplex.  Static: no tree needed.
+    static void local_bounds(const double *d_in, int n, double *lo, double *hi, be::Stream stream) {
+        std::vector<ChunkDesc> chunks;
+        for (int a = 0; a < n; a += BBOX_CHUNK) chunks.push_back(ChunkDesc{0, a, std::min(a + BBOX_CHUNK, n)});
+        const int nch = (int)chunks.size();
+        for (int k = 0; k < D; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+        if (!nch) return;
+        DevTmp<ChunkDesc> dch((size_t)nch);
+        DevTmp<double> dp((size_t)nch * 2 * D);
+        be::h2d(dch.p, chunks.data(), sizeof(ChunkDesc) * (size_t)nch, stream);
+        BboxArgs<D> ba{d_in, dch.p, dp.p};
+        VOR_LAUNCH(BboxArgs<D>, bbox_chunk_body<D>, nch, ba, stream);
+        std::vector<double> partial((size_t)nch * 2 * D);
+        be::d2h(partial.data(), dp.p, sizeof(double) * partial.size(), stream);
+        be::sync(stream);
+        for (int c = 0; c < nch; c++)
+            for (int k = 0; k < D; k++) {
+                lo[k] = std::fmin(lo[k], partial[(size_t)c * 2 * D + k]);
+                hi[k] = std::fmax(hi[k], partial[(size_t)c * 2 * D + D + k]);
+            }
+    }
+    static int count_outside(const double *d_in, int n, const double *lo, const double *hi, be::Stream stream) {
+        double c[D], ud = 0.0, ld = 0.0;
+        for (int k = 0; k < D; k++) c[k] = (hi[k] + lo[k]) / 2.0;
+        for (int k = 0; k < D; k++) { const double d = hi[k] - c[k]; ud += d * d; }
+        for (int k = 0; k < D; k++) { const double d = lo[k] - c[k]; ld += d * d; }
+        ud = std::sqrt(ud); ld = std::sqrt(ld);
+        const double r = ud > ld ? ud : ld;
+        std::vector<ChunkDesc> chunks;
+        for (int a = 0; a < n; a += BBOX_CHUNK) chunks.push_back(ChunkDesc{0, a, std::min(a + BBOX_CHUNK, n)});
+        const int nch = (int)chunks.size();
+        if (!nch) return 0;
+        DevTmp<ChunkDesc> dch((size_t)nch);
+        DevTmp<double> dc((size_t)D), dr(1);
+        DevTmp<int> dout(1);
+        be::h2d(dch.p, chunks.data(), sizeof(ChunkDesc) * (size_t)nch, stream);
+        be::h2d(dc.p, c, sizeof(double) * D, stream);
+        be::h2d(dr.p, &r, sizeof(double), stream);
+        be::dmemset(dout.p, 0, sizeof(int), stream);
+        OutsideArgs<D> oa{d_in, dch.p, dc.p, dr.p, dout.p};
+        VOR_LAUNCH(OutsideArgs<D>, count_outside_body<D>, nch, oa, stream);
+        int out = 0;
+        be::d2h(&out, dout.p, sizeof(int), stream);
+        be::sync(stream);
+        return out;
+    }
+    // certification pass of a slab: every live simplex with a vertex flagged in `h_owned` (per input index) must have the
+    // part of its circumsphere that lies inside the data box within [range_lo, range_hi] along `axis` -- the range in
+    // which this tree holds EVERY point of the global set.  Returns the number of simplices that do not, and the extent
+    // they need (need[0] <= range_lo, need[1] >= range_hi).
+    long long certify_slab(const unsigned char *h_owned, int axis, double range_lo, double range_hi, double shell, double *need) {
+        DevTmp<unsigned char> down((size_t)std::max(ninput, 1));
+        DevTmp<unsigned long long> dcount(1);
+        DevTmp<double> dneed(2);
+        be::h2d(down.p, h_owned, (size_t)ninput, stream);
+        be::dmemset(dcount.p, 0, sizeof(unsigned long long), stream);
+        const double init[2] = {range_lo, range_hi};
+        be::h2d(dneed.p, init, sizeof(init), stream);
+        CertifyArgs<D> ca{mesh, inputIdx, down.p, dcount.p, dneed.p, axis, range_lo, range_hi, shell};
+        for (int k = 0; k < 3; k++) { ca.boxLo[k] = k < D ? boxLo[k] : 0.0; ca.boxHi[k] = k < D ? boxHi[k] : 0.0; }
+        VOR_LAUNCH(CertifyArgs<D>, certify_body<D>, hcnt->ntets, ca, stream);
+        unsigned long long cnt = 0;
+        be::d2h(&cnt, dcount.p, sizeof(cnt), stream);
+        be::d2h(need, dneed.p, sizeof(double) * 2, stream);
+        be::sync(stream);
+        return (long long)cnt;
     }
 
     // per-set (edge count, checksum64 of the set-local edge list) of a batch tree; h_setOff = nsets + 1 input offsets

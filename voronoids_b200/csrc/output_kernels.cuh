@@ -144,6 +144,83 @@ VOR_HD void set_edge_stats_body(const SetEdgeArgs &A, int b) {
     if (c) { atomic_add_ull(&A.cnt[s], c); atomic_add_ull(&A.sum[s], acc); }
 }
 
+// ---- slab certification.  A simplex of the triangulation of (own points + halo + coarse sample) is a
+// simplex of the GLOBAL triangulation iff no point of the global set lies strictly inside its circumsphere.  This tree
+// holds every global point whose `axis` coordinate is in [lo, hi]; all points lie in the data box.  So it suffices that
+// (open ball) n (data box) stays inside [lo, hi] along `axis`.  The ball is taken from the certified sphere block
+// (sphere.cuh): the true open ball is contained in { q : |q - c|^2 <= rout2 } (c relative to the origin), hence the
+// test errs only on the side of "not certified".  Only simplices with a vertex this slab OWNS need the certificate.
+VOR_HD double atomic_min_d(double *p, double v) {
+#ifdef __CUDA_ARCH__
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(p), old = *a, assumed;
+    do { assumed = old; if (__longlong_as_double((long long)assumed) <= v) break; old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v)); } while (old != assumed);
+    return __longlong_as_double((long long)old);
+#else
+    const double o = *p; if (v < o) *p = v; return o;
+#endif
+}
+VOR_HD double atomic_max_d(double *p, double v) {
+#ifdef __CUDA_ARCH__
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(p), old = *a, assumed;
+    do { assumed = old; if (__longlong_as_double((long long)assumed) >= v) break; old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v)); } while (old != assumed);
+    return __longlong_as_double((long long)old);
+#else
+    const double o = *p; if (v > o) *p = v; return o;
+#endif
+}
+template <int D> struct CertifyArgs {
+    Mesh<D> m;
+    const int *inputIdx;          // vertex -> input index (-1: super vertex)
+    const unsigned char *owned;   // per input index
+    unsigned long long *count;
+    double *need;                 // [2]: extent along `axis` the uncertified simplices reach
+    int axis;
+    double lo, hi;
+    double shell;                 // the tree also holds every global point within `shell` of a lateral face of the data box
+    double boxLo[3], boxHi[3];
+};
+template <int D> VOR_HD void certify_body(const CertifyArgs<D> &A, int t) {
+    constexpr int M = Dim<D>::M;
+    const Mesh<D> &m = A.m;
+    if (!simplex_live(m, t)) return;
+    const int4 tv = TV(m, t);
+    bool mine = false;
+    for (int k = 0; k < M; k++) {
+        const int v = get4(tv, k);
+        if (v >= m.nsuper && A.owned[A.inputIdx[v]]) mine = true;
+    }
+    if (!mine) return;
+    const OwnBlk b = load_blk(m, t);
+    const double org[3] = {m.sref.ox, m.sref.oy, m.sref.oz};
+    const double c[3] = {(double)b.cx + org[0], (double)b.cy + org[1], (double)b.cz + org[2]};
+    double elo = A.boxLo[A.axis], ehi = A.boxHi[A.axis];       // no filter (rout2 = inf): the whole box
+    const double r2 = (double)b.rout2 * (1.0 + 1e-12);
+    if (r2 < 1e300) {
+        // squared distance of the centre to the part of the box this tree may be missing points from: the box shrunk by the
+        // shell in the OTHER axes (an empty rest: every point of the box is held, nothing to certify)
+        double d2 = 0.0;
+        const double sh = A.shell * (1.0 - 1e-9);
+        for (int k = 0; k < D; k++) {
+            if (k == A.axis) continue;
+            const double l = A.boxLo[k] + sh, h = A.boxHi[k] - sh;
+            if (l >= h) return;
+            const double d = c[k] < l ? l - c[k] : (c[k] > h ? c[k] - h : 0.0);
+            d2 += d * d;
+        }
+        d2 *= (1.0 - 1e-12);
+        if (r2 <= d2) return;                                   // the ball misses the data box: nothing can be inside it
+        const double half = sqrt(r2 - d2) * (1.0 + 1e-12) + 1e-300;
+        const double slack = 4.0 * SPH_EPS * (fabs(c[A.axis]) + half);
+        elo = fmax(elo, c[A.axis] - half - slack);
+        ehi = fmin(ehi, c[A.axis] + half + slack);
+        if (elo > ehi) return;                                  // misses the box along the axis
+    }
+    if (elo >= A.lo && ehi <= A.hi) return;                     // certified
+    atomic_add_ull(A.count, 1ULL);
+    if (elo < A.lo) atomic_min_d(&A.need[0], elo);
+    if (ehi > A.hi) atomic_max_d(&A.need[1], ehi);
+}
+
 // ---- validation
 template <int D> struct ValidateArgs {
     Mesh<D> m;
