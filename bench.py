@@ -47,6 +47,9 @@ WORKLOADS = {
     "b3_8192x100k": (3, "stream", 819_200_000, 1000, "batch of 8,192 independent 3D uniform sets x 100k points (BASELINE.json configs[4]), sharded over the GPUs"),
 }
 STREAM_SETS = int(os.environ.get("VOR_STREAM_SETS", "8192"))
+# ONE triangulation over the GPUs (voronoids_b200/slab.py): fixed 10M-point set, strong scaling
+WORKLOADS["u3_10m_slab"] = (3, "slab", 10_000_000, 0, "3D uniform random 10M points, ONE triangulation in slabs over the GPUs (halo exchange, certified)")
+WORKLOADS["u3_1m_slab"] = (3, "slab", 1_000_000, 0, "3D uniform random 1M points, ONE triangulation in slabs over the GPUs (halo exchange, certified)")
 BATCH_SETS, BATCH_SIZE = 64, 100_000
 
 
@@ -315,6 +318,75 @@ def run_stream(args, name, rank, world, local_rank):
     return 0
 
 
+def run_slab(args, name, rank, world, local_rank):
+    """One triangulation in slabs over the ranks (strong scaling); the timed region is the whole slab pipeline on device-resident
+    points: bounds, coarse sample, halo rounds, certification, this rank's part of the canonical edge list."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from voronoids_b200 import _lib, pointgen, slab
+    lib = _lib.lib()
+    dim, kind, n, seed, desc = WORKLOADS[name]
+    allp = torch.from_numpy(pointgen.uniform(n, dim, seed)).cuda()
+    mine, gidx = slab.partition_by_axis(allp, world, rank, axis=0)
+    del allp
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        res = slab.delaunay_slab(lib, mine, gidx, device=local_rank, axis=0)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), res
+
+    for _ in range(args.warmup):
+        step()
+    launches0 = lib.vor_kernel_launches()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_ms = []
+    for _ in range(args.steps):
+        ms, res = step()
+        t_ms.append(ms)
+    barrier()
+    clocks = sampler.stop()
+    launches = (lib.vor_kernel_launches() - launches0) // max(args.steps, 1)
+    tot = torch.tensor([sum(t_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tot.item()) / args.steps
+    infos = [res.info]
+    if world > 1:
+        infos = [None] * world
+        dist.all_gather_object(infos, res.info)
+    full = slab.gather_edges(res.edges)
+    if rank == 0:
+        cfg = bench_config(desc, n // world, dim, world)
+        cfg.update({"parallelism": f"1 point set in {world} slab(s) along x: shared 1/16 coarse sample, halo + hull shell exchanged peer to peer "
+                                   f"(NCCL send/recv), certification on the cached circumspheres",
+                    "halo_rows_received_per_rank": [i.get("halo_rows_received", 0) for i in infos],
+                    "halo_bytes_received_per_rank": [i.get("halo_rows_received", 0) * (dim + 1) * 8 for i in infos],
+                    "coarse_points": infos[0].get("coarse_points", 0), "tree_points_per_rank": [i.get("tree_points", 0) for i in infos],
+                    "certification_rounds": max(i.get("rounds", 0) for i in infos),
+                    "edges": int(full.shape[0]), "edges_sha256": hashlib.sha256(np.ascontiguousarray(full).tobytes()).hexdigest()})
+        line = {"metric": "delaunay_points_inserted_per_sec", "value": n / (ms_per_step * 1e-3), "unit": "points/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": None, "cpu_baseline": None, "e2e": None,
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -356,6 +428,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if kind == "stream":
         return run_stream(args, name, rank, world, local_rank)
+    if kind == "slab":
+        return run_slab(args, name, rank, world, local_rank)
     import voronoids_b200 as vb
     from voronoids_b200 import _capi, _lib
     lib = _lib.lib()

@@ -164,6 +164,12 @@ vor_status vor_tree_create_bounds(int dim, const double *lo, const double *hi, u
 vor_status vor_tree_certify_slab(vor_tree *t, const uint8_t *owned, size_t n_owned, int axis, double range_lo, double range_hi, double shell,
                                  uint64_t *n_uncertified, double *need);
 
+/* this slab's part of the global canonical edge list (host block of the library's allocator, release with vor_host_free):
+ * edges of the tree whose endpoint with the lower GLOBAL index is owned by the slab, as sorted (lo, hi) global index pairs.
+ * global_index / owned: one entry per inserted point, in insertion order.  The parts of all slabs are disjoint; their
+ * sorted union is the canonical edge list of the whole set. */
+vor_status vor_tree_edges_slab(vor_tree *t, const int64_t *global_index, const uint8_t *owned, size_t n, uint32_t **edges, size_t *n_edges);
+
 /* TEST HOOK for the checker above (the reference's check_delaunay is never fed a broken mesh either,
  * tests/test_delaunay_tree.rs:37): damages one interior simplex of a finished tree so that fail counter `kind`
  * (0..5, order of fail_counts) must fire.  The tree is unusable for further inserts afterwards. */

@@ -39,6 +39,7 @@ SYMBOLS = {
     "vor_find_placement": (C.c_int, [i64p, i32p, C.c_size_t, u64p, C.c_int]),
     "vor_tree_check_delaunay": (C.c_int, [tree_p, C.POINTER(C.c_int), i32p]),
     "vor_debug_corrupt": (C.c_int, [tree_p, C.c_int]),
+    "vor_tree_edges_slab": (C.c_int, [tree_p, i64p, C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "vor_slab_local_bounds": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_int, dp, dp]),
     "vor_slab_count_outside": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_int, dp, dp, u64p]),
     "vor_tree_create_bounds": (C.c_int, [C.c_int, dp, dp, C.c_uint64, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(tree_p)]),

@@ -571,6 +571,21 @@ vor_status vor_tree_certify_slab(vor_tree *t, const uint8_t *owned, size_t n_own
     });
 }
 
+vor_status vor_tree_edges_slab(vor_tree *t, const int64_t *global_index, const uint8_t *owned, size_t n, uint32_t **edges, size_t *n_edges) {
+    return guarded([&]() -> vor_status {
+        if (!t || !global_index || !owned || !edges || !n_edges) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        return t->visit([&](auto &e) -> vor_status {
+            if ((size_t)e.ninput != n) { g_err = "global_index / owned must cover every inserted point"; return VOR_ERR_ARG; }
+            long long m = 0;
+            static_assert(sizeof(long long) == sizeof(int64_t), "index width");
+            *edges = e.slab_edges_to_host_block(reinterpret_cast<const long long *>(global_index), owned, &m);
+            *n_edges = (size_t)m;
+            return VOR_OK;
+        });
+    });
+}
+
 vor_status vor_debug_corrupt(vor_tree *t, int kind) {
     return guarded([&]() -> vor_status {
         if (!t) { g_err = "null tree"; return VOR_ERR_ARG; }

@@ -993,6 +993,37 @@ template <int D> class Engine {
         return (long long)cnt;
     }
 
+    // slab mode: this slab's part of the global canonical edge list in a host block of the caching host allocator
+    // (h_gmap / h_owned: per local input index); the caller owns the block (vor_host_free)
+    uint32_t *slab_edges_to_host_block(const long long *h_gmap, const unsigned char *h_owned, long long *m_out) {
+        const long long m = edges();
+        if (m > 0x7ffffff0LL) fail(ERR_OOM, "too many edges");
+        DevTmp<long long> dg((size_t)std::max(ninput, 1));
+        DevTmp<unsigned char> down((size_t)std::max(ninput, 1));
+        DevTmp<unsigned long long> k0((size_t)m + 2), k1((size_t)m + 2), dcount(1);
+        be::h2d(dg.p, h_gmap, sizeof(long long) * (size_t)ninput, stream);
+        be::h2d(down.p, h_owned, (size_t)ninput, stream);
+        SlabEdgeArgs ka{d_edges, dg.p, down.p, k0.p};
+        VOR_LAUNCH(SlabEdgeArgs, slab_edge_key_body, m, ka, stream);
+        be::dmemset(k0.p + m, 0xff, sizeof(unsigned long long), stream);   // sentinel ~0 behind the last key
+        be::sort_keys(reinterpret_cast<uint64_t *>(k0.p), reinterpret_cast<uint64_t *>(k1.p), (size_t)m + 1, stream);
+        be::dmemset(dcount.p, 0, sizeof(unsigned long long), stream);
+        KeyCountArgs ca{k1.p, dcount.p};
+        VOR_LAUNCH(KeyCountArgs, key_count_body, m, ca, stream);
+        unsigned long long cnt = 0;
+        be::d2h(&cnt, dcount.p, sizeof(cnt), stream);
+        be::sync(stream);
+        DevTmp<uint32_t> dout(2 * (size_t)std::max<unsigned long long>(cnt, 1));
+        KeyUnpackArgs ua{k1.p, dout.p};
+        VOR_LAUNCH(KeyUnpackArgs, key_unpack_body, (long long)cnt, ua, stream);
+        bool pinned = false;
+        uint32_t *h = (uint32_t *)be::g_hostpool.alloc(sizeof(uint32_t) * 2 * (size_t)std::max<unsigned long long>(cnt, 1), &pinned);
+        if (pinned) { be::d2h(h, dout.p, sizeof(uint32_t) * 2 * (size_t)cnt, stream); be::sync(stream); }
+        else be::d2h_big(h, dout.p, sizeof(uint32_t) * 2 * (size_t)cnt, stream);
+        *m_out = (long long)cnt;
+        return h;
+    }
+
     // per-set (edge count, checksum64 of the set-local edge list) of a batch tree; h_setOff = nsets + 1 input offsets
     void per_set_edge_stats(const int *h_setOff, unsigned long long *h_cnt, unsigned long long *h_sum) {
         const long long m = edges();

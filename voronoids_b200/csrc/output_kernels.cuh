@@ -221,6 +221,27 @@ template <int D> VOR_HD void certify_body(const CertifyArgs<D> &A, int t) {
     if (ehi > A.hi) atomic_max_d(&A.need[1], ehi);
 }
 
+// slab mode: this slab's part of the GLOBAL canonical edge list.  An edge of the local list (local input indices) is
+// emitted iff the endpoint with the lower GLOBAL index is owned by this slab; key = lo << 32 | hi in global indices,
+// ~0 for edges that belong to another slab (they sort to the end).
+struct SlabEdgeArgs { const uint32_t *edges; const long long *gmap; const unsigned char *owned; unsigned long long *keys; };
+VOR_HD void slab_edge_key_body(const SlabEdgeArgs &A, int i) {
+    const uint32_t a = A.edges[2 * (size_t)i], b = A.edges[2 * (size_t)i + 1];
+    const long long ga = A.gmap[a], gb = A.gmap[b];
+    const bool mine = ga < gb ? A.owned[a] != 0 : A.owned[b] != 0;
+    const unsigned long long lo = (unsigned long long)(ga < gb ? ga : gb), hi = (unsigned long long)(ga < gb ? gb : ga);
+    A.keys[i] = mine ? ((lo << 32) | hi) : ~0ULL;
+}
+struct KeyCountArgs { const unsigned long long *keys; unsigned long long *count; };
+VOR_HD void key_count_body(const KeyCountArgs &A, int i) {   // sorted keys: the first ~0 marks the end of the part
+    if (A.keys[i] != ~0ULL && A.keys[i + 1] == ~0ULL) *A.count = (unsigned long long)i + 1;
+}
+struct KeyUnpackArgs { const unsigned long long *keys; uint32_t *out; };
+VOR_HD void key_unpack_body(const KeyUnpackArgs &A, int i) {
+    A.out[2 * (size_t)i] = (uint32_t)(A.keys[i] >> 32);
+    A.out[2 * (size_t)i + 1] = (uint32_t)(A.keys[i] & 0xffffffffULL);
+}
+
 // ---- validation
 template <int D> struct ValidateArgs {
     Mesh<D> m;

@@ -271,20 +271,14 @@ def delaunay_slab(lib, points, global_index, device=0, axis=0, coarse_div=16, ha
         info.update({"rounds": rounds, "halo_rows_sent": sent_rows, "halo_rows_received": recv_rows, "coarse_points": int(c_pts.shape[0]),
                      "tree_points": int(sum(len(g) for g in gmap)), "region": have, "own_range": [my_lo, my_hi]})
 
-        # ---- 5. edges at owned points, emitted by the owner of the endpoint with the lower global index
+        # ---- 5. edges at owned points, emitted by the owner of the endpoint with the lower global index (mapped, filtered and
+        # sorted on the device: vor_tree_edges_slab)
+        gm = np.ascontiguousarray(np.concatenate(gmap) if gmap else np.zeros(0, dtype=np.int64))
+        own_np = np.ascontiguousarray(np.concatenate(owned) if owned else np.zeros(0, dtype=np.uint8))
         n_e = C.c_size_t()
         ptr = C.c_void_p()
-        chk(lib.vor_tree_edges_host(h, C.byref(ptr), C.byref(n_e)))
-        e = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=(n_e.value, 2)) if n_e.value else np.zeros((0, 2), dtype=np.uint32)
-        gm = np.concatenate(gmap) if gmap else np.zeros(0, dtype=np.int64)
-        own_np = np.concatenate(owned) if owned else np.zeros(0, dtype=np.uint8)
-        ga, gb = gm[e[:, 0]], gm[e[:, 1]]
-        low_is_a = ga < gb
-        keep = np.where(low_is_a, own_np[e[:, 0]], own_np[e[:, 1]]) != 0
-        out_e = np.stack([np.minimum(ga, gb)[keep], np.maximum(ga, gb)[keep]], axis=1).astype(np.uint32)
-        lib.vor_host_free(ptr)
-        key = (out_e[:, 0].astype(np.uint64) << np.uint64(32)) | out_e[:, 1].astype(np.uint64)
-        out_e = out_e[np.argsort(key, kind="stable")]
+        chk(lib.vor_tree_edges_slab(h, gm.ctypes.data_as(_capi.i64p), own_np.ctypes.data_as(C.POINTER(C.c_uint8)), len(gm), C.byref(ptr), C.byref(n_e)))
+        out_e = np.asarray(_capi._HostBlock(lib, ptr.value, (n_e.value, 2), "<u4")) if n_e.value else np.zeros((0, 2), dtype=np.uint32)
     finally:
         lib.vor_tree_destroy(h)
     return SlabResult(out_e, info)
