@@ -74,6 +74,8 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        if os.environ.get("VOR_NO_SAMPLER"):   # diagnostics only: a bench line without clocks is not a valid bench line
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)

@@ -104,7 +104,18 @@ struct HostPool {
     std::mutex mu;
     std::multimap<std::pair<int, size_t>, void *> cache;          // (pinned, size) -> block
     std::unordered_map<void *, std::pair<int, size_t>> live;
-    static bool want_pinned() { static const bool p = [] { const char *e = getenv("VOR_PINNED_RESULTS"); return e && atoi(e) != 0; }(); return p; }
+    // page-locked result blocks by default (the DMA writes them directly: 621 MB of edges in ~12 ms instead of ~30 ms through
+    // the staging chunks); VOR_PINNED_RESULTS=0 for pageable blocks.  The first block of a size costs a cudaMallocHost
+    // (~270 ms for 621 MB): vor_delaunay warms the pool on a side thread while the points are inserted.
+    static bool want_pinned() { static const bool p = [] { const char *e = getenv("VOR_PINNED_RESULTS"); return !e || atoi(e) != 0; }(); return p; }
+    bool has_block(size_t bytes) {
+        const size_t g = (size_t)2 << 20;
+        const size_t need = (std::max(bytes, (size_t)16) + g - 1) / g * g;
+        const int pin = want_pinned() ? 1 : 0;
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.lower_bound({pin, need});
+        return it != cache.end() && it->first.first == pin && it->first.second <= need + need / 4 + g;
+    }
     void *alloc(size_t bytes, bool *pinned_out) {
         const size_t g = (size_t)2 << 20;
         const size_t need = (std::max(bytes, (size_t)16) + g - 1) / g * g;

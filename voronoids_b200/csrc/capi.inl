@@ -92,6 +92,7 @@ int vor_set_option(const char *name, double value) {
     else if (n == "tet_factor") g_opts.tet_factor = value;
     else if (n == "compact_frac") g_opts.compact_frac = value;
     else if (n == "stage_log") g_opts.stage_log = (int)value;
+    else if (n == "tiled") g_opts.tiled = (int)value;
     else if (n == "capk") { g_opts.capk = (int)value; g_opts.capb = 2 * g_opts.capk + 4; }
     else if (n == "big_slots") g_opts.big_slots = (int)value;
     else if (n == "big_capk") g_opts.big_capk = (int)value;
@@ -327,6 +328,22 @@ vor_status vor_delaunay(int dim, const double *points, size_t n, int device, vor
     return guarded([&]() -> vor_status {
         if (!out || (dim != 2 && dim != 3)) { g_err = "bad argument"; return VOR_ERR_ARG; }
         vor::be::set_device(device);
+        // warm the host pool for the edge list the caller is about to ask for (~7.8 edges per 3D point, ~3 per 2D point):
+        // the page-locking of a fresh block runs on a side thread under the insertion
+        std::thread warm;
+#if VOR_GPU
+        const size_t est = (size_t)((dim == 3 ? 8.2 : 3.2) * (double)n) * 8;
+        if (n >= 100000 && vor::be::HostPool::want_pinned() && !vor::be::g_hostpool.has_block(est))
+            warm = std::thread([est, device] {
+                try {
+                    vor::be::set_device(device);
+                    bool pinned = false;
+                    void *p = vor::be::g_hostpool.alloc(est, &pinned);
+                    vor::be::g_hostpool.free(p);
+                } catch (...) {}
+            });
+#endif
+        struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{warm};
         DevBuf d(sizeof(double) * n * dim);
         vor::be::h2d_big(d.p, points, sizeof(double) * n * dim, vor::be::Stream{});
         vor_tree *t = nullptr;

@@ -558,6 +558,70 @@ k_attempt_hot(AttemptArgs<D> A, RoundSel rsel) {
     }
 }
 
+// Tiled form of the same kernel (option "tiled"; a recorded NEGATIVE result, off by default: 10M points 138.6 ms against 115.3 ms,
+// attempt 60.6 vs 52.9 ms, commit 56.7 vs 40.5 ms).  Resident blocks of 4 warps pull TILES of `tile` consecutive
+// slots from a device-side queue (one atomicAdd per tile); the threads of the block first classify the tile's slots in
+// parallel (entry out of range / point already inserted / exact twin's point -> status written at once), the live slots
+// are compacted into shared memory, and the warps take live slots from that list until it is empty.  A third to a half of
+// the slots of a round are dead: with one block per pair of slots the SMs kept launching blocks that exit at once (24 of
+// 36 resident warps busy on average, ncu round 2); here every resident warp works on a live attempt, the load is balanced
+// inside the block by the shared list and across blocks by the tile queue.  `tile` shrinks with the round (engine.cuh)
+// so that a small round still spreads one slot per warp over the whole machine.
+// Why it loses (as the per-SM queues of round 1 and the strided resident warps did): with one block per pair of slots the
+// hardware scheduler hands the slots out IN ORDER, so the ~5,000 attempts in flight at any moment are one contiguous run
+// of the Morton-ordered list -- neighbours in space, whose conflict regions share simplices, 64 B lines and DRAM pages
+// at (nearly) the same time.  Any scheme that gives a block or a warp a private range spreads the attempts in flight over
+// the whole round and loses that sharing (L2 hit rate of the attempt kernel: 41 % with the in-order window).
+#define VOR_TILE_BLOCK 128
+template <int D>
+__global__ void __launch_bounds__(VOR_TILE_BLOCK, (65536 / (VOR_HOT_REGS * VOR_TILE_BLOCK)) > 16 ? 16 : (65536 / (VOR_HOT_REGS * VOR_TILE_BLOCK)))
+k_attempt_hot_tiled(AttemptArgs<D> A, RoundSel rsel, int tile) {
+    constexpr int W = VOR_TILE_BLOCK / 32;
+    __shared__ int s_kid[W][VOR_SK];
+    __shared__ int4 s_knb[W][VOR_SK];
+    __shared__ int s_list[VOR_TILE_BLOCK];
+    __shared__ int s_n, s_next, s_tile;
+    const Mesh<D> &m = A.m;
+    const int w = threadIdx.x >> 5, gl = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { m.cnt->sph_lo = m.cnt->ntets; m.cnt->q_commit = 0; }
+    const int ntiles = (rsel.nsel + tile - 1) / tile;
+    for (;;) {
+        if (threadIdx.x == 0) { s_tile = atomicAdd(&m.cnt->q_attempt, 1); s_n = 0; s_next = 0; }
+        __syncthreads();
+        const int t = s_tile;
+        if (t >= ntiles) break;
+        // classify the slots of the tile, one thread each
+        if ((int)threadIdx.x < tile) {
+            const int slot = t * tile + (int)threadIdx.x;
+            if (slot < rsel.nsel) {
+                const int a = slot_entry(rsel, slot);
+                bool live = false;
+                if (a < rsel.nact) {
+                    const int v = A.act[a];
+                    if (m.seed[v] >= 0) {
+                        const int fl = A.slowFlag[v];
+                        if (fl == 0) live = true;
+                        else if (fl != A.keybase) A.scr.slowSlots[atomicAdd(&m.cnt->nslow, 1)] = slot;   // the exact twin's point
+                    }
+                }
+                if (live) s_list[atomicAdd(&s_n, 1)] = slot;
+                else A.scr.slotStatus[slot] = ST_LOST;
+            }
+        }
+        __syncthreads();
+        const int n = s_n;
+        for (;;) {
+            int i = 0;
+            if (gl == 0) i = atomicAdd(&s_next, 1);
+            i = __shfl_sync(0xffffffffu, i, 0);
+            if (i >= n) break;
+            attempt_hot_one<D>(A, rsel, s_list[i], s_kid[w], s_knb[w]);
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+}
+
 // the exact twin behind the hot kernel: the slots the hot kernel queued this round (points flagged in earlier rounds)
 template <int D, int RED>
 __global__ void __launch_bounds__(VOR_ATTEMPT_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_ATTEMPT_BLOCK)) k_attempt_slow(AttemptArgs<D> A, RoundSel rsel) {
@@ -837,6 +901,40 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
     }
 }
 
+// tiled form (see k_attempt_hot_tiled): most slots of a round hold no winner candidate
+template <int D>
+__global__ void __launch_bounds__(VOR_TILE_BLOCK) k_commit_tiled(CheckArgs<D> A, const int *act, RoundSel rsel, int stats, int tile) {
+    constexpr int W = VOR_TILE_BLOCK / 32;
+    __shared__ CommitSmem<D> s_cav[W];
+    __shared__ int s_list[VOR_TILE_BLOCK];
+    __shared__ int s_n, s_next, s_tile;
+    const Mesh<D> &m = A.m;
+    const int w = threadIdx.x >> 5, gl = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { m.cnt->nbig = 0; m.cnt->nslow = 0; m.cnt->q_attempt = 0; }
+    const int ntiles = (rsel.nsel + tile - 1) / tile;
+    for (;;) {
+        if (threadIdx.x == 0) { s_tile = atomicAdd(&m.cnt->q_commit, 1); s_n = 0; s_next = 0; }
+        __syncthreads();
+        const int t = s_tile;
+        if (t >= ntiles) break;
+        if ((int)threadIdx.x < tile) {
+            const int slot = t * tile + (int)threadIdx.x;
+            if (slot < rsel.nsel && A.scr.slotStatus[slot] == ST_OK) s_list[atomicAdd(&s_n, 1)] = slot;
+        }
+        __syncthreads();
+        const int n = s_n;
+        for (;;) {
+            int i = 0;
+            if (gl == 0) i = atomicAdd(&s_next, 1);
+            i = __shfl_sync(0xffffffffu, i, 0);
+            if (i >= n) break;
+            commit_one<D, 32>(A, act, rsel, stats, s_list[i], s_cav[w]);
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // spheres: ownership words (free) + certified circumsphere filter (sphere.cuh) of the simplices created by the commit
 // kernel just before it in the stream -- the slots [cnt->sph_lo, cnt->ntets) of the bump allocator.  One thread per new
@@ -846,7 +944,7 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
 // first thread of the next attempt kernel (the allocator does not move during an attempt kernel).
 // ------------------------------------------------------------------------------------------
 #ifndef VOR_SPH_MINB
-#define VOR_SPH_MINB 2
+#define VOR_SPH_MINB 3
 #endif
 template <int D>
 __global__ void __launch_bounds__(256, VOR_SPH_MINB) k_spheres(Mesh<D> m) {

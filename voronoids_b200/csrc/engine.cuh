@@ -45,6 +45,7 @@ struct EngineOptions {
     int commit_smem = 1;         // commit retriangulates cavities staged in shared memory (0 = through the global store)
     int split_exact = 1;         // attempt kernel as a hot twin without exact predicates + an exact twin for the points it flags
     int red = 1;                 // kill reservation as a fire-and-forget reduction (match.any dedup), see k_attempt_coop
+    int tiled = 0;               // round kernels as resident blocks pulling tiles of slots from a device queue (measured slower: off)
     int smem_pad = 0;            // diagnostics: extra dynamic shared memory per block of the round kernels (caps resident warps)
     int persist_waves = 1000000; // grid of the round kernels = resident blocks x this (1 = persistent warps; large = one block per slot pair)
     double compact_frac = 0.85;  // the active list is compacted (at a host read-back) once fewer than this fraction of it is pending
@@ -63,6 +64,7 @@ inline void options_from_env(EngineOptions &o) {
     if (const char *e = getenv("VOR_COMPACT_FRAC")) o.compact_frac = atof(e);
     if (const char *e = getenv("VOR_PERSIST_WAVES")) o.persist_waves = std::max(1, atoi(e));
     if (const char *e = getenv("VOR_SMEM_PAD")) o.smem_pad = atoi(e);
+    if (const char *e = getenv("VOR_TILED")) o.tiled = atoi(e);
     if (const char *e = getenv("VOR_COOP")) o.coop = atoi(e);
     if (const char *e = getenv("VOR_ROUNDS_PER_SYNC")) o.rounds_per_sync = atoi(e);
     if (const char *e = getenv("VOR_SELECT_MODE")) o.select_mode = atoi(e);
@@ -106,7 +108,8 @@ template <int D> class Engine {
     Scratch scr{};
     bool slowPending = false, splitDisabled = false;
     int flagPending = 0;
-    int occHot = -1, occCommit = -1;   // resident blocks of the round kernels on this device
+    int occHot = -1, occCommit = -1, occTiledHot = 1, occTiledCommit = 1;   // resident blocks of the round kernels on this device
+    int tileNow = 4;
     int *act = nullptr, *act2 = nullptr, *blockCnt = nullptr, *slowFlag = nullptr;
     long long *d_misc = nullptr;
     long long insertedTotal = 0;
@@ -575,6 +578,11 @@ template <int D> class Engine {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_commit_coop<D, G>, VOR_COOP_BLOCK, 0);
             occHot = std::max(1, o1) * nsm;
             occCommit = std::max(1, o2) * nsm;
+            int o3 = 1, o4 = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, k_attempt_hot_tiled<D>, VOR_TILE_BLOCK, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o4, k_commit_tiled<D>, VOR_TILE_BLOCK, 0);
+            occTiledHot = std::max(1, o3) * nsm;
+            occTiledCommit = std::max(1, o4) * nsm;
         }
         const unsigned grid = (unsigned)std::min<long long>(((long long)sel.nsel * G + VOR_COOP_BLOCK - 1) / VOR_COOP_BLOCK, (long long)occCommit * opt.persist_waves);
         const unsigned agrid = (unsigned)(((long long)sel.nsel * G + VOR_ATTEMPT_BLOCK - 1) / VOR_ATTEMPT_BLOCK);
@@ -582,8 +590,17 @@ template <int D> class Engine {
         if (opt.red && aa.slowFlag) {
             // hot twin without the exact predicates in its call tree; while flagged points are pending (host
             // knowledge, one read-back old) the exact twin follows and attempts only those
-            const unsigned hgrid = (unsigned)std::min<long long>(((long long)sel.nsel * G + VOR_HOT_BLOCK - 1) / VOR_HOT_BLOCK, (long long)occHot * opt.persist_waves);
-            k_attempt_hot<D><<<hgrid, VOR_HOT_BLOCK, (size_t)opt.smem_pad, stream>>>(aa, sel);
+            if (opt.tiled) {
+                // tile = slots per block visit: large rounds 128, small rounds down to one slot per warp
+                const long long per = (long long)sel.nsel / std::max(1, occTiledHot);
+                tileNow = 4;
+                while (tileNow < VOR_TILE_BLOCK && tileNow < per) tileNow <<= 1;
+                const long long ntiles = ((long long)sel.nsel + tileNow - 1) / tileNow;
+                k_attempt_hot_tiled<D><<<(unsigned)std::min<long long>(ntiles, occTiledHot), VOR_TILE_BLOCK, (size_t)opt.smem_pad, stream>>>(aa, sel, tileNow);
+            } else {
+                const unsigned hgrid = (unsigned)std::min<long long>(((long long)sel.nsel * G + VOR_HOT_BLOCK - 1) / VOR_HOT_BLOCK, (long long)occHot * opt.persist_waves);
+                k_attempt_hot<D><<<hgrid, VOR_HOT_BLOCK, (size_t)opt.smem_pad, stream>>>(aa, sel);
+            }
             if (slowNow) {
                 // the slots the hot kernel queued (points it flagged in earlier rounds); a small grid-stride launch
                 AttemptArgs<D> as = aa;
@@ -600,7 +617,12 @@ template <int D> class Engine {
         }
         prof.stop(stream);
         prof.start(2, stream);
-        k_commit_coop<D, G><<<grid, VOR_COOP_BLOCK, (size_t)opt.smem_pad, stream>>>(ca, act, sel, (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2));
+        if (opt.tiled && opt.red && aa.slowFlag) {
+            const long long ntiles = ((long long)sel.nsel + tileNow - 1) / tileNow;
+            k_commit_tiled<D><<<(unsigned)std::min<long long>(ntiles, occTiledCommit), VOR_TILE_BLOCK, (size_t)opt.smem_pad, stream>>>(
+                ca, act, sel, (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2), tileNow);
+        } else
+            k_commit_coop<D, G><<<grid, VOR_COOP_BLOCK, (size_t)opt.smem_pad, stream>>>(ca, act, sel, (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2));
         prof.stop(stream);
         prof.start(1, stream);
         {

@@ -17,7 +17,8 @@
 //   a, b, c  = computed edge vectors p_i - p_0; the true centre c* relative to p_0 solves 2 M* x = s* (M* = true edge
 //              vectors as rows, s*_i = |edge_i|^2).  For the computed x^ (Cramer's rule in f64) the residual of the TRUE
 //              system is bounded by |r^_i| + 16 EPS (2 |edge_i|.|x^| + |edge_i|^2), with r^ evaluated in f64, and
-//              |x^ - c*'| = |M*^-1 r*| / 2 <= ||permanent adjugate||_F |r*| / (2 (|det| - 8 EPS permanent(det))).
+//              |x^ - c*'| = |M*^-1 r*| / 2 <= ||adj M||_F |r*| / (2 (|det| - 8 EPS permanent(|M|))), with the cheap upper bounds
+//              ||adj M||_F^2 <= |b|^2|c|^2 + |c|^2|a|^2 + |a|^2|b|^2 and permanent(|M|) <= product of the row 1-norms.
 //              A simplex whose determinant bound is not positive gets no filter (rin2 = 0, rout2 = +inf).
 //   storing   the centre as floats relative to the origin adds the measured deviation |float(g) - g| and the rounding of
 //              the two additions; the query q = fl(p - origin) adds EPS |p - origin| (Mesh::sref.qerr bounds it).
@@ -103,18 +104,17 @@ VOR_HD SphereBlk sphere_make(const double4 &p0, const double4 &p1, const double4
     const double ax = p1.x - p0.x, ay = p1.y - p0.y, az = p1.z - p0.z;
     const double bx = p2.x - p0.x, by = p2.y - p0.y, bz = p2.z - p0.z;
     const double cx = p3.x - p0.x, cy = p3.y - p0.y, cz = p3.z - p0.z;
-    // adjugate columns (cross products) and their permanents
+    // adjugate columns (cross products)
     const double bcx = by * cz - bz * cy, bcy = bz * cx - bx * cz, bcz = bx * cy - by * cx;
     const double cax = cy * az - cz * ay, cay = cz * ax - cx * az, caz = cx * ay - cy * ax;
     const double abx = ay * bz - az * by, aby = az * bx - ax * bz, abz = ax * by - ay * bx;
-    const double pbcx = fabs(by * cz) + fabs(bz * cy), pbcy = fabs(bz * cx) + fabs(bx * cz), pbcz = fabs(bx * cy) + fabs(by * cx);
-    const double pcax = fabs(cy * az) + fabs(cz * ay), pcay = fabs(cz * ax) + fabs(cx * az), pcaz = fabs(cx * ay) + fabs(cy * ax);
-    const double pabx = fabs(ay * bz) + fabs(az * by), paby = fabs(az * bx) + fabs(ax * bz), pabz = fabs(ax * by) + fabs(ay * bx);
     const double det = ax * bcx + ay * bcy + az * bcz;
-    const double permdet = fabs(ax) * pbcx + fabs(ay) * pbcy + fabs(az) * pbcz;
-    const double detLow = fabs(det) - 8.0 * SPH_EPS * permdet;
-    if (!(detLow > 0.0)) return sphere_none();
     const double sa = ax * ax + ay * ay + az * az, sb = bx * bx + by * by + bz * bz, sc = cx * cx + cy * cy + cz * cz;
+    // cheap upper bounds in place of the permanents (the kernel that runs this is bound by the FP64 pipe): the permanent of
+    // |M| is at most the product of the row 1-norms, and |u x v| <= |u| |v| bounds the Frobenius norm of the adjugate
+    const double a1 = fabs(ax) + fabs(ay) + fabs(az), b1 = fabs(bx) + fabs(by) + fabs(bz), c1 = fabs(cx) + fabs(cy) + fabs(cz);
+    const double detLow = fabs(det) - 8.0 * SPH_EPS * (a1 * b1 * c1) * (1.0 + 1e-9);
+    if (!(detLow > 0.0)) return sphere_none();
     const double inv = 0.5 / det;
     const double ccx = (sa * bcx + sb * cax + sc * abx) * inv;
     const double ccy = (sa * bcy + sb * cay + sc * aby) * inv;
@@ -123,8 +123,8 @@ VOR_HD SphereBlk sphere_make(const double4 &p0, const double4 &p1, const double4
     const double ra = fabs(2.0 * (ax * ccx + ay * ccy + az * ccz) - sa) + 16.0 * SPH_EPS * (2.0 * (fabs(ax) * acx + fabs(ay) * acy + fabs(az) * acz) + sa);
     const double rb = fabs(2.0 * (bx * ccx + by * ccy + bz * ccz) - sb) + 16.0 * SPH_EPS * (2.0 * (fabs(bx) * acx + fabs(by) * acy + fabs(bz) * acz) + sb);
     const double rc = fabs(2.0 * (cx * ccx + cy * ccy + cz * ccz) - sc) + 16.0 * SPH_EPS * (2.0 * (fabs(cx) * acx + fabs(cy) * acy + fabs(cz) * acz) + sc);
-    const double adj2 = pbcx * pbcx + pbcy * pbcy + pbcz * pbcz + pcax * pcax + pcay * pcay + pcaz * pcaz + pabx * pabx + paby * paby + pabz * pabz;
-    const double rho_c = 0.5 * sqrt(adj2) * sqrt(ra * ra + rb * rb + rc * rc) / detLow * (1.0 + 1e-9);
+    const double adj2 = (sb * sc + sc * sa + sa * sb) * (1.0 + 1e-9);
+    const double rho_c = 0.5 * sqrt(adj2 * (ra * ra + rb * rb + rc * rc)) / detLow * (1.0 + 1e-9);
     return sphere_finish(p0.x, p0.y, p0.z, ccx, ccy, ccz, rho_c, R);
 }
 

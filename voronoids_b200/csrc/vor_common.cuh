@@ -141,6 +141,7 @@ struct Counters {
     unsigned long long part[128][4];
     int nflag_set, nflag_done;       // points handed to / finished by the exact twin of the attempt kernel
     int sph_lo, nslow;                // simplex slots below sph_lo have their sphere block (k_spheres); slots queued for the exact twin
+    int q_attempt, q_commit;          // tile queues of the tiled round kernels (each is reset by the other kernel)
     unsigned long long sph_undecided; // conflict tests the stored sphere filter left to the determinant predicate
 };
 constexpr int NPART = 128;
