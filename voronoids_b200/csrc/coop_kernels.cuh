@@ -30,7 +30,7 @@ template <int G> __device__ __forceinline__ unsigned group_mask() {
 // Selection is implicit and stratified: slot g of a round attempts active entry a = g * stride + offset, i.e. one
 // point per run of `stride` consecutive entries of the Morton-ordered active list (rotating offset), so no selection
 // kernel and no compaction of the selected set are needed.  A round is two launches: attempt, commit.
-struct RoundSel { int nact; int stride; int offset; int nsel; };
+struct RoundSel { int nact; int stride; int offset; int nsel; int first; int last; };   // this launch works on slots [first, last) of the round's nsel
 __device__ __forceinline__ int slot_entry(const RoundSel &rs, int slot) { return slot * rs.stride + rs.offset; }
 
 template <int D> struct GeoCoop;
@@ -552,7 +552,7 @@ k_attempt_hot(AttemptArgs<D> A, RoundSel rsel) {
     __shared__ int4 s_knb[VOR_HOT_BLOCK / 32][VOR_SK];
     if (blockIdx.x == 0 && threadIdx.x == 0) A.m.cnt->sph_lo = A.m.cnt->ntets;   // k_spheres of the last round is done
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < rsel.nsel; slot += nwarps) {
+    for (int slot = rsel.first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); slot < rsel.last; slot += nwarps) {
         attempt_hot_one<D>(A, rsel, slot, s_kid[threadIdx.x >> 5], s_knb[threadIdx.x >> 5]);
         __syncwarp();
     }
@@ -647,9 +647,9 @@ __global__ void __launch_bounds__(AttemptLaunch<EXACT>::block, AttemptLaunch<EXA
     // flood level starts from shared memory instead of two dependent round trips (scratch, then record)
     __shared__ int s_kid[AttemptLaunch<EXACT>::block / G][VOR_SK];
     __shared__ int4 s_knb[AttemptLaunch<EXACT>::block / G][VOR_SK];
-    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;   // group = attempt slot
+    const int gid = rsel.first + (blockIdx.x * blockDim.x + threadIdx.x) / G;   // group = attempt slot
     if (blockIdx.x == 0 && threadIdx.x == 0) A.m.cnt->sph_lo = A.m.cnt->ntets;   // k_spheres of the last round is done
-    if (gid >= rsel.nsel) return;
+    if (gid >= rsel.last) return;
     attempt_one<D, G, RED, EXACT>(A, rsel, gid, s_kid[threadIdx.x / G], s_knb[threadIdx.x / G]);
 }
 
@@ -895,7 +895,7 @@ __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, 
     const unsigned gmask = group_mask<G>();
     if (blockIdx.x == 0 && threadIdx.x == 0) { A.m.cnt->nbig = 0; A.m.cnt->nslow = 0; }   // overflow slots and the exact twin's queue are per round (attempt is over)
     const int ngroups = (gridDim.x * blockDim.x) / G;
-    for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) / G; slot < rsel.nsel; slot += ngroups) {
+    for (int slot = rsel.first + (blockIdx.x * blockDim.x + threadIdx.x) / G; slot < rsel.last; slot += ngroups) {
         commit_one<D, G>(A, act, rsel, stats, slot, s_cav[threadIdx.x / G]);
         __syncwarp(gmask);
     }

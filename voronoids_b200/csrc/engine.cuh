@@ -45,6 +45,8 @@ struct EngineOptions {
     int commit_smem = 1;         // commit retriangulates cavities staged in shared memory (0 = through the global store)
     int split_exact = 1;         // attempt kernel as a hot twin without exact predicates + an exact twin for the points it flags
     int red = 1;                 // kill reservation as a fire-and-forget reduction (match.any dedup), see k_attempt_coop
+    int subround = 0;            // > 0: rounds larger than this many slots run as spatially contiguous sub-rounds of about this size (measured
+                                 // slower at every size: 16k 144 ms, 32k 129, 64k 120, off 114 -- launch tails outweigh the L2 reuse)
     int tiled = 0;               // round kernels as resident blocks pulling tiles of slots from a device queue (measured slower: off)
     int smem_pad = 0;            // diagnostics: extra dynamic shared memory per block of the round kernels (caps resident warps)
     int persist_waves = 1000000; // grid of the round kernels = resident blocks x this (1 = persistent warps; large = one block per slot pair)
@@ -65,6 +67,7 @@ inline void options_from_env(EngineOptions &o) {
     if (const char *e = getenv("VOR_PERSIST_WAVES")) o.persist_waves = std::max(1, atoi(e));
     if (const char *e = getenv("VOR_SMEM_PAD")) o.smem_pad = atoi(e);
     if (const char *e = getenv("VOR_TILED")) o.tiled = atoi(e);
+    if (const char *e = getenv("VOR_SUBROUND")) o.subround = atoi(e);
     if (const char *e = getenv("VOR_COOP")) o.coop = atoi(e);
     if (const char *e = getenv("VOR_ROUNDS_PER_SYNC")) o.rounds_per_sync = atoi(e);
     if (const char *e = getenv("VOR_SELECT_MODE")) o.select_mode = atoi(e);
@@ -584,8 +587,9 @@ template <int D> class Engine {
             occTiledHot = std::max(1, o3) * nsm;
             occTiledCommit = std::max(1, o4) * nsm;
         }
-        const unsigned grid = (unsigned)std::min<long long>(((long long)sel.nsel * G + VOR_COOP_BLOCK - 1) / VOR_COOP_BLOCK, (long long)occCommit * opt.persist_waves);
-        const unsigned agrid = (unsigned)(((long long)sel.nsel * G + VOR_ATTEMPT_BLOCK - 1) / VOR_ATTEMPT_BLOCK);
+        const long long nslots = (long long)sel.last - sel.first;
+        const unsigned grid = (unsigned)std::min<long long>((nslots * G + VOR_COOP_BLOCK - 1) / VOR_COOP_BLOCK, (long long)occCommit * opt.persist_waves);
+        const unsigned agrid = (unsigned)((((long long)sel.last - sel.first) * G + VOR_ATTEMPT_BLOCK - 1) / VOR_ATTEMPT_BLOCK);
         prof.start(0, stream);
         if (opt.red && aa.slowFlag) {
             // hot twin without the exact predicates in its call tree; while flagged points are pending (host
@@ -598,7 +602,7 @@ template <int D> class Engine {
                 const long long ntiles = ((long long)sel.nsel + tileNow - 1) / tileNow;
                 k_attempt_hot_tiled<D><<<(unsigned)std::min<long long>(ntiles, occTiledHot), VOR_TILE_BLOCK, (size_t)opt.smem_pad, stream>>>(aa, sel, tileNow);
             } else {
-                const unsigned hgrid = (unsigned)std::min<long long>(((long long)sel.nsel * G + VOR_HOT_BLOCK - 1) / VOR_HOT_BLOCK, (long long)occHot * opt.persist_waves);
+                const unsigned hgrid = (unsigned)std::min<long long>((nslots * G + VOR_HOT_BLOCK - 1) / VOR_HOT_BLOCK, (long long)occHot * opt.persist_waves);
                 k_attempt_hot<D><<<hgrid, VOR_HOT_BLOCK, (size_t)opt.smem_pad, stream>>>(aa, sel);
             }
             if (slowNow) {
@@ -627,7 +631,7 @@ template <int D> class Engine {
         prof.start(1, stream);
         {
             // new simplices of the round: at most ~36 per attempted point; grid-stride over whatever the allocator handed out
-            const long long want = ((long long)sel.nsel * (D == 3 ? 36 : 9) + 255) / 256;
+            const long long want = (nslots * (D == 3 ? 36 : 9) + 255) / 256;
             k_spheres<D><<<(unsigned)std::max(1LL, std::min(want, 148LL * 16)), 256, 0, stream>>>(mesh);
         }
         prof.stop(stream);
@@ -666,7 +670,7 @@ template <int D> class Engine {
                 if (epoch <= 0) reset_owners();
                 roundSalt = roundSalt * 1664525u + 1013904223u;
                 const int keybase = epoch << (bits + 1);
-                const RoundSel sel{nact, stride, (int)((roundSalt >> 8) % (uint32_t)stride), nsel};
+                const RoundSel sel{nact, stride, (int)((roundSalt >> 8) % (uint32_t)stride), nsel, 0, nsel};
                 // hot / exact twins of the attempt kernel -- unless this input keeps leaving the FP64 filter (near-degenerate:
                 // thousands of flagged points), where one kernel with the exact path inside is the better deal
                 const bool split = opt.split_exact && !splitDisabled;
@@ -675,7 +679,18 @@ template <int D> class Engine {
                 // the exact twin is pure latency for a handful of points (~26 us per launch): it runs once per batch of
                 // rounds, and in every round once the flagged points are most of what is left of the stage
                 const bool slowNow = slowPending && (r == R - 1 || 4LL * flagPending >= (long long)pending);
-                launch_round<32>(aa, ca, sel, slowNow);
+                if (opt.subround > 0 && nsel > opt.subround + opt.subround / 2 && !opt.tiled) {
+                    // a large round as a sequence of spatially contiguous sub-rounds (slots are in Morton order): what the
+                    // attempt kernel of a sub-round pulled into L2 is still there for its commit and sphere kernels
+                    const int parts = (nsel + opt.subround - 1) / opt.subround;
+                    for (int q = 0; q < parts; q++) {
+                        RoundSel sub = sel;
+                        sub.first = (int)((long long)nsel * q / parts);
+                        sub.last = (int)((long long)nsel * (q + 1) / parts);
+                        launch_round<32>(aa, ca, sub, slowNow && q == parts - 1);
+                    }
+                } else
+                    launch_round<32>(aa, ca, sel, slowNow);
                 epoch--;
                 rs.rounds++;
                 rs.slots += (unsigned long long)nsel;
