@@ -271,6 +271,23 @@ extern std::atomic<unsigned long long> g_launches;   // kernels of this library 
 // a launch-configuration failure must surface at the launch, not as "no progress" hundreds of rounds later
 inline void check_launch(const char *what) { check(cudaGetLastError(), what); }
 
+// launch with the programmatic-stream-serialization attribute (see pdl_wait / pdl_trigger in coop_kernels.cuh); pdl == false:
+// a plain launch (the kernel's griddepcontrol instructions are no-ops then)
+template <class... KArgs, class... Args>
+inline void launch_pdl(bool pdl, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, Stream s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    VOR_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 // per-kernel-class CUDA-event timing on the launching stream (bench.py roofline; off unless option "profile")
 struct Prof {
     bool on = false;

@@ -21,6 +21,12 @@
 #if VOR_GPU
 namespace vor {
 
+// Programmatic dependent launch (sm_90+): the three kernels of a round depend on each other completely, but the NEXT kernel's
+// blocks can be set up and made resident while the current one drains -- they wait here until it has completed and flushed.
+// pdl_wait() must come before the first global access; pdl_trigger() lets the dependent launch begin early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <int G> __device__ __forceinline__ unsigned group_mask() {
     if (G == 32) return 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -550,6 +556,8 @@ __global__ void __launch_bounds__(VOR_HOT_BLOCK, (65536 / (VOR_HOT_REGS * VOR_HO
 k_attempt_hot(AttemptArgs<D> A, RoundSel rsel) {
     __shared__ int s_kid[VOR_HOT_BLOCK / 32][VOR_SK];
     __shared__ int4 s_knb[VOR_HOT_BLOCK / 32][VOR_SK];
+    pdl_trigger();
+    pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0) A.m.cnt->sph_lo = A.m.cnt->ntets;   // k_spheres of the last round is done
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int slot = rsel.first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); slot < rsel.last; slot += nwarps) {
@@ -627,6 +635,8 @@ template <int D, int RED>
 __global__ void __launch_bounds__(VOR_ATTEMPT_BLOCK, 65536 / (VOR_ATTEMPT_REGS * VOR_ATTEMPT_BLOCK)) k_attempt_slow(AttemptArgs<D> A, RoundSel rsel) {
     __shared__ int s_kid[VOR_ATTEMPT_BLOCK / 32][VOR_SK];
     __shared__ int4 s_knb[VOR_ATTEMPT_BLOCK / 32][VOR_SK];
+    pdl_trigger();
+    pdl_wait();
     const int n = min(A.m.cnt->nslow, A.scr.nslots);
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < n; idx += nwarps) {
@@ -733,8 +743,20 @@ __device__ __noinline__ void commit_global(const Mesh<D> &m, const ScrView sv, i
 // of pair_simplices (delaunay_tree.rs:674-695) and the forwarding choice never leave the SM; HBM sees one full 32 B
 // record per new simplex, one back-pointer per outer facet and one dead mark per killed simplex.
 constexpr int COMMIT_HS = 128;
+#ifndef VOR_RIDGE_HASH
+#define VOR_RIDGE_HASH 0          // 1: sibling links through a hash of the cavity's boundary ridges in shared memory instead of pivoting
+                                  // around every ridge through the staged cavity.  Parity-green, fewer instructions, but 64 instead of
+                                  // 40 registers and 64-bit shared-memory CAS: commit 43.2 vs 40.3 ms per 10M points (11.5 vs 12.0 per 1M)
+#endif
+constexpr int RIDGE_HS = 256;     // >= 1.5 x VOR_CB ridges, power of two
 template <int D> struct CommitSmem {
-    int4 tv[VOR_CK], tn[VOR_CK];
+    int4 tv[VOR_CK];
+#if VOR_RIDGE_HASH
+    unsigned long long rkey[RIDGE_HS];
+    int rval[RIDGE_HS][2];
+#else
+    int4 tn[VOR_CK];
+#endif
     int id[VOR_CK], fw[VOR_CK], hash[COMMIT_HS], f[VOR_CB], o[VOR_CB];
 };
 template <int D, int G>
@@ -755,9 +777,12 @@ __device__ __forceinline__ void commit_one(const CheckArgs<D> &A, const int *act
     const ScrView sv = scr_view(A.scr, slot, A.scr.slotBig[slot]);
     const int nk = A.scr.slotNk[slot], nb = A.scr.slotNb[slot];
     const bool fast = !(stats & 2) && nk <= CK && nb <= CB;   // stats bit 1: force the global-store path (A/B switch)
-    int4 *const tvs = sm.tv, *const tns = sm.tn;
+    int4 *const tvs = sm.tv;
     int *const ids = sm.id, *const fw = sm.fw, *const hash = sm.hash, *const sf = sm.f, *const so = sm.o;
+#if !VOR_RIDGE_HASH
+    int4 *const tns = sm.tn;
     int *const tni = reinterpret_cast<int *>(tns);
+#endif
 
     // -- ownership check; the fast path loads the cavity in the same level of gathers
     bool bad = false;
@@ -768,7 +793,10 @@ __device__ __forceinline__ void commit_one(const CheckArgs<D> &A, const int *act
             int4 tv, tn;
             load_rec_cg(m, t, tv, tn);
             if (ow.x != key_k || ow.y < key_k) bad = true;     // best killer, and no better point has it in its ring
-            ids[e] = t; tvs[e] = tv; tns[e] = tn; fw[e] = 0;
+            ids[e] = t; tvs[e] = tv; fw[e] = 0;
+#if !VOR_RIDGE_HASH
+            tns[e] = tn;
+#endif
         }
         for (int j = gl; j < nb; j += G) {
             const int f = sv.f[j], code = sv.o[j];
@@ -776,6 +804,9 @@ __device__ __forceinline__ void commit_one(const CheckArgs<D> &A, const int *act
             sf[j] = f; so[j] = code;
         }
         for (int h = gl; h < HS; h += G) hash[h] = -1;
+#if VOR_RIDGE_HASH
+        for (int h = gl; h < RIDGE_HS; h += G) { sm.rkey[h] = ~0ULL; sm.rval[h][0] = -1; }
+#endif
     } else {
         for (int j = gl; j < nk; j += G) {
             const int2 ow = __ldcg(reinterpret_cast<const int2 *>(&OWK(m, sv.k[j])));
@@ -821,6 +852,102 @@ __device__ __forceinline__ void commit_one(const CheckArgs<D> &A, const int *act
             set_err(m.cnt, ERR_CUDA);   // a pivot left the cavity: cannot happen on a consistent mesh
             return -1;
         };
+#if VOR_RIDGE_HASH
+        // Sibling links (pair_simplices, delaunay_tree.rs:674-695, O(k^2 M^2) there) through a hash of the boundary RIDGES: the
+        // boundary of a cavity is a closed surface (3D: every edge of it lies in exactly two boundary triangles; 2D: every vertex
+        // in two boundary edges), and the two new simplices on those two facets are each other's neighbours across the
+        // facet that contains the new point and the ridge.  One lane per new simplex: insert its M-1 ridges (key = the
+        // ridge's vertex ids, value = new simplex and the slot opposite the shared facet), then read the partner of each.
+        int myh[M], e0s = -1, is = 0;
+        int4 verts = make_int4(-1, -1, -1, -1);
+        for (int j0 = 0; j0 < nb; j0 += G) {          // nb <= VOR_CB: at most ceil(CB / G) passes, state of ONE facet per lane and pass
+            const int j = j0 + gl;
+            if (j < nb) {
+                const int f = sf[j];
+                const int e0 = local_of(f >> 2), i = f & 3;
+                e0s = e0; is = i;
+                if (e0 >= 0) {
+                    fw[e0] = j;                // any of its boundary facets (benign race)
+                    const int4 cv0 = tvs[e0];
+                    verts = cv0;
+                    set4(verts, i, v);
+#pragma unroll
+                    for (int k = 0; k < M; k++) {
+                        myh[k] = -1;
+                        if (k == i) continue;
+                        unsigned r0 = 0xffffffffu, r1 = 0xffffffffu;
+#pragma unroll
+                        for (int sidx = 0; sidx < M; sidx++) {
+                            if (sidx == i || sidx == k) continue;
+                            if (r0 == 0xffffffffu) r0 = (unsigned)get4(cv0, sidx); else r1 = (unsigned)get4(cv0, sidx);
+                        }
+                        const unsigned lo = r0 < r1 ? r0 : r1, hi = r0 < r1 ? r1 : r0;     // 2D: hi stays 0xffffffff
+                        const unsigned long long key = ((unsigned long long)lo << 32) | hi;
+                        unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ULL) >> 56) & (RIDGE_HS - 1);
+                        for (int probe = 0; probe < RIDGE_HS; probe++) {
+                            const unsigned long long old = atomicCAS(&sm.rkey[h], ~0ULL, key);
+                            if (old == ~0ULL || old == key) break;
+                            h = (h + 1) & (RIDGE_HS - 1);
+                        }
+                        myh[k] = (int)h;
+                        if (atomicCAS(&sm.rval[h][0], -1, j * 4 + k) != -1) sm.rval[h][1] = j * 4 + k;
+                    }
+                }
+            }
+            __syncwarp(gmask);
+            if (nb <= G) break;                        // the common case: one pass, links resolved below from registers
+            // more facets than lanes: resolve this pass's links after ALL passes have inserted (second loop below)
+        }
+        if (nb <= G) {
+            const int j = gl;
+            if (j < nb && e0s >= 0) {
+                const int i = is, outer = so[j], T = slot_of(j);
+                int4 nbr = make_int4(-1, -1, -1, -1);
+                set4(nbr, i, outer);
+#pragma unroll
+                for (int k = 0; k < M; k++) {
+                    if (k == i) continue;
+                    const int a = sm.rval[myh[k]][0], b = sm.rval[myh[k]][1];
+                    const int partner = a == j * 4 + k ? b : a;
+                    set4(nbr, k, slot_of(partner >> 2) * 4 + (partner & 3));
+                }
+                store_rec(m, T, verts, nbr);   // its ownership + sphere block is written by k_spheres, next in the stream
+                if (outer >= 0) TNI(m, outer >> 2, outer & 3) = T * 4 + i;
+            }
+        } else {
+            for (int j = gl; j < nb; j += G) {
+                const int f = sf[j];
+                const int e0 = local_of(f >> 2), i = f & 3;
+                if (e0 < 0) continue;
+                const int outer = so[j], T = slot_of(j);
+                const int4 cv0 = tvs[e0];
+                int4 vv = cv0;
+                set4(vv, i, v);
+                int4 nbr = make_int4(-1, -1, -1, -1);
+                set4(nbr, i, outer);
+#pragma unroll
+                for (int k = 0; k < M; k++) {
+                    if (k == i) continue;
+                    unsigned r0 = 0xffffffffu, r1 = 0xffffffffu;
+#pragma unroll
+                    for (int sidx = 0; sidx < M; sidx++) {
+                        if (sidx == i || sidx == k) continue;
+                        if (r0 == 0xffffffffu) r0 = (unsigned)get4(cv0, sidx); else r1 = (unsigned)get4(cv0, sidx);
+                    }
+                    const unsigned lo = r0 < r1 ? r0 : r1, hi = r0 < r1 ? r1 : r0;
+                    const unsigned long long key = ((unsigned long long)lo << 32) | hi;
+                    unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ULL) >> 56) & (RIDGE_HS - 1);
+                    for (int probe = 0; probe < RIDGE_HS && sm.rkey[h] != key; probe++) h = (h + 1) & (RIDGE_HS - 1);
+                    const int a = sm.rval[h][0], b = sm.rval[h][1];
+                    const int partner = a == j * 4 + k ? b : a;
+                    set4(nbr, k, slot_of(partner >> 2) * 4 + (partner & 3));
+                }
+                store_rec(m, T, vv, nbr);
+                if (outer >= 0) TNI(m, outer >> 2, outer & 3) = T * 4 + i;
+            }
+        }
+        __syncwarp(gmask);
+#else
         // phase A: markers on the boundary facets of the staged cavity, forwarding choice per killed simplex
         for (int j = gl; j < nb; j += G) {
             const int f = sf[j];
@@ -873,6 +1000,7 @@ __device__ __forceinline__ void commit_one(const CheckArgs<D> &A, const int *act
             store_rec(m, T, verts, nbr);   // its ownership + sphere block is written by k_spheres, next in the stream
             if (outer >= 0) TNI(m, outer >> 2, outer & 3) = T * 4 + i;
         }
+#endif
         // phase C: the killed simplices die; a dead simplex forwards to a new simplex on one of its own boundary
         // facets (interior simplices: to the first new simplex)
         for (int e = gl; e < nk; e += G) OWK(m, ids[e]) = ~slot_of(fw[e]);
@@ -893,6 +1021,8 @@ template <int D, int G>
 __global__ void __launch_bounds__(VOR_COOP_BLOCK) k_commit_coop(CheckArgs<D> A, const int *act, RoundSel rsel, int stats) {
     __shared__ CommitSmem<D> s_cav[VOR_COOP_BLOCK / G];
     const unsigned gmask = group_mask<G>();
+    pdl_trigger();
+    pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0) { A.m.cnt->nbig = 0; A.m.cnt->nslow = 0; }   // overflow slots and the exact twin's queue are per round (attempt is over)
     const int ngroups = (gridDim.x * blockDim.x) / G;
     for (int slot = rsel.first + (blockIdx.x * blockDim.x + threadIdx.x) / G; slot < rsel.last; slot += ngroups) {
@@ -948,6 +1078,8 @@ __global__ void __launch_bounds__(VOR_TILE_BLOCK) k_commit_tiled(CheckArgs<D> A,
 #endif
 template <int D>
 __global__ void __launch_bounds__(256, VOR_SPH_MINB) k_spheres(Mesh<D> m) {
+    pdl_trigger();
+    pdl_wait();
     const int lo = m.cnt->sph_lo, hi = min(m.cnt->ntets, m.cap);
     for (int t = lo + blockIdx.x * blockDim.x + threadIdx.x; t < hi; t += gridDim.x * blockDim.x) {
         const int4 tv = TV(m, t);

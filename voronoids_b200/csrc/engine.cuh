@@ -45,6 +45,10 @@ struct EngineOptions {
     int commit_smem = 1;         // commit retriangulates cavities staged in shared memory (0 = through the global store)
     int split_exact = 1;         // attempt kernel as a hot twin without exact predicates + an exact twin for the points it flags
     int red = 1;                 // kill reservation as a fire-and-forget reduction (match.any dedup), see k_attempt_coop
+    int pdl = 131072;            // rounds of at most this many slots launch their kernels with programmatic dependent launch (the next
+                                 // kernel's blocks are set up while the current one drains: -15..20 % on 100k..1M points; on large
+                                 // rounds the early-resident blocks cost more than the launch gap: 10M points 128 ms with every round, 117 without,
+                                 // 112.6 with this threshold)
     int subround = 0;            // > 0: rounds larger than this many slots run as spatially contiguous sub-rounds of about this size (measured
                                  // slower at every size: 16k 144 ms, 32k 129, 64k 120, off 114 -- launch tails outweigh the L2 reuse)
     int tiled = 0;               // round kernels as resident blocks pulling tiles of slots from a device queue (measured slower: off)
@@ -68,6 +72,7 @@ inline void options_from_env(EngineOptions &o) {
     if (const char *e = getenv("VOR_SMEM_PAD")) o.smem_pad = atoi(e);
     if (const char *e = getenv("VOR_TILED")) o.tiled = atoi(e);
     if (const char *e = getenv("VOR_SUBROUND")) o.subround = atoi(e);
+    if (const char *e = getenv("VOR_PDL")) o.pdl = atoi(e);
     if (const char *e = getenv("VOR_COOP")) o.coop = atoi(e);
     if (const char *e = getenv("VOR_ROUNDS_PER_SYNC")) o.rounds_per_sync = atoi(e);
     if (const char *e = getenv("VOR_SELECT_MODE")) o.select_mode = atoi(e);
@@ -588,6 +593,7 @@ template <int D> class Engine {
             occTiledCommit = std::max(1, o4) * nsm;
         }
         const long long nslots = (long long)sel.last - sel.first;
+        const bool pdlNow = nslots <= (long long)opt.pdl;
         const unsigned grid = (unsigned)std::min<long long>((nslots * G + VOR_COOP_BLOCK - 1) / VOR_COOP_BLOCK, (long long)occCommit * opt.persist_waves);
         const unsigned agrid = (unsigned)((((long long)sel.last - sel.first) * G + VOR_ATTEMPT_BLOCK - 1) / VOR_ATTEMPT_BLOCK);
         prof.start(0, stream);
@@ -603,13 +609,13 @@ template <int D> class Engine {
                 k_attempt_hot_tiled<D><<<(unsigned)std::min<long long>(ntiles, occTiledHot), VOR_TILE_BLOCK, (size_t)opt.smem_pad, stream>>>(aa, sel, tileNow);
             } else {
                 const unsigned hgrid = (unsigned)std::min<long long>((nslots * G + VOR_HOT_BLOCK - 1) / VOR_HOT_BLOCK, (long long)occHot * opt.persist_waves);
-                k_attempt_hot<D><<<hgrid, VOR_HOT_BLOCK, (size_t)opt.smem_pad, stream>>>(aa, sel);
+                be::launch_pdl(pdlNow, k_attempt_hot<D>, hgrid, VOR_HOT_BLOCK, (size_t)opt.smem_pad, stream, aa, sel);
             }
             if (slowNow) {
                 // the slots the hot kernel queued (points it flagged in earlier rounds); a small grid-stride launch
                 AttemptArgs<D> as = aa;
                 as.thr = 2u;
-                k_attempt_slow<D, 1><<<(unsigned)std::min<long long>(agrid, 148LL * 8), VOR_ATTEMPT_BLOCK, 0, stream>>>(as, sel);
+                be::launch_pdl(pdlNow, k_attempt_slow<D, 1>, (unsigned)std::min<long long>(agrid, 148LL * 8), VOR_ATTEMPT_BLOCK, (size_t)0, stream, as, sel);
                 be::g_launches++;
             }
         } else if (opt.red) {
@@ -626,13 +632,14 @@ template <int D> class Engine {
             k_commit_tiled<D><<<(unsigned)std::min<long long>(ntiles, occTiledCommit), VOR_TILE_BLOCK, (size_t)opt.smem_pad, stream>>>(
                 ca, act, sel, (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2), tileNow);
         } else
-            k_commit_coop<D, G><<<grid, VOR_COOP_BLOCK, (size_t)opt.smem_pad, stream>>>(ca, act, sel, (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2));
+            be::launch_pdl(pdlNow, k_commit_coop<D, G>, grid, VOR_COOP_BLOCK, (size_t)opt.smem_pad, stream, ca, (const int *)act, sel,
+                           (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2));
         prof.stop(stream);
         prof.start(1, stream);
         {
             // new simplices of the round: at most ~36 per attempted point; grid-stride over whatever the allocator handed out
             const long long want = (nslots * (D == 3 ? 36 : 9) + 255) / 256;
-            k_spheres<D><<<(unsigned)std::max(1LL, std::min(want, 148LL * 16)), 256, 0, stream>>>(mesh);
+            be::launch_pdl(pdlNow, k_spheres<D>, (unsigned)std::max(1LL, std::min(want, 148LL * 16)), 256, (size_t)0, stream, mesh);
         }
         prof.stop(stream);
         be::g_launches += 3;
