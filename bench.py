@@ -72,13 +72,20 @@ class ClockSampler:
         self.index = index
         self.rows = []
         self.proc = None
+        self.first = 0
+
+    def mark(self):
+        """The timed region starts here.  The process is started BEFORE the warm-up steps: nvidia-smi takes a few hundred ms to
+        come up (NVML initialisation holds driver locks), which used to fall into the timed region and doubled the time of
+        workloads whose whole timed region is a few tens of ms."""
+        self.first = len(self.rows)
 
     def start(self):
         if os.environ.get("VOR_NO_SAMPLER"):   # diagnostics only: a bench line without clocks is not a valid bench line
             return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -98,7 +105,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[self.first:] or self.rows[-1:]    # a timed region shorter than the 100 ms sampling period: the last sample before it
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -257,12 +265,13 @@ def run_stream(args, name, rank, world, local_rank):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1), ne, ck
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     launches0 = lib.vor_kernel_launches()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     t_ms = []
     for _ in range(args.steps):
         ms, ne, ck = step_device()
@@ -348,12 +357,13 @@ def run_slab(args, name, rank, world, local_rank):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1), res
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     launches0 = lib.vor_kernel_launches()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     t_ms = []
     for _ in range(args.steps):
         ms, res = step()
@@ -482,12 +492,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up, then K timed steps (barrier + synchronize on both sides; time = max over ranks)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     launches0 = lib.vor_kernel_launches()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     t_ms = []
     for _ in range(args.steps):
         ms, _ = step_device()
@@ -548,6 +559,8 @@ def main():
 
     # ---- end to end through the public API with host buffers (H2D + D2H inside the timed region)
     e2e = None
+    lib.vor_set_option(b"stats", 0.0)      # the instrumented steps above must not leak their counters (atomics) into the end-to-end steps
+    lib.vor_set_option(b"profile", 0.0)
     if not args.no_e2e:
         def step_e2e():
             t0 = time.perf_counter()

@@ -95,6 +95,7 @@ int vor_set_option(const char *name, double value) {
     else if (n == "tiled") g_opts.tiled = (int)value;
     else if (n == "subround") g_opts.subround = (int)value;
     else if (n == "pdl") g_opts.pdl = (int)value;
+    else if (n == "carry_frac") g_opts.carry_frac = value;
     else if (n == "capk") { g_opts.capk = (int)value; g_opts.capb = 2 * g_opts.capk + 4; }
     else if (n == "big_slots") g_opts.big_slots = (int)value;
     else if (n == "big_capk") g_opts.big_capk = (int)value;

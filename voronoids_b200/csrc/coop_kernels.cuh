@@ -366,17 +366,36 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
 #ifndef VOR_HOT_WALK
 #define VOR_HOT_WALK 48           // power-descent steps before the point goes to the exact twin
 #endif
+// Lane groups of the hot kernel: G lanes per attempted point.  A 3D flood level has (frontier x 4) items -- 4, ~12, ~24, ~30 -- and
+// a 2D one 3, 6, 6: a whole warp per point leaves most lanes idle, and what bounds the kernel is the number of attempts in
+// flight, so sub-warp groups put 2 (3D) / 4 (2D) attempts into one warp's registers.
+#ifndef VOR_HOT_G3
+#define VOR_HOT_G3 32
+#endif
+#ifndef VOR_HOT_G2
+#define VOR_HOT_G2 16
+#endif
+#ifndef VOR_SK2
+#define VOR_SK2 16                // 2D: killed simplices staged in shared memory (mean cavity: 4)
+#endif
+template <int D> struct HotCfg {
+    static constexpr int G = D == 3 ? VOR_HOT_G3 : VOR_HOT_G2;
+    static constexpr int SK = D == 3 ? VOR_SK : (VOR_HOT_G2 == 32 ? VOR_SK : VOR_SK2);
+};
 __device__ __forceinline__ double pow_mid(const OwnBlk &b, const RelPt &q) {
     const double dx = q.x - (double)b.cx, dy = q.y - (double)b.cy, dz = q.z - (double)b.cz;
     // a simplex without a filter (rout2 = inf) never attracts the walk
     return (dx * dx + dy * dy + dz * dz) - 0.5 * ((double)b.rin2 + (double)b.rout2);
 }
-template <int D>
+template <int D, int G>
 __device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const RoundSel &rsel, const int slot, int *const sk, int4 *const sn) {
     constexpr int M = Dim<D>::M;
-    constexpr int SK = VOR_SK;
+    constexpr int SK = HotCfg<D>::SK;
+    constexpr unsigned GFULL = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
     const Mesh<D> &m = A.m;
-    const int gl = threadIdx.x & 31;
+    const int gl = threadIdx.x & (G - 1);                          // lane inside the group
+    const unsigned gmask = group_mask<G>();
+    const int gshift = (threadIdx.x & 31) & ~(G - 1);              // first lane of the group inside the warp
     const int a = slot_entry(rsel, slot);
     if (a >= rsel.nact) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }
     const int v = A.act[a];
@@ -421,19 +440,19 @@ __device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const R
         int who = gl;
 #pragma unroll
         for (int d = 1; d < 4; d <<= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, d);
-            const int ow = __shfl_xor_sync(0xffffffffu, who, d);
+            const double ob = __shfl_xor_sync(gmask, best, d, G);
+            const int ow = __shfl_xor_sync(gmask, who, d, G);
             if (ob < best || (ob == best && ow < who)) { best = ob; who = ow; }
         }
-        best = __shfl_sync(0xffffffffu, best, 0);
-        who = __shfl_sync(0xffffffffu, who, 0);
+        best = __shfl_sync(gmask, best, 0, G);
+        who = __shfl_sync(gmask, who, 0, G);
         if (!(best < pw0)) { give = true; break; }          // stuck: undecidable from the filters
-        s = __shfl_sync(0xffffffffu, code, who) >> 2;
-        sb.kill = __shfl_sync(0xffffffffu, nbk.kill, who); sb.ring = __shfl_sync(0xffffffffu, nbk.ring, who);
-        sb.cx = __shfl_sync(0xffffffffu, nbk.cx, who); sb.cy = __shfl_sync(0xffffffffu, nbk.cy, who); sb.cz = __shfl_sync(0xffffffffu, nbk.cz, who);
-        sb.rin2 = __shfl_sync(0xffffffffu, nbk.rin2, who); sb.rout2 = __shfl_sync(0xffffffffu, nbk.rout2, who);
-        stn.x = __shfl_sync(0xffffffffu, nnn.x, who); stn.y = __shfl_sync(0xffffffffu, nnn.y, who);
-        stn.z = __shfl_sync(0xffffffffu, nnn.z, who); stn.w = __shfl_sync(0xffffffffu, nnn.w, who);
+        s = __shfl_sync(gmask, code, who, G) >> 2;
+        sb.kill = __shfl_sync(gmask, nbk.kill, who, G); sb.ring = __shfl_sync(gmask, nbk.ring, who, G);
+        sb.cx = __shfl_sync(gmask, nbk.cx, who, G); sb.cy = __shfl_sync(gmask, nbk.cy, who, G); sb.cz = __shfl_sync(gmask, nbk.cz, who, G);
+        sb.rin2 = __shfl_sync(gmask, nbk.rin2, who, G); sb.rout2 = __shfl_sync(gmask, nbk.rout2, who, G);
+        stn.x = __shfl_sync(gmask, nnn.x, who, G); stn.y = __shfl_sync(gmask, nnn.y, who, G);
+        stn.z = __shfl_sync(gmask, nnn.z, who, G); stn.w = __shfl_sync(gmask, nnn.w, who, G);
     }
     if (!give) {
         if (gl == 0 && steps) m.seed[v] = s;
@@ -445,13 +464,13 @@ __device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const R
         tests = gl == 0 ? 1u : 0u;
         ScrView sv = scr_view(A.scr, slot, -1);
         if (gl == 0) { sv.k[0] = s; sk[0] = s; sn[0] = stn; }
-        __syncwarp();
+        __syncwarp(gmask);
         nk = 1;
         int head = 0;
         while (head < nk && !lost && !give) {
             const int tail = nk;
             const int items = (tail - head) * M;
-            for (int base = 0; base < items; base += 32) {
+            for (int base = 0; base < items; base += G) {
                 const int j = base + gl;
                 bool pushB = false, lostLane = false, giveLane = false;
                 int fcode = 0, ocode = 0;
@@ -489,25 +508,25 @@ __device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const R
                         }
                     }
                 }
-                if (__any_sync(0xffffffffu, giveLane)) { give = true; break; }
-                if (__any_sync(0xffffffffu, lostLane)) { lost = true; break; }
-                const unsigned same = __match_any_sync(0xffffffffu, claim);
-                const bool pushK = claim >= 0 && (__ffs(same) - 1) == gl;
-                const unsigned mk = __ballot_sync(0xffffffffu, pushK);
-                const unsigned mb = __ballot_sync(0xffffffffu, pushB);
+                if (__any_sync(gmask, giveLane)) { give = true; break; }
+                if (__any_sync(gmask, lostLane)) { lost = true; break; }
+                const unsigned same = __match_any_sync(gmask, claim);
+                const bool pushK = claim >= 0 && (__ffs(same) - 1) == (int)(threadIdx.x & 31);
+                const unsigned mk = (__ballot_sync(gmask, pushK) >> gshift) & GFULL;
+                const unsigned mb = (__ballot_sync(gmask, pushB) >> gshift) & GFULL;
                 const int ck = __popc(mk), cb = __popc(mb);
                 if (nk + ck > sv.capk || nb + cb > sv.capb) {
                     // spill to an overflow slot (contiguous, much larger)
                     if (big >= 0) { if (gl == 0) set_err(m.cnt, ERR_CAPACITY); lost = true; break; }
                     if (gl == 0) big = atomicAdd(&m.cnt->nbig, 1);
-                    big = __shfl_sync(0xffffffffu, big, 0);
+                    big = __shfl_sync(gmask, big, 0, G);
                     if (big >= A.scr.nbig) { lost = true; break; }
                     const ScrView bv = scr_view(A.scr, slot, big);
-                    for (int x = gl; x < nk; x += 32) bv.k[x] = sv.k[x];
-                    for (int x = gl; x < nb; x += 32) { bv.f[x] = sv.f[x]; bv.o[x] = sv.o[x]; }
+                    for (int x = gl; x < nk; x += G) bv.k[x] = sv.k[x];
+                    for (int x = gl; x < nb; x += G) { bv.f[x] = sv.f[x]; bv.o[x] = sv.o[x]; }
                     sv = bv;
                     if (gl == 0) A.scr.slotBig[slot] = big;
-                    __syncwarp();
+                    __syncwarp(gmask);
                     if (nk + ck > sv.capk || nb + cb > sv.capb) { if (gl == 0) set_err(m.cnt, ERR_CAPACITY); lost = true; break; }
                 }
                 const unsigned lt = (1u << gl) - 1u;
@@ -519,7 +538,7 @@ __device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const R
                 if (pushB) { const int pos = nb + __popc(mb & lt); sv.f[pos] = fcode; sv.o[pos] = ocode; }
                 nk += ck;
                 nb += cb;
-                __syncwarp();
+                __syncwarp(gmask);
             }
             head = tail;
         }
@@ -537,7 +556,7 @@ __device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const R
         if (big < 0) A.scr.slotBig[slot] = -1;
     }
     if (A.stats) {
-        for (int d = 16; d > 0; d >>= 1) tests += __shfl_xor_sync(0xffffffffu, tests, d);
+        for (int d = G / 2; d > 0; d >>= 1) tests += __shfl_xor_sync(gmask, tests, d, G);
         if (gl == 0) {
             atomicAdd(&m.cnt->walk_steps, (unsigned long long)steps);
             atomicAdd(&m.cnt->tests, (unsigned long long)tests);
@@ -551,18 +570,19 @@ __device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const R
 // Resident warps with a static stride over the slots (grid = what fits on the machine, engine.cuh): a third to a half of
 // the slots of a round hold points that are already inserted or are the exact twin's; with one block per pair of slots
 // the SMs spent their time launching blocks that exit at once (ncu, round 2: 24 of 36 warps resident on average).
-template <int D>
+template <int D, int G>
 __global__ void __launch_bounds__(VOR_HOT_BLOCK, (65536 / (VOR_HOT_REGS * VOR_HOT_BLOCK)) > 32 ? 32 : (65536 / (VOR_HOT_REGS * VOR_HOT_BLOCK)))
 k_attempt_hot(AttemptArgs<D> A, RoundSel rsel) {
-    __shared__ int s_kid[VOR_HOT_BLOCK / 32][VOR_SK];
-    __shared__ int4 s_knb[VOR_HOT_BLOCK / 32][VOR_SK];
+    __shared__ int s_kid[VOR_HOT_BLOCK / G][HotCfg<D>::SK];
+    __shared__ int4 s_knb[VOR_HOT_BLOCK / G][HotCfg<D>::SK];
     pdl_trigger();
     pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0) A.m.cnt->sph_lo = A.m.cnt->ntets;   // k_spheres of the last round is done
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int slot = rsel.first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); slot < rsel.last; slot += nwarps) {
-        attempt_hot_one<D>(A, rsel, slot, s_kid[threadIdx.x >> 5], s_knb[threadIdx.x >> 5]);
-        __syncwarp();
+    const unsigned gmask = group_mask<G>();
+    const int ngroups = (gridDim.x * blockDim.x) / G;
+    for (int slot = rsel.first + (blockIdx.x * blockDim.x + threadIdx.x) / G; slot < rsel.last; slot += ngroups) {
+        attempt_hot_one<D, G>(A, rsel, slot, s_kid[threadIdx.x / G], s_knb[threadIdx.x / G]);
+        __syncwarp(gmask);
     }
 }
 
@@ -623,7 +643,7 @@ k_attempt_hot_tiled(AttemptArgs<D> A, RoundSel rsel, int tile) {
             if (gl == 0) i = atomicAdd(&s_next, 1);
             i = __shfl_sync(0xffffffffu, i, 0);
             if (i >= n) break;
-            attempt_hot_one<D>(A, rsel, s_list[i], s_kid[w], s_knb[w]);
+            attempt_hot_one<D, 32>(A, rsel, s_list[i], s_kid[w], s_knb[w]);
             __syncwarp();
         }
         __syncthreads();
@@ -749,21 +769,42 @@ constexpr int COMMIT_HS = 128;
                                   // 40 registers and 64-bit shared-memory CAS: commit 43.2 vs 40.3 ms per 10M points (11.5 vs 12.0 per 1M)
 #endif
 constexpr int RIDGE_HS = 256;     // >= 1.5 x VOR_CB ridges, power of two
+// Lane groups of the commit kernel (as for the hot kernel): a 2D cavity has ~4 killed simplices and ~6 boundary edges
+#ifndef VOR_COMMIT_G3
+#define VOR_COMMIT_G3 32
+#endif
+#ifndef VOR_COMMIT_G2
+#define VOR_COMMIT_G2 16
+#endif
+#ifndef VOR_CK2
+#define VOR_CK2 16
+#endif
+#ifndef VOR_CB2
+#define VOR_CB2 36
+#endif
+template <int D> struct CommitCfg {
+    static constexpr int G = D == 3 ? VOR_COMMIT_G3 : VOR_COMMIT_G2;
+    static constexpr bool SMALL = D == 2 && VOR_COMMIT_G2 != 32;     // sub-warp groups in 2D: staging sized for 2D cavities
+    static constexpr int CK = SMALL ? VOR_CK2 : VOR_CK;
+    static constexpr int CB = SMALL ? VOR_CB2 : VOR_CB;
+    static constexpr int HS = SMALL ? 32 : COMMIT_HS;                // id -> local index hash, at most half full
+    static constexpr int HSHIFT = SMALL ? 27 : 25;                   // 32 - log2(HS)
+};
 template <int D> struct CommitSmem {
-    int4 tv[VOR_CK];
+    int4 tv[CommitCfg<D>::CK];
 #if VOR_RIDGE_HASH
     unsigned long long rkey[RIDGE_HS];
     int rval[RIDGE_HS][2];
 #else
-    int4 tn[VOR_CK];
+    int4 tn[CommitCfg<D>::CK];
 #endif
-    int id[VOR_CK], fw[VOR_CK], hash[COMMIT_HS], f[VOR_CB], o[VOR_CB];
+    int id[CommitCfg<D>::CK], fw[CommitCfg<D>::CK], hash[CommitCfg<D>::HS], f[CommitCfg<D>::CB], o[CommitCfg<D>::CB];
 };
 template <int D, int G>
 __device__ __forceinline__ void commit_one(const CheckArgs<D> &A, const int *act, const RoundSel &rsel, int stats, const int slot, CommitSmem<D> &sm) {
     constexpr int M = Dim<D>::M;
-    constexpr int CK = VOR_CK, CB = VOR_CB, HS = COMMIT_HS;
-    static_assert(HS >= 2 * CK, "hash must stay at most half full");
+    constexpr int CK = CommitCfg<D>::CK, CB = CommitCfg<D>::CB, HS = CommitCfg<D>::HS, HSHIFT = CommitCfg<D>::HSHIFT;
+    static_assert(HS >= 2 * CK && (1 << (32 - HSHIFT)) == HS, "hash must stay at most half full");
     const Mesh<D> &m = A.m;
     const int gid = slot;
     const int gl = threadIdx.x & (G - 1);
@@ -837,12 +878,12 @@ __device__ __forceinline__ void commit_one(const CheckArgs<D> &A, const int *act
         auto slot_of = [&](int j) -> int { return base + j; };
         // id -> local index (open addressing, at most 3/8 full)
         for (int e = gl; e < nk; e += G) {
-            unsigned h = ((unsigned)ids[e] * 2654435761u) >> 25;
+            unsigned h = ((unsigned)ids[e] * 2654435761u) >> HSHIFT;
             while (atomicCAS(&hash[h], -1, e) != -1) h = (h + 1) & (HS - 1);
         }
         __syncwarp(gmask);
         auto local_of = [&](int t) -> int {
-            unsigned h = ((unsigned)t * 2654435761u) >> 25;
+            unsigned h = ((unsigned)t * 2654435761u) >> HSHIFT;
             for (int probe = 0; probe < HS; probe++) {
                 const int e = hash[h];
                 if (e < 0) break;

@@ -54,6 +54,9 @@ struct EngineOptions {
     int tiled = 0;               // round kernels as resident blocks pulling tiles of slots from a device queue (measured slower: off)
     int smem_pad = 0;            // diagnostics: extra dynamic shared memory per block of the round kernels (caps resident warps)
     int persist_waves = 1000000; // grid of the round kernels = resident blocks x this (1 = persistent warps; large = one block per slot pair)
+    double carry_frac = 0.125;   // a stage that is not the last one of its insert call stops once fewer than this fraction of its points is
+                                 // pending: the stragglers join the active list of the next stage instead of costing the stage a tail of
+                                 // nearly empty rounds at full round latency (the triangulation does not depend on the insertion order)
     double compact_frac = 0.85;  // the active list is compacted (at a host read-back) once fewer than this fraction of it is pending
     double tet_factor = 0.0;     // simplex slots per vertex (0 = default: 31 in 3D, 7.5 in 2D)
 };
@@ -68,6 +71,7 @@ inline void options_from_env(EngineOptions &o) {
     if (const char *e = getenv("VOR_VERBOSE")) o.verbose = atoi(e);
     if (const char *e = getenv("VOR_TET_FACTOR")) o.tet_factor = atof(e);
     if (const char *e = getenv("VOR_COMPACT_FRAC")) o.compact_frac = atof(e);
+    if (const char *e = getenv("VOR_CARRY_FRAC")) o.carry_frac = atof(e);
     if (const char *e = getenv("VOR_PERSIST_WAVES")) o.persist_waves = std::max(1, atoi(e));
     if (const char *e = getenv("VOR_SMEM_PAD")) o.smem_pad = atoi(e);
     if (const char *e = getenv("VOR_TILED")) o.tiled = atoi(e);
@@ -122,6 +126,8 @@ template <int D> class Engine {
     long long *d_misc = nullptr;
     long long insertedTotal = 0;
     long long remainingInCall = 0;   // points of the current insert call not inserted yet
+    int maxStageCall = 0;            // largest stage of the current insert call
+    int carried = 0;                 // pending entries at the front of `act` handed over by the previous stage (pipelined path)
     int actcap = 0;
     // key layout
     int setBits = 0, axisBits = 0;
@@ -521,9 +527,12 @@ template <int D> class Engine {
         epochMax = (1 << (30 - (bits + 1))) - 1;
         reset_owners();
         ensure_scratch(std::min(maxStage, opt.slot_cap));
-        if (maxStage > actcap) {
+        // active list: a stage plus the stragglers the stage before it handed over (at most carry_frac of that stage)
+        maxStageCall = maxStage;
+        const int actNeed = maxStage + (int)std::min<long long>((long long)(std::max(0.0, std::min(opt.carry_frac, 0.5)) * (double)maxStage) + 1024, maxStage);
+        if (actNeed > actcap) {
             be::dfree(act); be::dfree(act2); be::dfree(blockCnt);
-            actcap = maxStage;
+            actcap = actNeed;
             act = (int *)be::dmalloc(sizeof(int) * (size_t)actcap);
             act2 = (int *)be::dmalloc(sizeof(int) * (size_t)actcap);
             blockCnt = (int *)be::dmalloc(sizeof(int) * (size_t)(actcap / 256 + 2));
@@ -536,12 +545,16 @@ template <int D> class Engine {
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tins0).count());
         }
         // ---- stages
+        int lastStage = 0;
+        for (int st = 0; st < 64; st++)
+            if (stageLo[st + 1] > stageLo[st]) lastStage = st;
+        carried = 0;
         for (int st = 0; st < 64; st++) {
             const int lo = vbase + stageLo[st], hi = vbase + stageLo[st + 1];
             if (hi <= lo) continue;
             const auto t0 = std::chrono::steady_clock::now();
             const unsigned long long r0 = rs.rounds;
-            run_stage(lo, hi);
+            run_stage(lo, hi, st == lastStage);
             if (opt.verbose) {
                 be::sync(stream);
                 const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -577,13 +590,14 @@ template <int D> class Engine {
         return (long long)std::min(byRounds, byRemaining) + 4096;
     }
     template <int G> void launch_round(const AttemptArgs<D> &aa, const CheckArgs<D> &ca, const RoundSel &sel, bool slowNow) {
+        constexpr int HG = HotCfg<D>::G, CG = CommitCfg<D>::G;     // lanes per attempted point in the hot / commit kernels
         // resident warps: as many blocks as fit on the machine (occupancy queried once), each warp strides over the slots
         if (occHot < 0) {
             int dev = 0, nsm = 148, o1 = 1, o2 = 1;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_attempt_hot<D>, VOR_HOT_BLOCK, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_commit_coop<D, G>, VOR_COOP_BLOCK, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_attempt_hot<D, HG>, VOR_HOT_BLOCK, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_commit_coop<D, CG>, VOR_COOP_BLOCK, 0);
             occHot = std::max(1, o1) * nsm;
             occCommit = std::max(1, o2) * nsm;
             int o3 = 1, o4 = 1;
@@ -594,7 +608,7 @@ template <int D> class Engine {
         }
         const long long nslots = (long long)sel.last - sel.first;
         const bool pdlNow = nslots <= (long long)opt.pdl;
-        const unsigned grid = (unsigned)std::min<long long>((nslots * G + VOR_COOP_BLOCK - 1) / VOR_COOP_BLOCK, (long long)occCommit * opt.persist_waves);
+        const unsigned grid = (unsigned)std::min<long long>((nslots * CG + VOR_COOP_BLOCK - 1) / VOR_COOP_BLOCK, (long long)occCommit * opt.persist_waves);
         const unsigned agrid = (unsigned)((((long long)sel.last - sel.first) * G + VOR_ATTEMPT_BLOCK - 1) / VOR_ATTEMPT_BLOCK);
         prof.start(0, stream);
         if (opt.red && aa.slowFlag) {
@@ -608,8 +622,8 @@ template <int D> class Engine {
                 const long long ntiles = ((long long)sel.nsel + tileNow - 1) / tileNow;
                 k_attempt_hot_tiled<D><<<(unsigned)std::min<long long>(ntiles, occTiledHot), VOR_TILE_BLOCK, (size_t)opt.smem_pad, stream>>>(aa, sel, tileNow);
             } else {
-                const unsigned hgrid = (unsigned)std::min<long long>((nslots * G + VOR_HOT_BLOCK - 1) / VOR_HOT_BLOCK, (long long)occHot * opt.persist_waves);
-                be::launch_pdl(pdlNow, k_attempt_hot<D>, hgrid, VOR_HOT_BLOCK, (size_t)opt.smem_pad, stream, aa, sel);
+                const unsigned hgrid = (unsigned)std::min<long long>((nslots * HG + VOR_HOT_BLOCK - 1) / VOR_HOT_BLOCK, (long long)occHot * opt.persist_waves);
+                be::launch_pdl(pdlNow, k_attempt_hot<D, HG>, hgrid, VOR_HOT_BLOCK, (size_t)opt.smem_pad, stream, aa, sel);
             }
             if (slowNow) {
                 // the slots the hot kernel queued (points it flagged in earlier rounds); a small grid-stride launch
@@ -632,7 +646,7 @@ template <int D> class Engine {
             k_commit_tiled<D><<<(unsigned)std::min<long long>(ntiles, occTiledCommit), VOR_TILE_BLOCK, (size_t)opt.smem_pad, stream>>>(
                 ca, act, sel, (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2), tileNow);
         } else
-            be::launch_pdl(pdlNow, k_commit_coop<D, G>, grid, VOR_COOP_BLOCK, (size_t)opt.smem_pad, stream, ca, (const int *)act, sel,
+            be::launch_pdl(pdlNow, k_commit_coop<D, CG>, grid, VOR_COOP_BLOCK, (size_t)opt.smem_pad, stream, ca, (const int *)act, sel,
                            (opt.stats ? 1 : 0) | (opt.commit_smem ? 0 : 2));
         prof.stop(stream);
         prof.start(1, stream);
@@ -645,24 +659,29 @@ template <int D> class Engine {
         be::g_launches += 3;
         be::check_launch("round kernels");
     }
-    void run_stage_pipelined(int lo, int hi) {
-        const int total = hi - lo;
+    void run_stage_pipelined(int lo, int hi, bool last) {
+        // the active list: the stragglers of the stage before (already at the front of `act`, with seeds), then this stage's points
+        const int fresh = hi - lo;
+        const int total = carried + fresh;
         int nact = total, pending = total;
+        // a stage that is not the last one hands its last few pending points over to the next stage
+        const int carryLimit = last ? 0 : std::min((int)(std::max(0.0, std::min(opt.carry_frac, 0.5)) * (double)fresh), actcap - maxStageCall);
         SeedArgs<D> sd{keysAll, mesh.pts, mesh.ptTet, mesh.owner, mesh.seed, nsuper, lo, refLo, refHi, D * axisBits};
-        VOR_LAUNCH(SeedArgs<D>, init_seeds_body<D>, nact, sd, stream);
+        VOR_LAUNCH(SeedArgs<D>, init_seeds_body<D>, fresh, sd, stream);
         if (opt.bulk_locate) {
             LocateArgs<D> la{mesh, lo, opt.stats};
-            VOR_LAUNCH(LocateArgs<D>, locate_body<D>, nact, la, stream);
+            VOR_LAUNCH(LocateArgs<D>, locate_body<D>, fresh, la, stream);
         }
-        IotaArgs ia{act, lo};
-        VOR_LAUNCH(IotaArgs, iota_body, nact, ia, stream);
+        IotaArgs ia{act + carried, lo};
+        VOR_LAUNCH(IotaArgs, iota_body, fresh, ia, stream);
+        carried = 0;
         pull_counters();
         const unsigned long long win0 = win_total();
         const int dup0 = hcnt->ndup;
         int stall = 0;
         uint32_t roundSalt = (uint32_t)mix64((uint64_t)lo * 0x9E37u + rs.rounds);
         const double newPerPoint = D == 3 ? 36.0 : 9.0;   // allocator margin per attempted point (mean is 27 / 6)
-        while (pending > 0) {
+        while (pending > std::max(0, carryLimit)) {
             const int R = opt.verbose > 2 ? 1 : std::max(1, opt.rounds_per_sync);
             // attempt about max(min_attempt, inserted/attempt_div) of the pending points per round, one per run of
             // `stride` consecutive entries of the active list (which also holds the entries inserted since the last
@@ -743,16 +762,24 @@ template <int D> class Engine {
                 if (nact != pending) fail(ERR_CUDA, "active list compaction lost points");
             }
         }
+        if (pending > 0) {
+            // hand the stragglers over: they keep their seeds and lead the active list of the next stage
+            nact = compact_active(nact);
+            if (nact != pending) fail(ERR_CUDA, "active list compaction lost points");
+            carried = nact;
+        }
         rs.attempts = hcnt->attempts;
         rs.winners = win_total();
         if (opt.verbose)
-            fprintf(stderr, "[vor] stage [%d,%d) done: rounds so far %llu, simplices %d\n", lo, hi, rs.rounds, hcnt->ntets);
+            fprintf(stderr, "[vor] stage [%d,%d) done: rounds so far %llu, simplices %d, %d point(s) handed to the next stage\n", lo, hi, rs.rounds,
+                    hcnt->ntets, carried);
     }
 #endif
 
-    void run_stage(int lo, int hi) {
+    void run_stage(int lo, int hi, bool last) {
+        (void)last;
 #if VOR_GPU
-        if (opt.coop) { run_stage_pipelined(lo, hi); return; }
+        if (opt.coop) { run_stage_pipelined(lo, hi, last); return; }
 #endif
         int nact = hi - lo;
         int pending = nact;

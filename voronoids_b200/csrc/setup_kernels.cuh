@@ -188,6 +188,14 @@ template <int D> VOR_HD void init_seeds_body(const SeedArgs<D> &A, int j) {
             const double d = dist2(A.pts[c], p);
             if (d < bestd) { bestd = d; best = c; }
         }
+        // every candidate pending (a duplicate, or a straggler the reference stage handed over): look further along the curve
+        for (int r = 3; best < 0 && r <= 18; r++)
+            for (int side = 0; side < 2 && best < 0; side++) {
+                const int c = side ? lo + r - 1 : lo - r;
+                if (c < A.plo || c >= A.phi) continue;
+                if ((int)((A.keysAll[c - A.nsuper] & mask) >> A.setShift) != set) continue;
+                if (A.ptTet[c] >= 0) best = c;
+            }
         if (best >= 0) seed = A.ptTet[best];
     }
     int o;
