@@ -6,6 +6,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <map>
@@ -195,10 +196,18 @@ inline Staging &staging_here() {
 }
 // host memcpy on a few threads: the destination of a result copy is usually freshly allocated memory, so the copy is
 // dominated by first-touch page faults, which scale with threads
+inline int copy_threads() {
+    static const int T = [] {
+        int t = (int)std::thread::hardware_concurrency() / 2;
+        if (const char *e = getenv("VOR_COPY_THREADS")) t = atoi(e);
+        return std::max(1, std::min(t, 16));
+    }();
+    return T;
+}
 inline void par_memcpy(char *dst, const char *src, size_t n) {
-    const int T = 4;
-    if (n < ((size_t)4 << 20)) { memcpy(dst, src, n); return; }
-    std::thread th[T - 1];
+    const int T = copy_threads();
+    if (T == 1 || n < ((size_t)4 << 20)) { memcpy(dst, src, n); return; }
+    std::thread th[16];
     const size_t part = (n / T + 4095) & ~(size_t)4095;
     for (int i = 1; i < T; i++) {
         const size_t off = std::min(n, part * i), len = std::min(n - off, part);

@@ -38,6 +38,11 @@ template <int G> __device__ __forceinline__ unsigned group_mask() {
 // kernel and no compaction of the selected set are needed.  A round is two launches: attempt, commit.
 struct RoundSel { int nact; int stride; int offset; int nsel; int first; int last; };   // this launch works on slots [first, last) of the round's nsel
 __device__ __forceinline__ int slot_entry(const RoundSel &rs, int slot) { return slot * rs.stride + rs.offset; }
+// per-slot result word of an attempt (Scratch::slotInfo); a slot without a complete cavity only needs its status
+__device__ __forceinline__ void slot_lost(const Scratch &scr, int slot) { reinterpret_cast<int *>(scr.slotInfo + slot)[0] = ST_LOST; }
+__device__ __forceinline__ int4 slot_pack(int status, bool flagged, int big, int nk, int nb, int v) {
+    return make_int4(status | (flagged ? 4 : 0) | ((big + 1) << 3), nk, nb, v);
+}
 
 template <int D> struct GeoCoop;
 template <> struct GeoCoop<3> {
@@ -124,16 +129,18 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
     if (gid >= rsel.nsel) return;
     const int slot = gid;
     const int a = slot_entry(rsel, slot);
-    if (a >= rsel.nact) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }
+    if (a >= rsel.nact) { if (gl == 0) slot_lost(A.scr, slot); return; }
     const int v = A.act[a];
     int s = m.seed[v];
-    if (s < 0) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }   // already inserted
+    if (s < 0) { if (gl == 0) slot_lost(A.scr, slot); return; }   // already inserted
+    bool flagged = false;                                          // a point the hot twin handed over (commit counts it as done)
     if (A.slowFlag) {
         const int fl = A.slowFlag[v];
+        flagged = fl != 0;
         if (EXACT ? (A.thr == 2u && (fl == 0 || fl == A.keybase)) : fl != 0) {
             // not this twin's point.  The hot twin runs first and owns the slot's status; the slow twin leaves the
             // status of the points it skips alone
-            if (!EXACT && gl == 0) A.scr.slotStatus[slot] = ST_LOST;
+            if (!EXACT && gl == 0) slot_lost(A.scr, slot);
             return;
         }
     }
@@ -293,7 +300,6 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
                     for (int x = gl; x < nk; x += G) bv.k[x] = sv.k[x];
                     for (int x = gl; x < nb; x += G) { bv.f[x] = sv.f[x]; bv.o[x] = sv.o[x]; }
                     sv = bv;
-                    if (gl == 0) A.scr.slotBig[slot] = big;
                     __syncwarp(gmask);
                     if (nk + ck > sv.capk || nb + cb > sv.capb) { if (gl == 0) set_err(m.cnt, ERR_CAPACITY); lost = true; break; }
                 }
@@ -321,12 +327,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
             status = ST_LOST;
         }
     }
-    if (gl == 0) {
-        A.scr.slotStatus[slot] = status;
-        A.scr.slotNk[slot] = nk;
-        A.scr.slotNb[slot] = nb;
-        if (big < 0) A.scr.slotBig[slot] = -1;
-    }
+    if (gl == 0) A.scr.slotInfo[slot] = slot_pack(status, flagged, big, nk, nb, v);
     if (A.stats) {
         // every lane counted its own tests
         for (int d = G / 2; d > 0; d >>= 1) tests += __shfl_xor_sync(gmask, tests, d);
@@ -397,15 +398,15 @@ __device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const R
     const unsigned gmask = group_mask<G>();
     const int gshift = (threadIdx.x & 31) & ~(G - 1);              // first lane of the group inside the warp
     const int a = slot_entry(rsel, slot);
-    if (a >= rsel.nact) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }
+    if (a >= rsel.nact) { if (gl == 0) slot_lost(A.scr, slot); return; }
     const int v = A.act[a];
     int s = m.seed[v];
-    if (s < 0) { if (gl == 0) A.scr.slotStatus[slot] = ST_LOST; return; }   // already inserted
+    if (s < 0) { if (gl == 0) slot_lost(A.scr, slot); return; }   // already inserted
     const int fl = A.slowFlag[v];
     if (fl != 0) {
         // the exact twin's point: queue its slot for this round unless the flag is of this very round
         if (gl == 0) {
-            A.scr.slotStatus[slot] = ST_LOST;
+            slot_lost(A.scr, slot);
             if (fl != A.keybase) A.scr.slowSlots[atomicAdd(&m.cnt->nslow, 1)] = slot;
         }
         return;
@@ -525,7 +526,6 @@ __device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const R
                     for (int x = gl; x < nk; x += G) bv.k[x] = sv.k[x];
                     for (int x = gl; x < nb; x += G) { bv.f[x] = sv.f[x]; bv.o[x] = sv.o[x]; }
                     sv = bv;
-                    if (gl == 0) A.scr.slotBig[slot] = big;
                     __syncwarp(gmask);
                     if (nk + ck > sv.capk || nb + cb > sv.capb) { if (gl == 0) set_err(m.cnt, ERR_CAPACITY); lost = true; break; }
                 }
@@ -550,10 +550,7 @@ __device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const R
             A.slowFlag[v] = A.keybase;
             atomicAdd(&m.cnt->nflag_set, 1);
         }
-        A.scr.slotStatus[slot] = status;
-        A.scr.slotNk[slot] = nk;
-        A.scr.slotNb[slot] = nb;
-        if (big < 0) A.scr.slotBig[slot] = -1;
+        A.scr.slotInfo[slot] = slot_pack(status, false, big, nk, nb, v);
     }
     if (A.stats) {
         for (int d = G / 2; d > 0; d >>= 1) tests += __shfl_xor_sync(gmask, tests, d, G);
@@ -633,7 +630,7 @@ k_attempt_hot_tiled(AttemptArgs<D> A, RoundSel rsel, int tile) {
                     }
                 }
                 if (live) s_list[atomicAdd(&s_n, 1)] = slot;
-                else A.scr.slotStatus[slot] = ST_LOST;
+                else slot_lost(A.scr, slot);
             }
         }
         __syncthreads();
@@ -810,13 +807,13 @@ __device__ __forceinline__ void commit_one(const CheckArgs<D> &A, const int *act
     const int gl = threadIdx.x & (G - 1);
     const unsigned gmask = group_mask<G>();
     const int gshift = (threadIdx.x & 31) & ~(G - 1);
-    if (A.scr.slotStatus[slot] != ST_OK) return;
-    const int a = slot_entry(rsel, slot);
-    const int v = act[a];
+    const int4 info = A.scr.slotInfo[slot];                        // status, cavity sizes, overflow slot and vertex in one load
+    if ((info.x & 3) != ST_OK) return;
+    const int v = info.w;
     const uint32_t q = bij_hash((uint32_t)slot, A.bits, A.salt);   // unique among the slots of this round
     const int key_k = A.keybase | (int)(q << 1);
-    const ScrView sv = scr_view(A.scr, slot, A.scr.slotBig[slot]);
-    const int nk = A.scr.slotNk[slot], nb = A.scr.slotNb[slot];
+    const ScrView sv = scr_view(A.scr, slot, (info.x >> 3) - 1);
+    const int nk = info.y, nb = info.z;
     const bool fast = !(stats & 2) && nk <= CK && nb <= CB;   // stats bit 1: force the global-store path (A/B switch)
     int4 *const tvs = sm.tv;
     int *const ids = sm.id, *const fw = sm.fw, *const hash = sm.hash, *const sf = sm.f, *const so = sm.o;
@@ -1050,7 +1047,7 @@ __device__ __forceinline__ void commit_one(const CheckArgs<D> &A, const int *act
         m.ptTet[v] = first;
         m.seed[v] = -1;
         atomicAdd(&m.cnt->part[gid & (NPART - 1)][0], (1ULL << 40) | (unsigned long long)nb);   // win_total, created_all
-        if (A.slowFlag && A.slowFlag[v] != 0) atomicAdd(&m.cnt->nflag_done, 1);
+        if (info.x & 4) atomicAdd(&m.cnt->nflag_done, 1);     // a point of the exact twin is done
         if (stats & 1) {
             atomicAdd(&m.cnt->killed, (unsigned long long)nk);
             atomicAdd(&m.cnt->created, (unsigned long long)nb);
@@ -1090,7 +1087,7 @@ __global__ void __launch_bounds__(VOR_TILE_BLOCK) k_commit_tiled(CheckArgs<D> A,
         if (t >= ntiles) break;
         if ((int)threadIdx.x < tile) {
             const int slot = t * tile + (int)threadIdx.x;
-            if (slot < rsel.nsel && A.scr.slotStatus[slot] == ST_OK) s_list[atomicAdd(&s_n, 1)] = slot;
+            if (slot < rsel.nsel && (reinterpret_cast<const int *>(A.scr.slotInfo + slot)[0] & 3) == ST_OK) s_list[atomicAdd(&s_n, 1)] = slot;
         }
         __syncthreads();
         const int n = s_n;

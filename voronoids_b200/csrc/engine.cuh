@@ -220,7 +220,7 @@ template <int D> class Engine {
     void free_scratch() {
         be::dfree(scr.killed); be::dfree(scr.bfacet); be::dfree(scr.bouter); be::dfree(scr.slotAct); be::dfree(scr.slotNk);
         be::dfree(scr.slotNb); be::dfree(scr.slotStatus); be::dfree(scr.slotBig); be::dfree(scr.bigK); be::dfree(scr.bigF);
-        be::dfree(scr.bigO); be::dfree(scr.winners); be::dfree(scr.wbase); be::dfree(scr.slowSlots);
+        be::dfree(scr.bigO); be::dfree(scr.winners); be::dfree(scr.wbase); be::dfree(scr.slowSlots); be::dfree(scr.slotInfo);
         scr = Scratch{};
     }
     void ensure_scratch(int nslots) {
@@ -240,6 +240,7 @@ template <int D> class Engine {
         scr.winners = (int *)be::dmalloc(sizeof(int) * (size_t)nslots);
         scr.wbase = (int *)be::dmalloc(sizeof(int) * (size_t)nslots);
         scr.slowSlots = (int *)be::dmalloc(sizeof(int) * (size_t)nslots);
+        scr.slotInfo = (int4 *)be::dmalloc(sizeof(int4) * (size_t)nslots);
         scr.nbig = opt.big_slots;
         scr.bigCapK = opt.big_capk;
         scr.bigCapB = 2 * opt.big_capk + 4;

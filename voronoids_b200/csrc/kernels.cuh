@@ -151,6 +151,8 @@ struct Scratch {
     int nbig, bigCapK, bigCapB;
     int *winners, *wbase;
     int *slowSlots;                    // slots queued for the exact twin of the attempt kernel this round (coop_kernels.cuh)
+    int4 *slotInfo;                    // cooperative kernels: {status | flagged << 2 | (overflow slot + 1) << 3, nk, nb, vertex} of a slot in ONE
+                                       // 16 B word: the commit kernel starts from one load instead of five over three dependent levels
 };
 
 enum : int { ST_LOST = 0, ST_OK = 1 };
