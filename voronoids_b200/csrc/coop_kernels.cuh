@@ -996,6 +996,17 @@ __device__ __forceinline__ void commit_one(const CheckArgs<D> &A, const int *act
             sf[j] = e * 4 + i;
         }
         __syncwarp(gmask);
+        // every facet of the staged cavity is now a marker (boundary) or leads to another killed simplex: translate those
+        // neighbour codes to LOCAL indices once, all lanes in parallel, so that the pivots below are plain shared-memory
+        // index chasing without a hash probe per step
+        for (int idx = gl; idx < nk * 4; idx += G) {
+            const int code = tni[idx];
+            if (code >= 0) {
+                const int ln = local_of(code >> 2);
+                tni[idx] = ln < 0 ? -1 : ln * 4 + (code & 3);       // -1: inconsistent mesh (error already set)
+            }
+        }
+        __syncwarp(gmask);
         // phase B: one lane per new simplex: vertices, outer neighbour, and the M-1 siblings found by pivoting around
         // each ridge through the staged cavity
         for (int j = gl; j < nb; j += G) {
@@ -1022,8 +1033,8 @@ __device__ __forceinline__ void commit_one(const CheckArgs<D> &A, const int *act
                     const int code = tni[cur * 4 + exitf];
                     if (code <= -2) { set4(nbr, k, slot_of(-code - 2) * 4 + enter); break; }
                     if (guard >= 4 * CK) { set_err(m.cnt, ERR_CUDA); break; }
-                    const int ln = local_of(code >> 2), jb = code & 3;
-                    if (ln < 0) break;
+                    if (code < 0) break;
+                    const int ln = code >> 2, jb = code & 3;
                     const int4 cv = tvs[ln];
                     int y = -1;
 #pragma unroll
