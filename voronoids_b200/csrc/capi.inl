@@ -89,6 +89,7 @@ int vor_set_option(const char *name, double value) {
     else if (n == "red") g_opts.red = (int)value;
     else if (n == "commit_smem") g_opts.commit_smem = (int)value;
     else if (n == "split_exact") g_opts.split_exact = (int)value;
+    else if (n == "mid_twin") g_opts.mid_twin = (int)value;
     else if (n == "tet_factor") g_opts.tet_factor = value;
     else if (n == "compact_frac") g_opts.compact_frac = value;
     else if (n == "stage_log") g_opts.stage_log = (int)value;

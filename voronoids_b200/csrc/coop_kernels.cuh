@@ -258,7 +258,7 @@ __device__ __forceinline__ void attempt_one(const AttemptArgs<D> &A, const Round
                             tests++;
                             int conf = sphere_test(blk, rq);
                             if (conf == 0) {
-                                atomicAdd(&m.cnt->sph_undecided, 1ULL);
+                                if (A.stats) atomicAdd(&m.cnt->sph_undecided, 1ULL);   // one address: only when counters are asked for
                                 conf = conflict_slow<D, (EXACT != 0)>(m.pts, m.tet, m.cnt, n, p.x, p.y, pt_z<D>(p));
                                 if (conf == 2) { cx.failed = true; conf = 0; }
                             }
@@ -388,7 +388,22 @@ __device__ __forceinline__ double pow_mid(const OwnBlk &b, const RelPt &q) {
     // a simplex without a filter (rout2 = inf) never attracts the walk
     return (dx * dx + dy * dy + dz * dz) - 0.5 * ((double)b.rin2 + (double)b.rout2);
 }
-template <int D, int G>
+// Middle stage of the hot kernel's conflict test, for the tests the cached sphere leaves undecided (~1e-5 of them on uniform
+// input, a third on the jittered lattice): the determinant test with the FP64 static filter, WITHOUT the exact arithmetic
+// (conflict_slow<D, false>, out of line: the hot loop pays no registers for it; the point is re-read, it is not kept in registers).
+// +1 in conflict, -1 not, 0 = the FP64 filter failed too (the exact twin's business).
+// MID is a template parameter of the hot kernel: the call site costs the determinant-free kernel its spill-free register
+// allocation (144 B of stack, attempt 51.4 -> 58.2 ms per 10M uniform points), so the engine starts with MID = 0 and switches to the
+// MID = 1 twin only for input that keeps leaving the sphere filter (jittered lattice: attempt 82 -> 69 ms per 5M points).
+template <int D, int MID> __device__ __forceinline__ int hot_mid_test(const Mesh<D> &m, int n, int v, int stats) {
+    if constexpr (MID != 0) {
+    const typename Dim<D>::Pt pp = m.pts[v];
+    if (stats) atomicAdd(&m.cnt->sph_undecided, 1ULL);   // one address: only when counters are asked for
+    const int c = conflict_slow<D, false>(m.pts, m.tet, m.cnt, n, pp.x, pp.y, pt_z<D>(pp));
+    return c == 2 ? 0 : (c ? 1 : -1);
+    } else return 0;
+}
+template <int D, int G, int MID>
 __device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const RoundSel &rsel, const int slot, int *const sk, int4 *const sn) {
     constexpr int M = Dim<D>::M;
     constexpr int SK = HotCfg<D>::SK;
@@ -424,7 +439,16 @@ __device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const R
     OwnBlk sb = load_blk(m, s);
     int4 stn = load_nbr(m.tet, s);
     while (sb.kill < 0) { s = ~sb.kill; sb = load_blk(m, s); stn = load_nbr(m.tet, s); }
-    while (sphere_test(sb, rq) <= 0) {
+    for (;;) {
+        const int st = sphere_test(sb, rq);
+        if (st > 0) break;
+        if (MID != 0 && st == 0) {
+            // p inside the shell of this simplex's filter (near-cospherical input: a third of all tests on the jittered lattice):
+            // the FP64 determinant filter decides whether the flood may start here; the walk goes on if it says "outside"
+            const int c = hot_mid_test<D, MID>(m, s, v, 0);
+            if (c > 0) break;
+            if (c == 0) { give = true; break; }
+        }
         if (++steps > VOR_HOT_WALK) { give = true; break; }
         const double pw0 = pow_mid(sb, rq);
         double pw = INFINITY;
@@ -497,7 +521,8 @@ __device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const R
                             pushB = true; fcode = t * 4 + i; ocode = code;   // already tested by me: not in conflict
                         } else {
                             tests++;
-                            const int conf = sphere_test(blk, rq);
+                            int conf = sphere_test(blk, rq);
+                            if (conf == 0) conf = hot_mid_test<D, MID>(m, n, v, A.stats);   // inside the filter's shell: FP64 determinant filter (out of line)
                             if (conf > 0) {
                                 if (!VOR_SPEC) nnb = load_nbr(m.tet, n);
                                 if (blk.ring < key_k) lostLane = true;   // a better point keeps n in its outer ring
@@ -505,7 +530,7 @@ __device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const R
                             } else if (conf < 0) {
                                 atomicMin(&OWR(m, n), key_o);            // outer-ring mark: fire and forget
                                 pushB = true; fcode = t * 4 + i; ocode = code;
-                            } else giveLane = true;                      // inside the filter's shell: the exact twin decides
+                            } else giveLane = true;                      // the FP64 filter fails too: the exact twin decides
                         }
                     }
                 }
@@ -567,8 +592,15 @@ __device__ __forceinline__ void attempt_hot_one(const AttemptArgs<D> &A, const R
 // Resident warps with a static stride over the slots (grid = what fits on the machine, engine.cuh): a third to a half of
 // the slots of a round hold points that are already inserted or are the exact twin's; with one block per pair of slots
 // the SMs spent their time launching blocks that exit at once (ncu, round 2: 24 of 36 warps resident on average).
-template <int D, int G>
-__global__ void __launch_bounds__(VOR_HOT_BLOCK, (65536 / (VOR_HOT_REGS * VOR_HOT_BLOCK)) > 32 ? 32 : (65536 / (VOR_HOT_REGS * VOR_HOT_BLOCK)))
+#ifndef VOR_MID_REGS
+#define VOR_MID_REGS 56           // register budget of the MID = 1 twin
+#endif
+template <int MID> struct HotLaunch {
+    static constexpr int regs = MID ? VOR_MID_REGS : VOR_HOT_REGS;
+    static constexpr int minBlocks = (65536 / (regs * VOR_HOT_BLOCK)) > 32 ? 32 : (65536 / (regs * VOR_HOT_BLOCK));
+};
+template <int D, int G, int MID>
+__global__ void __launch_bounds__(VOR_HOT_BLOCK, HotLaunch<MID>::minBlocks)
 k_attempt_hot(AttemptArgs<D> A, RoundSel rsel) {
     __shared__ int s_kid[VOR_HOT_BLOCK / G][HotCfg<D>::SK];
     __shared__ int4 s_knb[VOR_HOT_BLOCK / G][HotCfg<D>::SK];
@@ -578,7 +610,7 @@ k_attempt_hot(AttemptArgs<D> A, RoundSel rsel) {
     const unsigned gmask = group_mask<G>();
     const int ngroups = (gridDim.x * blockDim.x) / G;
     for (int slot = rsel.first + (blockIdx.x * blockDim.x + threadIdx.x) / G; slot < rsel.last; slot += ngroups) {
-        attempt_hot_one<D, G>(A, rsel, slot, s_kid[threadIdx.x / G], s_knb[threadIdx.x / G]);
+        attempt_hot_one<D, G, MID>(A, rsel, slot, s_kid[threadIdx.x / G], s_knb[threadIdx.x / G]);
         __syncwarp(gmask);
     }
 }
@@ -640,7 +672,7 @@ k_attempt_hot_tiled(AttemptArgs<D> A, RoundSel rsel, int tile) {
             if (gl == 0) i = atomicAdd(&s_next, 1);
             i = __shfl_sync(0xffffffffu, i, 0);
             if (i >= n) break;
-            attempt_hot_one<D, 32>(A, rsel, s_list[i], s_kid[w], s_knb[w]);
+            attempt_hot_one<D, 32, 0>(A, rsel, s_list[i], s_kid[w], s_knb[w]);
             __syncwarp();
         }
         __syncthreads();

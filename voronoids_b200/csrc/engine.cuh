@@ -43,6 +43,7 @@ struct EngineOptions {
     int select_mode = 1;         // 1 = stratified selection along the Morton-ordered active list, 0 = random subset
     int rounds_per_sync = 8;     // rounds launched back to back between two host read-backs of the counters
     int commit_smem = 1;         // commit retriangulates cavities staged in shared memory (0 = through the global store)
+    int mid_twin = 1;            // allow the switch to the hot kernel's twin with the FP64 determinant stage (see run_stage_pipelined)
     int split_exact = 1;         // attempt kernel as a hot twin without exact predicates + an exact twin for the points it flags
     int red = 1;                 // kill reservation as a fire-and-forget reduction (match.any dedup), see k_attempt_coop
     int pdl = 131072;            // rounds of at most this many slots launch their kernels with programmatic dependent launch (the next
@@ -84,6 +85,7 @@ inline void options_from_env(EngineOptions &o) {
     if (const char *e = getenv("VOR_RED")) o.red = atoi(e);
     if (const char *e = getenv("VOR_COMMIT_SMEM")) o.commit_smem = atoi(e);
     if (const char *e = getenv("VOR_SPLIT_EXACT")) o.split_exact = atoi(e);
+    if (const char *e = getenv("VOR_MID_TWIN")) o.mid_twin = atoi(e);
     if (const char *e = getenv("VOR_CAPK")) { o.capk = atoi(e); o.capb = 2 * o.capk + 4; }
 }
 
@@ -118,7 +120,7 @@ template <int D> class Engine {
     Counters *hcnt = nullptr; // pinned host mirror
     // scratch
     Scratch scr{};
-    bool slowPending = false, splitDisabled = false;
+    bool slowPending = false, splitDisabled = false, midTwin = false;
     int flagPending = 0;
     int occHot = -1, occCommit = -1, occTiledHot = 1, occTiledCommit = 1;   // resident blocks of the round kernels on this device
     int tileNow = 4;
@@ -597,7 +599,7 @@ template <int D> class Engine {
             int dev = 0, nsm = 148, o1 = 1, o2 = 1;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_attempt_hot<D, HG>, VOR_HOT_BLOCK, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_attempt_hot<D, HG, 0>, VOR_HOT_BLOCK, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_commit_coop<D, CG>, VOR_COOP_BLOCK, 0);
             occHot = std::max(1, o1) * nsm;
             occCommit = std::max(1, o2) * nsm;
@@ -624,7 +626,9 @@ template <int D> class Engine {
                 k_attempt_hot_tiled<D><<<(unsigned)std::min<long long>(ntiles, occTiledHot), VOR_TILE_BLOCK, (size_t)opt.smem_pad, stream>>>(aa, sel, tileNow);
             } else {
                 const unsigned hgrid = (unsigned)std::min<long long>((nslots * HG + VOR_HOT_BLOCK - 1) / VOR_HOT_BLOCK, (long long)occHot * opt.persist_waves);
-                be::launch_pdl(pdlNow, k_attempt_hot<D, HG>, hgrid, VOR_HOT_BLOCK, (size_t)opt.smem_pad, stream, aa, sel);
+                // the twin with the FP64 determinant stage inside for input that keeps leaving the sphere filter (midTwin, decided at a read-back)
+                if (midTwin) be::launch_pdl(pdlNow, k_attempt_hot<D, HG, 1>, hgrid, VOR_HOT_BLOCK, (size_t)opt.smem_pad, stream, aa, sel);
+                else be::launch_pdl(pdlNow, k_attempt_hot<D, HG, 0>, hgrid, VOR_HOT_BLOCK, (size_t)opt.smem_pad, stream, aa, sel);
             }
             if (slowNow) {
                 // the slots the hot kernel queued (points it flagged in earlier rounds); a small grid-stride launch
@@ -729,6 +733,9 @@ template <int D> class Engine {
             // an input that keeps leaving the filters (near-degenerate: the jittered lattice) is better off with the one
             // kernel that has the exact path inside
             if ((long long)hcnt->nflag_set > 512 + insertedTotal / 32) splitDisabled = true;
+            // ... and one that leaves the SPHERE filter more often than uniform input does (~6e-4 of the points) first gets the hot
+            // kernel's twin with the FP64 determinant stage inside
+            if (opt.mid_twin && (long long)hcnt->nflag_set > 256 + insertedTotal / 256) midTwin = true;
             const long long done = (long long)(win_total() - win0) + (long long)(hcnt->ndup - dup0);
             const int newPending = total - (int)done;
             insertedTotal += (long long)(pending - newPending);
