@@ -278,6 +278,8 @@ def run_stream(args, name, rank, world, local_rank):
         ms, ne, ck = step_device()
         t_ms.append(ms)
     barrier()
+    if os.environ.get("VOR_BENCH_VERBOSE"):
+        print("step ms:", ["%.2f" % x for x in t_ms], file=sys.stderr)
     clocks = sampler.stop()
     launches = (lib.vor_kernel_launches() - launches0) // max(args.steps, 1)
     tot = torch.tensor([sum(t_ms)], dtype=torch.float64, device="cuda")

@@ -1,17 +1,16 @@
 // dd_stage.cuh -- double-double re-evaluation of the predicates, tried at the head of the exact functions
-// (exact_int.cuh).  OFF in the product build (VOR_DD=0): measured on the B200, it takes the attempt kernel of the
-// jittered-lattice workload (0.02 % of the in-sphere tests leave the FP64 filter; each exact call is ~30 us on one lane
-// and a round cannot end before its slowest warp) from 81.7 to 56.7 ms per 5M points, but the mere presence of the
-// code in the kernel's call tree changes ptxas' register allocation of the hot loop and costs the uniform 10M-point
-// run 7-8 % (95 -> 102-104 ms), whether the stage is called from the predicate's cold branch, from one out-of-line
-// "cold" wrapper, or from inside the exact function.  Build with -DVOR_DD=1 for near-degenerate inputs
-// (tools/build_variant.sh dd -DVOR_DD=1; load with VOR_SO=...).  tests/emu compiles it in, so the CPU suite keeps its
-// logic under test (predicates against fractions.Fraction, engine parity).
+// (exact_int.cuh).  ON in the product build since the hot attempt kernel has no predicate code in its call tree (round 2):
+// on the jittered-lattice workload 0.02 % of the in-sphere tests leave the FP64 filter, each exact call is ~30 us on one lane
+// and a kernel cannot end before its slowest warp; the stage takes the attempt kernels of that workload from 68.8 to 52.7 ms
+// per 5M points (117 -> 88 ms in all) and leaves the uniform run alone (50.9 vs 51.3 ms, tools/r2_exp31.sh).  In round 1, with
+// ONE attempt kernel that had the predicates inside, the mere presence of this code changed ptxas' register allocation of the
+// hot loop and cost the uniform 10M-point run 7-8 %, wherever it was called from -- it was off then (-DVOR_DD=0 still builds
+// without it).  tests/emu compiles it in as well: predicates against fractions.Fraction, engine parity.
 #pragma once
 #include "vor_common.cuh"
 
 #ifndef VOR_DD
-#define VOR_DD 0
+#define VOR_DD 1
 #endif
 
 namespace vor {
