@@ -538,13 +538,13 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     t_attempt = sd["profile_ms"]["attempt"] * 1e-3
     achieved = (n * b_attempt / t_attempt / 1e9) if t_attempt > 0 else None
-    # DRAM traffic of the kernel from the committed ncu --set full capture of one full-size round (bytes per attempt
-    # slot of that launch), scaled to the average launch of this run
+    # DRAM traffic of the kernel from the committed ncu --set full capture of the largest round (every slot of that launch holds a
+    # live attempt: bytes per ATTEMPT), scaled to the attempts of the average launch of this run
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "attempt_traffic.json")))
         if tr.get("dim") == dim:
-            traffic = tr["dram_bytes_per_slot"] * sd["slots"] / max(sd["profile_launches"]["attempt"], 1)
+            traffic = tr["dram_bytes_per_attempt"] * sd["attempts"] / max(sd["profile_launches"]["attempt"], 1)
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "k_attempt_hot + its exact twin k_attempt_slow (locate + conflict + reservation)", "achieved": achieved,
@@ -553,6 +553,9 @@ def main():
                 "achieved_note": "algorithmic bytes of all launches (SURVEY.md 8d formula, measured K and C) / summed CUDA-event time of all "
                                  "launches (launch sizes vary by 4 orders of magnitude)",
                 "algorithmic_bytes_per_point_kernel": b_attempt, "algorithmic_bytes_per_point_path": b_total,
+                "algorithmic_bytes_per_launch": n * b_attempt / max(sd["profile_launches"]["attempt"], 1),
+                "traffic_note": "dram__bytes read + write per attempt of the committed ncu --set full capture of the largest round (profiles/attempt_traffic.json) "
+                                "x attempts per average launch of this run; compare with algorithmic_bytes_per_launch",
                 "kernel_launches": sd["profile_launches"]["attempt"], "kernel_ms_total": sd["profile_ms"]["attempt"],
                 "path_frac": (value / world) * b_total / (peak * 1e9),
                 "counters_per_point": {"W_walk_steps_all_attempts": sd["walk_steps"] / n, "E_tests_all_attempts": sd["tests"] / n,
