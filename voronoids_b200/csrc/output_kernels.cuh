@@ -190,12 +190,10 @@ template <int D> VOR_HD void certify_body(const CertifyArgs<D> &A, int t) {
         if (v >= m.nsuper && A.owned[A.inputIdx[v]]) mine = true;
     }
     if (!mine) return;
-    const OwnBlk b = load_blk(m, t);
-    const double org[3] = {m.sref.ox, m.sref.oy, m.sref.oz};
-    const double c[3] = {(double)b.cx + org[0], (double)b.cy + org[1], (double)b.cz + org[2]};
-    double elo = A.boxLo[A.axis], ehi = A.boxHi[A.axis];       // no filter (rout2 = inf): the whole box
-    const double r2 = (double)b.rout2 * (1.0 + 1e-12);
-    if (r2 < 1e300) {
+    // extent along the axis of (ball of centre c, squared radius r2) n (data box minus the lateral shell); false: it misses the box
+    auto extent = [&](const double c[3], double r2, double &elo, double &ehi) -> bool {
+        elo = A.boxLo[A.axis]; ehi = A.boxHi[A.axis];           // no bound (r2 = inf): the whole box
+        if (!(r2 < 1e300)) return true;
         // squared distance of the centre to the part of the box this tree may be missing points from: the box shrunk by the
         // shell in the OTHER axes (an empty rest: every point of the box is held, nothing to certify)
         double d2 = 0.0;
@@ -203,19 +201,38 @@ template <int D> VOR_HD void certify_body(const CertifyArgs<D> &A, int t) {
         for (int k = 0; k < D; k++) {
             if (k == A.axis) continue;
             const double l = A.boxLo[k] + sh, h = A.boxHi[k] - sh;
-            if (l >= h) return;
+            if (l >= h) return false;
             const double d = c[k] < l ? l - c[k] : (c[k] > h ? c[k] - h : 0.0);
             d2 += d * d;
         }
         d2 *= (1.0 - 1e-12);
-        if (r2 <= d2) return;                                   // the ball misses the data box: nothing can be inside it
+        if (r2 <= d2) return false;                             // the ball misses the data box: nothing can be inside it
         const double half = sqrt(r2 - d2) * (1.0 + 1e-12) + 1e-300;
         const double slack = 4.0 * SPH_EPS * (fabs(c[A.axis]) + half);
         elo = fmax(elo, c[A.axis] - half - slack);
         ehi = fmin(ehi, c[A.axis] + half + slack);
-        if (elo > ehi) return;                                  // misses the box along the axis
+        return elo <= ehi;                                      // else: misses the box along the axis
+    };
+    const OwnBlk b = load_blk(m, t);
+    const double cb[3] = {(double)b.cx + m.sref.ox, (double)b.cy + m.sref.oy, (double)b.cz + m.sref.oz};
+    double elo, ehi;
+    if (!extent(cb, (double)b.rout2 * (1.0 + 1e-12), elo, ehi)) return;
+    if (elo >= A.lo && ehi <= A.hi) return;                     // certified by the stored block
+    // second chance in f64: the float block of a hull simplex (radius of 1e3..1e5 box widths) is good enough for conflict tests
+    // but moves the reach of its cap into the box by tenths of the box (sphere.cuh, sphere_ball_d)
+    {
+        const typename Geo<D>::Verts vv = Geo<D>::load(m, tv);
+        double cd[3], Rout;
+        bool ok;
+        if constexpr (D == 3) ok = sphere_ball_d(vv.p0, vv.p1, vv.p2, vv.p3, cd, Rout);
+        else ok = sphere_ball_d(vv.p0, vv.p1, vv.p2, cd, Rout);
+        if (ok) {
+            double e0, e1;
+            if (!extent(cd, Rout * Rout * (1.0 + 16.0 * SPH_EPS), e0, e1)) return;
+            elo = fmax(elo, e0); ehi = fmin(ehi, e1);           // both are valid bounds of the same set
+            if (elo >= A.lo && ehi <= A.hi) return;
+        }
     }
-    if (elo >= A.lo && ehi <= A.hi) return;                     // certified
     atomic_add_ull(A.count, 1ULL);
     if (elo < A.lo) atomic_min_d(&A.need[0], elo);
     if (ehi > A.hi) atomic_max_d(&A.need[1], ehi);

@@ -147,6 +147,65 @@ VOR_HD SphereBlk sphere_make(const double2 &p0, const double2 &p1, const double2
     return sphere_finish(p0.x, p0.y, 0.0, ccx, ccy, 0.0, rho_c, R);
 }
 
+// The same ball WITHOUT the float rounding of the stored block: absolute centre and an outer radius Rout in f64 with
+//     true open ball  subset of  { q : |q - c| <= Rout }.
+// For the slab certification (output_kernels.cuh): the circumsphere of a simplex on the hull is nearly a plane (radius 1e3..1e5
+// box widths), and how far its cap reaches into the data box is sqrt(Rout^2 - d^2) with d within a hair of Rout -- the 6e-8
+// relative rounding of a float rout2 moves that reach by tenths of the box.  Same formulas and bounds as sphere_make /
+// sphere_finish minus the float storage terms.  false: no bound (degenerate simplex).
+VOR_HD bool sphere_ball_d(const double4 &p0, const double4 &p1, const double4 &p2, const double4 &p3, double c[3], double &Rout) {
+    const double ax = p1.x - p0.x, ay = p1.y - p0.y, az = p1.z - p0.z;
+    const double bx = p2.x - p0.x, by = p2.y - p0.y, bz = p2.z - p0.z;
+    const double cx = p3.x - p0.x, cy = p3.y - p0.y, cz = p3.z - p0.z;
+    const double bcx = by * cz - bz * cy, bcy = bz * cx - bx * cz, bcz = bx * cy - by * cx;
+    const double cax = cy * az - cz * ay, cay = cz * ax - cx * az, caz = cx * ay - cy * ax;
+    const double abx = ay * bz - az * by, aby = az * bx - ax * bz, abz = ax * by - ay * bx;
+    const double det = ax * bcx + ay * bcy + az * bcz;
+    const double sa = ax * ax + ay * ay + az * az, sb = bx * bx + by * by + bz * bz, sc = cx * cx + cy * cy + cz * cz;
+    // the permanent of |M| itself (this is not a hot path): the product of the row 1-norms that sphere_make uses overestimates it by
+    // orders of magnitude for a hull simplex (two long edges to super vertices, one short edge) and denies it a bound
+    const double perm = fabs(ax) * (fabs(by * cz) + fabs(bz * cy)) + fabs(ay) * (fabs(bz * cx) + fabs(bx * cz)) + fabs(az) * (fabs(bx * cy) + fabs(by * cx));
+    const double detLow = fabs(det) - 8.0 * SPH_EPS * perm * (1.0 + 1e-9);
+    if (!(detLow > 0.0)) return false;
+    const double inv = 0.5 / det;
+    const double ccx = (sa * bcx + sb * cax + sc * abx) * inv;
+    const double ccy = (sa * bcy + sb * cay + sc * aby) * inv;
+    const double ccz = (sa * bcz + sb * caz + sc * abz) * inv;
+    const double acx = fabs(ccx), acy = fabs(ccy), acz = fabs(ccz);
+    const double ra = fabs(2.0 * (ax * ccx + ay * ccy + az * ccz) - sa) + 16.0 * SPH_EPS * (2.0 * (fabs(ax) * acx + fabs(ay) * acy + fabs(az) * acz) + sa);
+    const double rb = fabs(2.0 * (bx * ccx + by * ccy + bz * ccz) - sb) + 16.0 * SPH_EPS * (2.0 * (fabs(bx) * acx + fabs(by) * acy + fabs(bz) * acz) + sb);
+    const double rc = fabs(2.0 * (cx * ccx + cy * ccy + cz * ccz) - sc) + 16.0 * SPH_EPS * (2.0 * (fabs(cx) * acx + fabs(cy) * acy + fabs(cz) * acz) + sc);
+    const double adj2 = (sb * sc + sc * sa + sa * sb) * (1.0 + 1e-9);
+    const double rho_c = 0.5 * sqrt(adj2 * (ra * ra + rb * rb + rc * rc)) / detLow * (1.0 + 1e-9);
+    c[0] = p0.x + ccx; c[1] = p0.y + ccy; c[2] = p0.z + ccz;
+    // |c - c*| <= rho_c + rounding of the three additions; true radius <= |p0 - c| + that
+    const double rho = rho_c + 4.0 * SPH_EPS * (fabs(p0.x) + acx + fabs(p0.y) + acy + fabs(p0.z) + acz);
+    const double rhat = sqrt(ccx * ccx + ccy * ccy + ccz * ccz);
+    Rout = rhat * (1.0 + 8.0 * SPH_EPS) + 2.0 * rho;
+    return Rout < 1e150 && rho >= 0.0;
+}
+VOR_HD bool sphere_ball_d(const double2 &p0, const double2 &p1, const double2 &p2, double c[3], double &Rout) {
+    const double ax = p1.x - p0.x, ay = p1.y - p0.y;
+    const double bx = p2.x - p0.x, by = p2.y - p0.y;
+    const double det = ax * by - ay * bx;
+    const double detLow = fabs(det) - 4.0 * SPH_EPS * (fabs(ax * by) + fabs(ay * bx));
+    if (!(detLow > 0.0)) return false;
+    const double sa = ax * ax + ay * ay, sb = bx * bx + by * by;
+    const double inv = 0.5 / det;
+    const double ccx = (sa * by - sb * ay) * inv;
+    const double ccy = (sb * ax - sa * bx) * inv;
+    const double acx = fabs(ccx), acy = fabs(ccy);
+    const double ra = fabs(2.0 * (ax * ccx + ay * ccy) - sa) + 16.0 * SPH_EPS * (2.0 * (fabs(ax) * acx + fabs(ay) * acy) + sa);
+    const double rb = fabs(2.0 * (bx * ccx + by * ccy) - sb) + 16.0 * SPH_EPS * (2.0 * (fabs(bx) * acx + fabs(by) * acy) + sb);
+    const double adj2 = ax * ax + ay * ay + bx * bx + by * by;
+    const double rho_c = 0.5 * sqrt(adj2) * sqrt(ra * ra + rb * rb) / detLow * (1.0 + 1e-9);
+    c[0] = p0.x + ccx; c[1] = p0.y + ccy; c[2] = 0.0;
+    const double rho = rho_c + 4.0 * SPH_EPS * (fabs(p0.x) + acx + fabs(p0.y) + acy);
+    const double rhat = sqrt(ccx * ccx + ccy * ccy);
+    Rout = rhat * (1.0 + 8.0 * SPH_EPS) + 2.0 * rho;
+    return Rout < 1e150 && rho >= 0.0;
+}
+
 // +1: certainly strictly inside, -1: certainly not strictly inside, 0: undecided (ask the determinant)
 VOR_HD int sphere_test(float cx, float cy, float cz, float rin2, float rout2, double qx, double qy, double qz) {
     const double dx = qx - (double)cx, dy = qy - (double)cy, dz = qz - (double)cz;

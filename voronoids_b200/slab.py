@@ -20,6 +20,7 @@ gloo in the CPU tests):
                 run, byte for byte (tests/test_slab.py, tests/test_gpu_slab.py).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -139,6 +140,7 @@ def delaunay_slab(lib, points, global_index, device=0, axis=0, coarse_div=16, ha
     product library; cpu for the kernel emulation in tests), all within this rank's range along `axis` (ranges of different
     ranks must not overlap); global_index: int64 [n], the input index of every point in the global set."""
     world, me = _world()
+    verbose = verbose or bool(os.environ.get("VOR_SLAB_VERBOSE"))
     dim = int(points.shape[1])
     cdev = _backend_device(points.device)
     n_own = int(points.shape[0])
@@ -197,6 +199,9 @@ def delaunay_slab(lib, points, global_index, device=0, axis=0, coarse_div=16, ha
         if p.shape[0] == 0:
             return
         p = p.contiguous()
+        if p.is_cuda:
+            # the tree works on its own stream: what torch (or NCCL, through torch's stream) is still writing must have landed
+            torch.cuda.current_stream(p.device).synchronize()
         chk(lib.vor_tree_insert_device(h, C.c_void_p(p.data_ptr()), int(p.shape[0]), 1))
         gmap.append(g.cpu().numpy().astype(np.int64))
         owned.append(own_flags)
