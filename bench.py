@@ -391,6 +391,7 @@ def run_slab(args, name, rank, world, local_rank):
                     "halo_bytes_received_per_rank": [i.get("halo_rows_received", 0) * (dim + 1) * 8 for i in infos],
                     "coarse_points": infos[0].get("coarse_points", 0), "tree_points_per_rank": [i.get("tree_points", 0) for i in infos],
                     "certification_rounds": max(i.get("rounds", 0) for i in infos),
+                    "simplices_certified_by_peers": [int(i.get("peer_certified", 0)) for i in infos],
                     "edges": int(full.shape[0]), "edges_sha256": hashlib.sha256(np.ascontiguousarray(full).tobytes()).hexdigest()})
         line = {"metric": "delaunay_points_inserted_per_sec", "value": n / (ms_per_step * 1e-3), "unit": "points/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -163,6 +163,15 @@ vor_status vor_tree_create_bounds(int dim, const double *lo, const double *hi, u
                                   vor_tree **out);
 vor_status vor_tree_certify_slab(vor_tree *t, const uint8_t *owned, size_t n_owned, int axis, double range_lo, double range_hi, double shell,
                                  uint64_t *n_uncertified, double *need);
+/* The same pass, also handing out the uncertified simplices themselves: verts = up to cap x (dim+1) x dim vertex coordinates
+ * (order of the mesh record: positively oriented), reach = cap x 2 extents along the axis.  For the certificate that is not a
+ * ball: a sliver on the hull has a circumsphere of 1e3..1e5 box widths that f64 cannot bound tightly (or at all); its owner asks
+ * the peers whether any of THEIR points lies strictly inside it (vor_points_in_spheres, exact predicate) -- none anywhere means the
+ * simplex is a simplex of the global triangulation.  inside[j] = number of the n device-resident points strictly inside the
+ * circumsphere of simplex j (k simplices of (dim+1) x dim doubles, positively oriented, on the host). */
+vor_status vor_tree_uncertified_slab(vor_tree *t, const uint8_t *owned, size_t n_owned, int axis, double range_lo, double range_hi, double shell,
+                                     double *verts, double *reach, size_t cap, uint64_t *n_uncertified, double *need);
+vor_status vor_points_in_spheres(int dim, const double *d_points, size_t n, const double *simplices, size_t k, int device, uint64_t *inside);
 
 /* this slab's part of the global canonical edge list (host block of the library's allocator, release with vor_host_free):
  * edges of the tree whose endpoint with the lower GLOBAL index is owned by the slab, as sorted (lo, hi) global index pairs.

@@ -64,3 +64,17 @@ def test_gpu_slab_union_is_the_single_gpu_edge_list(gpu_lib, golden, name, world
         # nobody triangulated the whole set.  (Clustered input is exact too, but its hull is not aligned with the data box:
         # the hull simplices' caps are not covered by the lateral shell and the ranges widen until they are -- DESIGN.md.)
         assert all(i["tree_points"] < 0.9 * g["n"] for i in infos), infos
+
+
+@pytest.mark.gpu
+def test_gpu_points_in_spheres_is_exact(gpu_lib):
+    """the peers' side of the certificate that is not a ball (vor_points_in_spheres) on the B200, against fractions.Fraction"""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_slab import _points_in_spheres_case
+    keep = []
+    def dev(pts):
+        keep.append(torch.from_numpy(np.ascontiguousarray(pts)).cuda())
+        torch.cuda.synchronize()
+        return keep[-1].data_ptr()
+    _points_in_spheres_case(gpu_lib, dev)

@@ -64,3 +64,61 @@ def test_slab_single_rank_is_the_plain_path(emu_lib, oracle):
     pts = pointgen.uniform(3000, 3, 9)
     res = slab.delaunay_slab(emu_lib, torch.from_numpy(pts), torch.arange(3000), device=0)
     assert np.array_equal(res.edges, oracle.ExactDelaunay(pts).edges())
+
+
+def _points_in_spheres_case(lib, device_points):
+    """vor_points_in_spheres against fractions.Fraction: exact in-sphere counts of random points (some within ulps of the sphere)
+    against a well-shaped simplex, a sliver and a nearly flat hull-like simplex with a super-vertex-sized edge."""
+    from fractions import Fraction as F
+    from voronoids_b200 import _capi
+    rng = np.random.default_rng(7)
+    simp = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]],
+                     [[0.1, 0.1, 0.1], [0.9, 0.12, 0.1], [0.5, 0.8, 0.1000001], [0.45, 0.3, 0.0999999]],
+                     [[0.2, 0.2, 0.999], [0.7, 0.3, 0.9991], [0.4, 0.8, 0.99905], [17.0, -3.0, 25.0]]], dtype=np.float64)
+    # orientation as the mesh stores it: positive (swap two vertices where it is not)
+    def det3(a, b, c, d):
+        m = [[F(a[i]) - F(d[i]) for i in range(3)], [F(b[i]) - F(d[i]) for i in range(3)], [F(c[i]) - F(d[i]) for i in range(3)]]
+        return (m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0])
+                + m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]))
+    pts = rng.random((4000, 3))
+    pts[:8] = simp[0][[0, 1, 2, 3, 0, 1, 2, 3]]            # ON the first sphere: not strictly inside
+    pts[8] = [0.5, 0.5, 0.5]
+    pts[9] = np.nextafter(1.0, 2.0), 0.0, 0.0               # an ulp outside a vertex
+    def insphere_exact(s, p):
+        rows = []
+        for v in s:
+            d = [F(v[i]) - F(p[i]) for i in range(3)]
+            rows.append(d + [d[0] * d[0] + d[1] * d[1] + d[2] * d[2]])
+        def minor(r, cols):
+            a, b, c = [[r[i][j] for j in cols] for i in range(3)]
+            return a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0])
+        det = 0
+        for i in range(4):
+            others = [rows[j] for j in range(4) if j != i]
+            det += (-1) ** (i + 3) * rows[i][3] * minor(others, [0, 1, 2])
+        return det
+    want = []
+    for k in range(len(simp)):
+        o = det3(*simp[k])
+        assert o != 0
+        if o < 0:
+            simp[k][[0, 1]] = simp[k][[1, 0]]
+            o = -o
+        # sign convention probed with the centroid of the simplex (strictly inside its circumsphere)
+        cen = simp[k].mean(axis=0)
+        sgn = 1 if insphere_exact(simp[k], cen) > 0 else -1
+        want.append(sum(1 for p in pts if sgn * insphere_exact(simp[k], p) > 0))
+    inside = np.zeros(len(simp), dtype=np.uint64)
+    st = lib.vor_points_in_spheres(3, C.c_void_p(device_points(pts)), len(pts), np.ascontiguousarray(simp).ctypes.data_as(_capi.dp), len(simp), 0,
+                                   inside.ctypes.data_as(_capi.u64p))
+    assert st == 0
+    assert [int(x) for x in inside] == want, (inside, want)
+    assert want[0] > 0 and want[0] < len(pts)
+
+
+def test_points_in_spheres_is_exact(emu_lib):
+    keep = []
+    def host(pts):
+        keep.append(np.ascontiguousarray(pts))
+        return keep[-1].ctypes.data
+    _points_in_spheres_case(emu_lib, host)

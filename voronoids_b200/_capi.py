@@ -44,6 +44,9 @@ SYMBOLS = {
     "vor_slab_count_outside": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_int, dp, dp, u64p]),
     "vor_tree_create_bounds": (C.c_int, [C.c_int, dp, dp, C.c_uint64, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(tree_p)]),
     "vor_tree_certify_slab": (C.c_int, [tree_p, C.POINTER(C.c_uint8), C.c_size_t, C.c_int, C.c_double, C.c_double, C.c_double, u64p, dp]),
+    "vor_tree_uncertified_slab": (C.c_int, [tree_p, C.POINTER(C.c_uint8), C.c_size_t, C.c_int, C.c_double, C.c_double, C.c_double, dp, dp,
+                                            C.c_size_t, u64p, dp]),
+    "vor_points_in_spheres": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, dp, C.c_size_t, C.c_int, u64p]),
     "vor_delaunay_batch_stream": (C.c_int, [C.c_int, C.c_void_p, C.c_int, i64p, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, u64p, u64p, C.c_void_p,
                                             C.c_void_p]),
     "vor_tree_super_simplex": (C.c_int, [tree_p, C.c_size_t, dp, dp, dp]),

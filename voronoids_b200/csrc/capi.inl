@@ -592,6 +592,52 @@ vor_status vor_tree_certify_slab(vor_tree *t, const uint8_t *owned, size_t n_own
     });
 }
 
+vor_status vor_tree_uncertified_slab(vor_tree *t, const uint8_t *owned, size_t n_owned, int axis, double range_lo, double range_hi, double shell,
+                                     double *verts, double *reach, size_t cap, uint64_t *n_uncertified, double *need) {
+    return guarded([&]() -> vor_status {
+        if (!t || !owned || !n_uncertified || !need || !verts || !reach || cap < 1 || cap > (1u << 20) || axis < 0 || axis >= t->dim) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(t->device);
+        return t->visit([&](auto &e) -> vor_status {
+            if ((size_t)e.ninput != n_owned) { g_err = "owned flags must cover every inserted point"; return VOR_ERR_ARG; }
+            *n_uncertified = (uint64_t)e.certify_slab(owned, axis, range_lo, range_hi, shell, need, verts, reach, (int)cap);
+            return VOR_OK;
+        });
+    });
+}
+
+vor_status vor_points_in_spheres(int dim, const double *d_points, size_t n, const double *simplices, size_t k, int device, uint64_t *inside) {
+    return guarded([&]() -> vor_status {
+        if ((dim != 2 && dim != 3) || !simplices || !inside || k < 1 || k > (1u << 20) || (n && !d_points)) { g_err = "bad argument"; return VOR_ERR_ARG; }
+        vor::be::set_device(device);
+        if (n == 0) { for (size_t j = 0; j < k; j++) inside[j] = 0; return VOR_OK; }
+        auto run = [&](auto tag) {
+            constexpr int D = decltype(tag)::value;
+            constexpr int M = D + 1;
+            vor::be::Stream st{};
+            DevBuf dsimp(sizeof(double) * k * M * D), dins(sizeof(unsigned long long) * k), dcnt(sizeof(vor::Counters));
+            vor::be::h2d(dsimp.p, simplices, sizeof(double) * k * M * D, st);
+            vor::be::dmemset(dins.p, 0, sizeof(unsigned long long) * k, st);
+            vor::be::dmemset(dcnt.p, 0, sizeof(vor::Counters), st);
+            const vor::InSpheresArgs<D> a{d_points, (const double *)dsimp.p, (int)k, (unsigned long long *)dins.p, (vor::Counters *)dcnt.p};
+            for (size_t done = 0; done < n; done += (size_t)1 << 30) {
+                vor::InSpheresArgs<D> b = a;
+                b.pts = d_points + done * D;
+                VOR_LAUNCH(vor::InSpheresArgs<D>, vor::in_spheres_body<D>, (long long)std::min(n - done, (size_t)1 << 30), b, st);
+            }
+            std::vector<unsigned long long> h(k);
+            vor::be::d2h(h.data(), dins.p, sizeof(unsigned long long) * k, st);
+            vor::Counters hc;
+            vor::be::d2h(&hc, dcnt.p, sizeof(hc), st);
+            vor::be::sync(st);
+            if (hc.err) throw vor::EngineError{hc.err, "points_in_spheres: coordinate range exceeds the exact arithmetic"};
+            for (size_t j = 0; j < k; j++) inside[j] = h[j];
+        };
+        if (dim == 3) run(std::integral_constant<int, 3>{});
+        else run(std::integral_constant<int, 2>{});
+        return VOR_OK;
+    });
+}
+
 vor_status vor_tree_edges_slab(vor_tree *t, const int64_t *global_index, const uint8_t *owned, size_t n, uint32_t **edges, size_t *n_edges) {
     return guarded([&]() -> vor_status {
         if (!t || !global_index || !owned || !edges || !n_edges) { g_err = "bad argument"; return VOR_ERR_ARG; }

@@ -1054,21 +1054,32 @@ template <int D> class Engine {
     // part of its circumsphere that lies inside the data box within [range_lo, range_hi] along `axis` -- the range in
     // which this tree holds EVERY point of the global set.  Returns the number of simplices that do not, and the extent
     // they need (need[0] <= range_lo, need[1] >= range_hi).
-    long long certify_slab(const unsigned char *h_owned, int axis, double range_lo, double range_hi, double shell, double *need) {
+    // h_verts / h_reach (optional): the first `cap` uncertified simplices as M x D vertex coordinates + their reach along the axis
+    long long certify_slab(const unsigned char *h_owned, int axis, double range_lo, double range_hi, double shell, double *need,
+                           double *h_verts = nullptr, double *h_reach = nullptr, int cap = 0) {
         DevTmp<unsigned char> down((size_t)std::max(ninput, 1));
         DevTmp<unsigned long long> dcount(1);
         DevTmp<double> dneed(2);
+        const bool list = h_verts && h_reach && cap > 0;
+        DevTmp<double> dverts(list ? (size_t)cap * M * D : 1), dreach(list ? (size_t)cap * 2 : 1);
         be::h2d(down.p, h_owned, (size_t)ninput, stream);
         be::dmemset(dcount.p, 0, sizeof(unsigned long long), stream);
         const double init[2] = {range_lo, range_hi};
         be::h2d(dneed.p, init, sizeof(init), stream);
         CertifyArgs<D> ca{mesh, inputIdx, down.p, dcount.p, dneed.p, axis, range_lo, range_hi, shell};
         for (int k = 0; k < 3; k++) { ca.boxLo[k] = k < D ? boxLo[k] : 0.0; ca.boxHi[k] = k < D ? boxHi[k] : 0.0; }
+        if (list) { ca.listVerts = dverts.p; ca.listReach = dreach.p; ca.listCap = cap; }
         VOR_LAUNCH(CertifyArgs<D>, certify_body<D>, hcnt->ntets, ca, stream);
         unsigned long long cnt = 0;
         be::d2h(&cnt, dcount.p, sizeof(cnt), stream);
         be::d2h(need, dneed.p, sizeof(double) * 2, stream);
         be::sync(stream);
+        if (list && cnt > 0) {
+            const size_t k = (size_t)std::min<unsigned long long>(cnt, (unsigned long long)cap);
+            be::d2h(h_verts, dverts.p, sizeof(double) * k * M * D, stream);
+            be::d2h(h_reach, dreach.p, sizeof(double) * k * 2, stream);
+            be::sync(stream);
+        }
         return (long long)cnt;
     }
 

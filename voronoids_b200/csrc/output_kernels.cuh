@@ -178,6 +178,11 @@ template <int D> struct CertifyArgs {
     double lo, hi;
     double shell;                 // the tree also holds every global point within `shell` of a lateral face of the data box
     double boxLo[3], boxHi[3];
+    // optional list of the uncertified simplices (vor_tree_uncertified_slab): M x D vertex coordinates in the order of the mesh
+    // record (positively oriented) and the reach [elo, ehi] of each, up to listCap of them; *count keeps counting beyond it
+    double *listVerts = nullptr;
+    double *listReach = nullptr;
+    int listCap = 0;
 };
 template <int D> VOR_HD void certify_body(const CertifyArgs<D> &A, int t) {
     constexpr int M = Dim<D>::M;
@@ -233,9 +238,49 @@ template <int D> VOR_HD void certify_body(const CertifyArgs<D> &A, int t) {
             if (elo >= A.lo && ehi <= A.hi) return;
         }
     }
-    atomic_add_ull(A.count, 1ULL);
+    const unsigned long long idx = atomic_add_ull(A.count, 1ULL);
     if (elo < A.lo) atomic_min_d(&A.need[0], elo);
     if (ehi > A.hi) atomic_max_d(&A.need[1], ehi);
+    if (A.listVerts && idx < (unsigned long long)A.listCap) {
+        for (int k = 0; k < M; k++) {
+            const typename Dim<D>::Pt q = m.pts[get4(tv, k)];
+            A.listVerts[(idx * M + k) * D + 0] = q.x;
+            A.listVerts[(idx * M + k) * D + 1] = q.y;
+            if constexpr (D == 3) A.listVerts[(idx * M + k) * D + 2] = q.z;
+        }
+        A.listReach[2 * idx] = elo;
+        A.listReach[2 * idx + 1] = ehi;
+    }
+}
+
+// slab mode, the certificate that is not a ball: how many of n points lie STRICTLY inside the circumsphere of each of k simplices
+// (exact predicate: FP64 filter -> exact).  A rank asks its peers this about the handful of simplices whose ball it cannot bound
+// (slivers on the hull); zero everywhere = the simplex is a simplex of the global triangulation.
+template <int D> struct InSpheresArgs {
+    const double *pts;            // n x D
+    const double *simp;           // k x M x D, positively oriented
+    int k;
+    unsigned long long *inside;   // [k]
+    Counters *cnt;
+};
+template <int D> VOR_HD void in_spheres_body(const InSpheresArgs<D> &A, int i) {
+    constexpr int M = Dim<D>::M;
+    typename Dim<D>::Pt p;
+    p.x = A.pts[(size_t)i * D]; p.y = A.pts[(size_t)i * D + 1];
+    if constexpr (D == 3) { p.z = A.pts[(size_t)i * D + 2]; p.w = 0.0; }
+    PredCtx cx{A.cnt};
+    for (int j = 0; j < A.k; j++) {
+        typename Geo<D>::Verts vv;
+        typename Dim<D>::Pt q[4];
+        for (int v = 0; v < M; v++) {
+            const double *c = A.simp + ((size_t)j * M + v) * D;
+            q[v].x = c[0]; q[v].y = c[1];
+            if constexpr (D == 3) { q[v].z = c[2]; q[v].w = 0.0; }
+        }
+        vv.p0 = q[0]; vv.p1 = q[1]; vv.p2 = q[2];
+        if constexpr (D == 3) vv.p3 = q[3];
+        if (Geo<D>::conflict(cx, vv, p)) atomic_add_ull(&A.inside[j], 1ULL);
+    }
 }
 
 // slab mode: this slab's part of the GLOBAL canonical edge list.  An edge of the local list (local input indices) is

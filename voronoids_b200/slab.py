@@ -36,6 +36,9 @@ def _backend_device(compute_device):
     return torch.device("cpu")
 
 
+PEER_CAP = 256     # uncertified simplices a rank may hand to its peers for the exact in-sphere certificate
+
+
 def _world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size(), dist.get_rank()
@@ -226,7 +229,7 @@ def delaunay_slab(lib, points, global_index, device=0, axis=0, coarse_div=16, ha
         want = [my_lo - halo_spacings * spacing, my_hi + halo_spacings * spacing, 2.0 * spacing] if world > 1 else [my_lo, my_hi, 0.0]
         have = [my_lo, my_hi, 0.0]            # region in which this tree holds every global point
         sent = {}                             # per peer: mask of my fine points already sent to it
-        rounds = sent_rows = recv_rows = 0
+        rounds = sent_rows = recv_rows = peer_certified = 0
         while True:
             want[0], want[1] = max(want[0], float(glo[axis])), min(want[1], float(ghi[axis]))
             if world > 1:
@@ -251,19 +254,51 @@ def delaunay_slab(lib, points, global_index, device=0, axis=0, coarse_div=16, ha
             rounds += 1
             own_np = np.concatenate(owned) if owned else np.zeros(0, dtype=np.uint8)
             nunc, need = C.c_uint64(0), np.zeros(2)
+            uverts, ureach = np.zeros((PEER_CAP, dim + 1, dim)), np.zeros((PEER_CAP, 2))
             if len(own_np):
-                chk(lib.vor_tree_certify_slab(h, own_np.ctypes.data_as(C.POINTER(C.c_uint8)), len(own_np), axis, have[0], have[1], have[2],
-                                              C.byref(nunc), need.ctypes.data_as(_capi.dp)))
+                chk(lib.vor_tree_uncertified_slab(h, own_np.ctypes.data_as(C.POINTER(C.c_uint8)), len(own_np), axis, have[0], have[1], have[2],
+                                                  uverts.ctypes.data_as(_capi.dp), ureach.ctypes.data_as(_capi.dp), PEER_CAP,
+                                                  C.byref(nunc), need.ctypes.data_as(_capi.dp)))
             else:
                 need[:] = have[:2]
-            worst = int(_allreduce(torch.tensor([nunc.value], dtype=torch.int64), dist.ReduceOp.MAX, cdev).item())
+            n_unc = int(nunc.value)
+            # ---- the certificate that is not a ball.  The few simplices a rank cannot certify from its own ball (slivers on the
+            # hull: a circumsphere of 1e3..1e5 box widths that f64 bounds loosely or not at all) go to every rank; each counts how many
+            # of ITS fine points lie strictly inside (exact predicate).  None anywhere: the simplex is a simplex of the global
+            # triangulation whatever its ball says.  Only when every rank's list fits (else the ranges are widened as before).
+            if world > 1:
+                fits = int(_allreduce(torch.tensor([1 if n_unc <= PEER_CAP else 0], dtype=torch.int64), dist.ReduceOp.MIN, cdev).item())
+                total = int(_allreduce(torch.tensor([n_unc], dtype=torch.int64), dist.ReduceOp.SUM, cdev).item())
+                if fits and total > 0:
+                    mine_rows = torch.from_numpy(uverts[:n_unc].reshape(n_unc, -1).copy()) if n_unc else torch.zeros((0, (dim + 1) * dim), dtype=torch.float64)
+                    lists = _allgather_rows(mine_rows, cdev)
+                    counts = [int(x.shape[0]) for x in lists]
+                    allv = torch.cat(lists).numpy() if total else np.zeros((0, (dim + 1) * dim))
+                    inside = np.zeros(max(total, 1), dtype=np.uint64)
+                    if total and fine_pts.shape[0]:
+                        fp = fine_pts.contiguous()
+                        if fp.is_cuda:
+                            torch.cuda.current_stream(fp.device).synchronize()
+                        allv = np.ascontiguousarray(allv, dtype=np.float64)
+                        chk(lib.vor_points_in_spheres(dim, C.c_void_p(fp.data_ptr()), int(fp.shape[0]), allv.ctypes.data_as(_capi.dp), total, device,
+                                                      inside.ctypes.data_as(_capi.u64p)))
+                    tot_in = _allreduce(torch.from_numpy(inside[:max(total, 1)].astype(np.int64)), dist.ReduceOp.SUM, cdev).numpy()
+                    off = int(sum(counts[:me]))
+                    bad = [j for j in range(n_unc) if tot_in[off + j] > 0]
+                    peer_certified += n_unc - len(bad)
+                    n_unc = len(bad)
+                    need[:] = have[:2]
+                    for j in bad:
+                        need[0], need[1] = min(need[0], ureach[j, 0]), max(need[1], ureach[j, 1])
+            worst = int(_allreduce(torch.tensor([n_unc], dtype=torch.int64), dist.ReduceOp.MAX, cdev).item())
             if verbose:
-                print(f"[slab {me}] round {rounds}: holds {sum(len(g) for g in gmap)} points, region {have}, uncertified {nunc.value}, need {need}", flush=True)
+                print(f"[slab {me}] round {rounds}: holds {sum(len(g) for g in gmap)} points, region {have}, uncertified {nunc.value} "
+                      f"({n_unc} after asking the peers), need {need}", flush=True)
             if worst == 0:
                 break
             if rounds >= max_rounds:
                 raise RuntimeError("slab mode: certification did not converge")
-            if nunc.value:
+            if n_unc:
                 if have[2] < shell_max:
                     # first thicken the shell (cheap: a few percent of the points), and follow the need along the axis only a
                     # few spacings at a time
@@ -273,7 +308,7 @@ def delaunay_slab(lib, points, global_index, device=0, axis=0, coarse_div=16, ha
                     grow = spacing
                     want = [min(have[0], float(need[0]) - grow) if need[0] < have[0] else have[0],
                             max(have[1], float(need[1]) + grow) if need[1] > have[1] else have[1], have[2]]
-        info.update({"rounds": rounds, "halo_rows_sent": sent_rows, "halo_rows_received": recv_rows, "coarse_points": int(c_pts.shape[0]),
+        info.update({"rounds": rounds, "peer_certified": peer_certified, "halo_rows_sent": sent_rows, "halo_rows_received": recv_rows, "coarse_points": int(c_pts.shape[0]),
                      "tree_points": int(sum(len(g) for g in gmap)), "region": have, "own_range": [my_lo, my_hi]})
 
         # ---- 5. edges at owned points, emitted by the owner of the endpoint with the lower global index (mapped, filtered and
