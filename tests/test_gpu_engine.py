@@ -295,10 +295,11 @@ def test_gpu_edges_pinned_block_outlives_tree(gpu_lib):
     assert gpu_lib.vor_host_free(12345) != 0
 
 
-ENGINE_DEFAULTS = {"red": 1, "commit_smem": 1, "split_exact": 1}
+ENGINE_DEFAULTS = {"red": 1, "commit_smem": 1, "split_exact": 1, "carry_frac": 0.125, "pdl": 131072, "mid_twin": 1}
 
 
-@pytest.mark.parametrize("opts", [{"red": 0}, {"commit_smem": 0}, {"split_exact": 0}, {"split_exact": 0, "commit_smem": 0}])
+@pytest.mark.parametrize("opts", [{"red": 0}, {"commit_smem": 0}, {"split_exact": 0}, {"split_exact": 0, "commit_smem": 0},
+                                  {"carry_frac": 0.0}, {"carry_frac": 0.5}, {"pdl": 0}, {"carry_frac": 0.5, "pdl": 0, "mid_twin": 0}])
 def test_gpu_engine_options_keep_parity(gpu_lib, oracle, opts):
     """every scheduling / layout option of the engine yields the oracle's edge set (3D and 2D)"""
     try:
@@ -310,6 +311,18 @@ def test_gpu_engine_options_keep_parity(gpu_lib, oracle, opts):
     finally:
         for k, v in ENGINE_DEFAULTS.items():
             gpu_lib.vor_set_option(k.encode(), float(v))
+
+
+@pytest.mark.parametrize("mid", [1, 0])
+def test_gpu_lattice_through_the_mid_twin(gpu_lib, oracle, mid):
+    """jittered lattice (a third of the conflict tests leave the float sphere filter): the hot kernel's twin with the FP64 determinant
+    stage inside, the double-double stage and the exact twin behind it -- and the same input with the twin switched off"""
+    try:
+        gpu_lib.vor_set_option(b"mid_twin", float(mid))
+        st = ec.check_against_oracle(gpu_lib, oracle, pointgen.make("lattice", 150_000, 3, 2))
+        assert st["winners"] == 150_000
+    finally:
+        gpu_lib.vor_set_option(b"mid_twin", 1.0)
 
 
 @pytest.mark.parametrize("dim", [2, 3])

@@ -1,17 +1,23 @@
 // coop_kernels.cuh -- lane-group-cooperative round kernels (CUDA only): the product path on the B200.
 //
-// G lanes (G = 32: a whole warp, north_star's "one warp per point"; G = 8 optional) work on ONE pending point.  The
-// serial dependency chain of the thread-per-point bodies in kernels.cuh (one in-sphere test after the other: ~60-100
-// tests x 3-4 dependent gathers each) becomes one chain per BFS LEVEL of the conflict region:
-//   attempt  walk: lane k evaluates the orientation of facet k (ballot -> facet to cross), one 256-bit record gather per
-//            step; flood: each lane takes one (frontier simplex, facet) item: gathers the neighbour code, its owner pair,
-//            its record and its 4 vertex sectors (256-bit loads) and evaluates the exact in-sphere test; reservation by
-//            red.min / atomicMin; new killed simplices / boundary facets are appended with ballot + popc prefix sums
-//            into the point's contiguous scratch.  One warp per block, 64 registers.
-//   commit   (check + retriangulate fused) the cavity is staged in shared memory, lanes vote on ownership; a winner
-//            allocates its block of simplex slots and retriangulates inside the SM (one lane per new simplex).
-// What bounds them on the B200 is the scattered-load-instruction rate beyond the TLB reach, hence
-// the wide loads; the compile-time switches below record the alternatives that were measured and lost.
+// G lanes (3D: a whole warp, north_star's "one warp per point"; 2D: 16, two points per warp) work on ONE pending point.  The
+// serial dependency chain of the thread-per-point bodies in kernels.cuh (one in-sphere test after the other) becomes one chain
+// per BFS LEVEL of the conflict region.  A round is three launches, chained by programmatic dependent launch on small rounds:
+//   k_attempt_hot   forwarding -> walk on the power distance of the cached spheres (lane i < M gathers the 64 B line of neighbour
+//            i: block + neighbour codes) -> flood: each lane takes one (frontier simplex, facet) item from the cavity staged in
+//            shared memory, gathers the neighbour's 32 B block -- ownership words + certified sphere filter (sphere.cuh) -- with
+//            ONE 256-bit load and decides from it; reservation by fire-and-forget red.min; new killed simplices / boundary
+//            facets are appended with ballot + popc prefix sums.  NO determinant code: 56 registers, spill-free.  Its MID twin
+//            (template parameter) puts the FP64 determinant filter behind the sphere filter for input that keeps leaving it;
+//            k_attempt_slow / k_attempt_coop are the exact twin (visibility walk with exact orient, filter -> FP64 determinant ->
+//            double-double -> exact integers) for the points the hot kernels hand over.  The result of a slot leaves as one 16 B word.
+//   k_commit_coop   (check + retriangulate fused) starts from that word, stages the cavity in shared memory with one level of
+//            gathers, lanes vote on ownership; a winner takes its block of simplex slots with one atomicAdd and retriangulates
+//            inside the SM (neighbour codes translated to local indices once, one lane per new simplex pivots around its ridges).
+//   k_spheres       block (free ownership words + sphere filter) of every simplex the commit just created.
+// What bounds them: on full rounds DRAM 26 / 41 / 53 % of peak with ~50 % of the issue slots busy; on the ~600 rounds below ~32 k
+// slots the latency of ONE attempt + commit + sphere pass (profiles/r2_round_ncu.md).  The compile-time switches
+// below record the alternatives that were measured and lost.
 // Same scratch format and same semantics as kernels.cuh (reference: delaunay_tree.rs:33-123, :213-334, scheduler.rs:6-55),
 // so the two implementations are interchangeable (option "coop"); tests/emu exercises the thread-per-point bodies on
 // the CPU, tests/test_gpu_* exercise these against the oracle on the B200.
