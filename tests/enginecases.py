@@ -56,6 +56,24 @@ def case_incremental(lib, O, dim, n0, n1, seed=0):
         t.close()
 
 
+def case_awkward_sizes(lib, O, dim):
+    """sizes around the first stage (256), the stage hand-over thresholds and the attempt-slot floor (8192), and a tree grown by many
+    small insert calls (each call starts new stages and must drain its last one)"""
+    for n in (16, 100, 255, 256, 257, 300, 511, 513, 1000, 2049, 8191, 8193, 20_001):
+        st = check_against_oracle(lib, O, pointgen.uniform(n, dim, 100 + n), simplices=n < 3000)
+        assert st["winners"] == n
+    pts = pointgen.uniform(6000, dim, 77)
+    t = _capi.Tree(lib, pts, insert=False)
+    try:
+        cuts = [0, 1, 2, 5, 40, 41, 300, 301, 1500, 1501, 1502, 6000]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            t.insert(pts[a:b], mode=1 if (b - a) > 1 else 0)
+        assert t.check_delaunay()[0]
+        assert np.array_equal(t.edges(), O.ExactDelaunay(pts).edges())
+    finally:
+        t.close()
+
+
 def case_batch(lib, O, dim, sizes, seed0=1000):
     sets = [pointgen.uniform(n, dim, seed0 + s) for s, n in enumerate(sizes)]
     off = np.zeros(len(sets) + 1, dtype=np.int64)

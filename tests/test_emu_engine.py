@@ -21,6 +21,11 @@ def test_emu_tiny_inputs(emu_lib, oracle, dim):
 
 
 @pytest.mark.parametrize("dim", [2, 3])
+def test_emu_awkward_sizes_and_many_small_inserts(emu_lib, oracle, dim):
+    ec.case_awkward_sizes(emu_lib, oracle, dim)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
 def test_emu_incremental_insert(emu_lib, oracle, dim):
     ec.case_incremental(emu_lib, oracle, dim, 700, 5000)
 

@@ -26,6 +26,11 @@ def test_gpu_tiny_inputs(gpu_lib, oracle, dim):
 
 
 @pytest.mark.parametrize("dim", [2, 3])
+def test_gpu_awkward_sizes_and_many_small_inserts(gpu_lib, oracle, dim):
+    ec.case_awkward_sizes(gpu_lib, oracle, dim)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
 def test_gpu_incremental_insert(gpu_lib, oracle, dim):
     # examples/parallel_insert.rs shape at 1/10 scale: 10k "sequential" + 100k "parallel"
     ec.case_incremental(gpu_lib, oracle, dim, 10_000, 100_000)
