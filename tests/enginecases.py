@@ -74,6 +74,41 @@ def case_awkward_sizes(lib, O, dim):
         t.close()
 
 
+def case_edge_wedge_ties(lib, O):
+    """3D edge list: the simplex whose wedge at the edge contains q = p_lo + dir emits the edge.  With dir chosen as the difference
+    of two vertices of the mesh, q falls exactly ON faces and ON edge lines of real simplices: the tie rules (lower simplex id
+    across the face / pivot around the edge) must still emit every edge exactly once.  Also the pivot-only path (the default:
+    the wedge test is a recorded alternative, parity-green but no faster on the B200)."""
+    # coordinates on a 2^-20 grid: differences and sums of points are exact, so q = p_lo + (p_b - p_a) IS a vertex / on an edge line
+    pts = np.random.default_rng(21).integers(0, 1 << 20, size=(3000, 3)).astype(np.float64) / float(1 << 20)
+    want = O.ExactDelaunay(pts).edges()
+    dirs = [(0.0, 0.0, 0.0)]
+    rng = np.random.default_rng(3)
+    for _ in range(6):
+        a, b = want[rng.integers(len(want))]
+        dirs.append(tuple(pts[b] - pts[a]))
+        dirs.append(tuple(pts[a] - pts[b]))
+    dirs.append((1.0, 0.0, 0.0))
+    try:
+        for wedge in (1, 0):
+            lib.vor_set_option(b"edge_wedge", float(wedge))
+            for d in (dirs if wedge else dirs[:1]):
+                for k, nm in enumerate((b"edge_dir_x", b"edge_dir_y", b"edge_dir_z")):
+                    lib.vor_set_option(nm, float(d[k]))
+                t = _capi.Tree(lib, pts)
+                try:
+                    z0 = t.stats()["exact_zero"]
+                    assert np.array_equal(t.edges(), want), ("edge list differs", wedge, d)
+                    if wedge and d != dirs[0] and d != dirs[-1]:
+                        assert t.stats()["exact_zero"] > z0, "the direction was meant to provoke exact ties in the wedge test"
+                finally:
+                    t.close()
+    finally:
+        lib.vor_set_option(b"edge_wedge", 0.0)      # the default: pivots
+        for nm in (b"edge_dir_x", b"edge_dir_y", b"edge_dir_z"):
+            lib.vor_set_option(nm, 0.0)
+
+
 def case_batch(lib, O, dim, sizes, seed0=1000):
     sets = [pointgen.uniform(n, dim, seed0 + s) for s, n in enumerate(sizes)]
     off = np.zeros(len(sets) + 1, dtype=np.int64)

@@ -25,6 +25,10 @@ def test_emu_awkward_sizes_and_many_small_inserts(emu_lib, oracle, dim):
     ec.case_awkward_sizes(emu_lib, oracle, dim)
 
 
+def test_emu_edge_wedge_ties(emu_lib, oracle):
+    ec.case_edge_wedge_ties(emu_lib, oracle)
+
+
 @pytest.mark.parametrize("dim", [2, 3])
 def test_emu_incremental_insert(emu_lib, oracle, dim):
     ec.case_incremental(emu_lib, oracle, dim, 700, 5000)

@@ -30,6 +30,10 @@ def test_gpu_awkward_sizes_and_many_small_inserts(gpu_lib, oracle, dim):
     ec.case_awkward_sizes(gpu_lib, oracle, dim)
 
 
+def test_gpu_edge_wedge_ties(gpu_lib, oracle):
+    ec.case_edge_wedge_ties(gpu_lib, oracle)
+
+
 @pytest.mark.parametrize("dim", [2, 3])
 def test_gpu_incremental_insert(gpu_lib, oracle, dim):
     # examples/parallel_insert.rs shape at 1/10 scale: 10k "sequential" + 100k "parallel"

@@ -2,4 +2,3 @@
 cd "$(dirname "$0")/.."
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-100
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-VOR_VERBOSE=1 python tools/e2e_breakdown.py 2>&1 | grep -E "edges:|iter" | tail -5

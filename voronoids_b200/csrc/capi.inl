@@ -90,6 +90,10 @@ int vor_set_option(const char *name, double value) {
     else if (n == "commit_smem") g_opts.commit_smem = (int)value;
     else if (n == "split_exact") g_opts.split_exact = (int)value;
     else if (n == "mid_twin") g_opts.mid_twin = (int)value;
+    else if (n == "edge_wedge") g_opts.edge_wedge = (int)value;
+    else if (n == "edge_dir_x") g_opts.edge_dir[0] = value;
+    else if (n == "edge_dir_y") g_opts.edge_dir[1] = value;
+    else if (n == "edge_dir_z") g_opts.edge_dir[2] = value;
     else if (n == "tet_factor") g_opts.tet_factor = value;
     else if (n == "compact_frac") g_opts.compact_frac = value;
     else if (n == "stage_log") g_opts.stage_log = (int)value;

@@ -96,6 +96,71 @@ template <int D> VOR_HD void edges_body(const EdgeArgs<D> &A, int t) {
     }
 }
 
+// ---- 3D count pass WITHOUT walking around the edges (option edge_wedge).  The simplices around an interior edge (a, b) tile the
+// full angle with their dihedral wedges, so exactly one of them contains the point q = p_lo + dir (p_lo = the endpoint with the
+// lower vertex id, dir a fixed generic direction: q is the SAME double point for every simplex around the edge): that simplex owns
+// the edge.  "q inside the wedge of t" = the orientation of t with the opposite vertex replaced by q is positive for both faces of
+// t through the edge (exact predicate: FP64 filter -> double-double -> integers).  Four gathered vertices and 12 orientations per
+// simplex instead of ~2.5 dependent record gathers per edge.  Ties (measure zero, but the rule must be consistent; provoked in
+// tests/enginecases.py::case_edge_wedge_ties): q exactly on ONE of the two faces -- that face is the boundary between t and its
+// neighbour across it, the lower simplex id takes the edge; q on BOTH planes, i.e. on the line through a and b -- every simplex
+// around the edge sees that, all fall back to the pivot rule.  A kernel body of its own with the slots resolved at compile time:
+// inside edges_body the point array and the predicates cost the replay pass and the pivot path their registers (count pass
+// 15.8 -> 25.3 ms, replay 7 -> 21 ms when it was tried there).
+struct EdgeWedgeArgs {
+    Mesh<3> m;
+    const int *inputIdx;
+    int *deg;
+    unsigned char *mask;
+    double dx, dy, dz;
+};
+template <int K> VOR_HD const double4 &pick4(const double4 &p0, const double4 &p1, const double4 &p2, const double4 &p3) {
+    if constexpr (K == 0) return p0; else if constexpr (K == 1) return p1; else if constexpr (K == 2) return p2; else return p3;
+}
+template <int K> VOR_HD int slot4(const int4 &v) {
+    if constexpr (K == 0) return v.x; else if constexpr (K == 1) return v.y; else if constexpr (K == 2) return v.z; else return v.w;
+}
+template <int SA, int SB> VOR_HD bool wedge_own(PredCtx &cx, const EdgeWedgeArgs &A, int t, const int4 &tv, const double4 &p0, const double4 &p1,
+                                                const double4 &p2, const double4 &p3) {
+    constexpr int SC = (SA != 0 && SB != 0) ? 0 : ((SA != 1 && SB != 1) ? 1 : 2);
+    constexpr int SD = 6 - SA - SB - SC;
+    const bool aLo = slot4<SA>(tv) < slot4<SB>(tv);
+    const double4 &pa = pick4<SA>(p0, p1, p2, p3), &pb = pick4<SB>(p0, p1, p2, p3);
+    double4 q;
+    q.x = (aLo ? pa.x : pb.x) + A.dx; q.y = (aLo ? pa.y : pb.y) + A.dy; q.z = (aLo ? pa.z : pb.z) + A.dz; q.w = 0.0;
+    const int o1 = orient3d(cx, SC == 0 ? q : p0, SC == 1 ? q : p1, SC == 2 ? q : p2, SC == 3 ? q : p3);
+    if (o1 < 0) return false;
+    const int o2 = orient3d(cx, SD == 0 ? q : p0, SD == 1 ? q : p1, SD == 2 ? q : p2, SD == 3 ? q : p3);
+    if (o2 < 0) return false;
+    if (o1 > 0 && o2 > 0) return true;
+    if (o1 == 0 && o2 == 0) return edge_owner3(A.m, t, tv, SA, SB);
+    const int code = get4(TN(A.m, t), o1 == 0 ? SC : SD);     // the neighbour across the face q lies on
+    return code >= 0 && t < (code >> 2);
+}
+VOR_HD void edges_wedge_body(const EdgeWedgeArgs &A, int t) {
+    const Mesh<3> &m = A.m;
+    if (!simplex_live(m, t)) return;
+    const int4 tv = TV(m, t);
+    const int ns = m.nsuper;
+    const bool r0 = tv.x >= ns, r1 = tv.y >= ns, r2 = tv.z >= ns, r3 = tv.w >= ns;
+    if ((int)r0 + (int)r1 + (int)r2 + (int)r3 < 2) { A.mask[t] = 0; return; }   // no edge of two real vertices
+    const Geo<3>::Verts vv = Geo<3>::load(m, tv);
+    PredCtx cx{m.cnt};
+    unsigned own = 0;
+    auto emit = [&](int va, int vb) {
+        const int ia = A.inputIdx[va], ib = A.inputIdx[vb];
+        atomic_add_i(&A.deg[ia < ib ? ia : ib], 1);
+    };
+    // edge numbering of edges_body: (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+    if (r0 && r1 && wedge_own<0, 1>(cx, A, t, tv, vv.p0, vv.p1, vv.p2, vv.p3)) { own |= 1u; emit(tv.x, tv.y); }
+    if (r0 && r2 && wedge_own<0, 2>(cx, A, t, tv, vv.p0, vv.p1, vv.p2, vv.p3)) { own |= 2u; emit(tv.x, tv.z); }
+    if (r0 && r3 && wedge_own<0, 3>(cx, A, t, tv, vv.p0, vv.p1, vv.p2, vv.p3)) { own |= 4u; emit(tv.x, tv.w); }
+    if (r1 && r2 && wedge_own<1, 2>(cx, A, t, tv, vv.p0, vv.p1, vv.p2, vv.p3)) { own |= 8u; emit(tv.y, tv.z); }
+    if (r1 && r3 && wedge_own<1, 3>(cx, A, t, tv, vv.p0, vv.p1, vv.p2, vv.p3)) { own |= 16u; emit(tv.y, tv.w); }
+    if (r2 && r3 && wedge_own<2, 3>(cx, A, t, tv, vv.p0, vv.p1, vv.p2, vv.p3)) { own |= 32u; emit(tv.z, tv.w); }
+    A.mask[t] = (unsigned char)own;
+}
+
 struct RowSortArgs { const int *off; uint32_t *hi; uint32_t *out; int n; };
 // sort each CSR row (insertion sort: rows hold ~8 entries in 3D, ~3 in 2D) and write (lo,hi) pairs
 VOR_HD void row_sort_body(const RowSortArgs &A, int r) {
