@@ -84,6 +84,11 @@ class ClockSampler:
     def start(self):
         if os.environ.get("VOR_NO_SAMPLER"):   # diagnostics only: a bench line without clocks is not a valid bench line
             return
+        # NVML in this process (the library nvidia-smi itself reads these fields from): a poll is two or three cheap calls.  A
+        # separate nvidia-smi process polling every 200 ms was measured to stretch the timed steps of the 10M-point run from
+        # 107-111 ms to 110-126 ms (tools/r2_exp23.sh, profiles/r2_bench_u3_10m.json history); it stays as the fallback.
+        if not os.environ.get("VOR_SAMPLER_SMI") and self._start_nvml():
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -92,18 +97,56 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _start_nvml(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                u = str(torch.cuda.get_device_properties(self.index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + u) if not u.startswith("GPU-") else u)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)     # fail here, not in the thread
+            self.nvml_stop = threading.Event()
+
+            def loop():
+                while not self.nvml_stop.is_set():
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        r = int(reasons_fn(h))
+                        act = lambda bit: "Active" if (r & bit) else "Not Active"
+                        # same column order as the nvidia-smi query: sm, max, power, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+                        self.rows.append([str(sm), str(mx), "0", act(0x8), act(0x40), act(0x20), act(0x4)])
+                    except Exception:
+                        pass
+                    self.nvml_stop.wait(0.2)
+            self.th = threading.Thread(target=loop, daemon=True)
+            self.th.start()
+            self.source = "nvml (in-process, every 200 ms)"
+            return True
+        except Exception:
+            return False
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if not self.proc:
+        if getattr(self, "nvml_stop", None) is not None:
+            self.nvml_stop.set()
+            self.th.join(timeout=2)
+        elif not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = self.rows[self.first:] or self.rows[-1:]    # a timed region shorter than the 200 ms sampling period: the last sample before it
@@ -117,7 +160,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": getattr(self, "source", "nvidia-smi -lms 200")}
 
 
 def bench_config(desc, n, dim, world):
